@@ -1,0 +1,65 @@
+"""Seeded synthetic inputs shared by `make_golden.py` (which runs the unmodified reference on them)
+and by the tests (which run the oracle / the CUDA path on the same arrays).
+
+numpy's legacy `RandomState` streams are stable across platforms and numpy versions, so only the
+reference's *outputs* are stored in the .npz fixtures; the inputs are regenerated from the seed.
+Statistics follow SURVEY.md §8(d): fmap ~ N(0, 1.45^2); coords = coords_grid + N(0, 5^2).
+"""
+import numpy as np
+
+F = np.float32
+FH, FW = 16, 32          # 1/8-resolution feature map of a 128x256 ERP image (smallest sane size)
+C = 256
+
+
+def fmaps(seed, B=1, c=C, h=FH, w=FW, n=4):
+    rs = np.random.RandomState(seed)
+    return [(rs.randn(B, c, h, w) * 1.45).astype(F) for _ in range(n)]
+
+
+def base_grid(B, h, w):
+    ys, xs = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    return np.repeat(np.stack([xs, ys], 0).astype(F)[None], B, 0)
+
+
+def coords(seed, B=1, h=FH, w=FW, sigma=5.0):
+    rs = np.random.RandomState(seed)
+    return (base_grid(B, h, w) + rs.randn(B, 2, h, w) * sigma).astype(F)
+
+
+def flow(seed, B=2, h=FH, w=FW, sigma=5.0):
+    rs = np.random.RandomState(seed)
+    return (rs.randn(B, 2, h, w) * sigma).astype(F)
+
+
+def edge_coords(h=FH, w=FW):
+    """Edge vectors of SURVEY.md §4 laid out as a [1,2,h,w] coords tensor: x exactly W-1, W-0.5,
+    tiny negative (-1e-8 % W == W), far outside, and y in {-1,-0.5,H-1,H-0.5,H}; rest = identity."""
+    c = base_grid(1, h, w)
+    xs = [w - 1.0, w - 0.5, -1e-8, -0.25, w + 3.75, -w - 2.5, 0.0, 1e-4, w - 1e-3, 2 * w + 0.5, 5.5, 7.25]
+    ys = [-1.0, -0.5, h - 1.0, h - 0.5, float(h), -3.5, 0.0, h + 6.0, 0.5, 3.75, h - 1.5, 1e-3]
+    k = 0
+    for yv in ys:
+        for xv in xs:
+            i, j = divmod(k, w)
+            if i >= h:
+                break
+            c[0, 0, i, j] = xv
+            c[0, 1, i, j] = yv
+            k += 1
+    return c.astype(F)
+
+
+def image(seed, B=1, H=64, W=128, ch=6):
+    rs = np.random.RandomState(seed)
+    return (rs.rand(B, ch, H, W) * 2 - 1).astype(F)
+
+
+def small_sampler_case(seed=11):
+    rs = np.random.RandomState(seed)
+    img = rs.randn(2, 5, 6, 8).astype(F)
+    pts = np.stack([rs.uniform(-3, 11, size=(2, 7, 9)), rs.uniform(-2, 8, size=(2, 7, 9))], -1).astype(F)
+    # plant exact edge values
+    pts[0, 0, :6, 0] = [7.0, 7.5, -1e-8, 8.0, 0.0, -0.5]
+    pts[0, 1, :6, 1] = [-1.0, -0.5, 5.0, 5.5, 6.0, 0.0]
+    return img, pts
