@@ -1,0 +1,189 @@
+/* priorcorr.h — C ABI of libpriorcorr.so, the B200 (sm_100a) implementation of PriOr-RAFT's
+ * correlation hot path.
+ *
+ * The reference (longliangLiu/PriOr-Flow) has no native/FFI layer: its hot path is eager PyTorch
+ * and its one native seam, `alt_cuda_corr.forward` (PriOr-RAFT/core/corr.py:86), is not shipped.
+ * The drop-in boundary is therefore the set of Python names `core/prior_raft.py` resolves
+ * (SURVEY.md §8b); this header is the C ABI *underneath* those names.  Every entry point cites the
+ * reference function it replaces (paths relative to PriOr-RAFT/).  INTEGRATION.md shows the
+ * ctypes binding and the reference-side patch a maintainer would add.
+ *
+ * Conventions
+ *   - plain C: raw device pointers + int shapes, no torch / CUDA types in any signature
+ *     (`stream` is a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - all tensors are dense fp32, row-major, in the layouts written next to each field;
+ *   - the library never allocates, frees or retains device memory: outputs and workspaces are
+ *     allocated by the caller (PyTorch's caching allocator in the host layer);
+ *   - every call is asynchronous on `stream`, re-entrant, and honours the current device;
+ *   - return 0 on success; non-zero => pf_last_error() (thread-local) describes the failure.
+ *     No abort(), no exceptions across the ABI, no implicit device synchronisation.
+ */
+#ifndef PRIORCORR_H_
+#define PRIORCORR_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_ABI_VERSION 1
+#define PF_MAX_LEVELS 4
+
+/* `tensor / python_scalar`: IEEE division on CPU, multiply by fp32 reciprocal in ATen's CUDA
+ * kernels.  Coordinates are bit-exact against the chosen flavour of the reference. */
+enum pf_div_mode { PF_DIV_IEEE = 0, PF_DIV_ATEN_CUDA = 1 };
+
+/* Arithmetic of the all-pairs contraction (core/prior_raft.py:73, fp32 cuBLAS in the reference). */
+enum pf_volume_mode {
+  PF_VOL_FP32_3XF16 = 0, /* tcgen05 kind::f16 on an fp16 hi/lo split of both operands, 3 MMAs   */
+                         /* (hi*hi + hi*lo + lo*hi): fp32-equivalent, the default               */
+  PF_VOL_F16 = 1,        /* tcgen05 kind::f16, hi*hi only: TF32-class accuracy, separately      */
+                         /* toleranced fast mode                                                */
+  PF_VOL_FP32_SIMT = 2   /* CUDA-core FFMA tiles: exact fp32 products, the on-device checker    */
+};
+
+int pf_abi_version(void);
+const char *pf_last_error(void);
+/* Compile-time facts of the build: "sm_100a;tcgen05;tma;abi=1". */
+const char *pf_build_info(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a) all-pairs correlation volume + average-pool pyramid, fused.
+ * Replaces PriOr_RAFT.corr (core/prior_raft.py:69-75; twin CorrBlock.corr core/corr.py:53-61) and
+ * DCCL.build_pyramid (core/corr.py:99-111; twin CorrBlock.__init__ core/corr.py:22-28).
+ *   level0[b, n, m] = sum_c fmap1[b,c,n] * fmap2[b,c,m] / sqrt(C)      n = y1*w+x1, m = y2*w+x2
+ *   level(l+1) = avg_pool2d(level l, 2, stride 2) over the (y2,x2) axes
+ * The tcgen05 modes need w % 32 == 0, h % 8 == 0, (h*w) % 128 == 0 and C % 32 == 0.
+ */
+typedef struct pf_volume_args {
+  int batch, channels, h, w;     /* fmaps are [B, C, h, w]                                         */
+  int num_levels;                /* 1..PF_MAX_LEVELS                                               */
+  int mode;                      /* enum pf_volume_mode                                            */
+  const float *fmap1;            /* [B, C, h, w]                                                   */
+  const float *fmap2;            /* [B, C, h, w]                                                   */
+  float *level[PF_MAX_LEVELS];   /* out: level l is [B*h*w, h>>l, w>>l]                            */
+  void *workspace;               /* tcgen05 modes: pf_volume_workspace_bytes() bytes, 1 KiB aligned */
+  long long workspace_bytes;
+} pf_volume_args;
+long long pf_volume_workspace_bytes(int batch, int channels, int h, int w, int mode);
+int pf_volume_build(const pf_volume_args *args, void *stream);
+
+/* One 2x2 average-pool level on its own (core/corr.py:108): in [planes, H, W] -> out [planes, H/2, W/2]. */
+int pf_avg_pool2x2(const float *in, float *out, long long planes, int H, int W, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (b) dual-cost pyramid lookup.
+ * Replaces DCCL.__call__ (core/corr.py:113-144) — own-view 9x9 window lookup, the window mapped
+ * through the level-0 rotation grid into the other view's volume, and the img_rotate of that map —
+ * and, with other[] == NULL and cyclic == 0, CorrBlock.__call__ (core/corr.py:30-51).
+ * Output channel = level*(2r+1)^2 + a*(2r+1) + b sampling (x + a - r, y + b - r)  (x-major window).
+ */
+typedef struct pf_lookup_args {
+  int batch, h, w;                     /* query grid: coords are [B, 2, h, w] (x, y)              */
+  int h2, w2;                          /* level-0 plane size of the pyramids                      */
+  int radius, num_levels;
+  int cyclic;                          /* 1: cycle_bilinear_sampler (x % W); 0: bilinear_sampler  */
+  int div_mode;                        /* enum pf_div_mode                                        */
+  const float *coords;                 /* [B, 2, h, w]                                            */
+  const float *own[PF_MAX_LEVELS];     /* [B*h*w, h2>>l, w2>>l]                                   */
+  const float *other[PF_MAX_LEVELS];   /* same shapes; all NULL => single-view lookup             */
+  const float *grid_w2c;               /* [B, 2, h, w] `sample_grid_*_W2C_8x`                     */
+  const float *grid_c2w;               /* [B, 2, h, w] `sample_grid_*_8x`                         */
+  long long grid_batch_stride;         /* elements between batches of the grids (0 = shared)      */
+  float *out_own;                      /* [B, L*(2r+1)^2, h, w]                                   */
+  float *out_other;                    /* [B, L*(2r+1)^2, h, w]                                   */
+  float *scratch;                      /* [B, L*(2r+1)^2, h, w] pre-rotation map (caller-owned)   */
+  float *dbg_own_xy;                   /* optional [B*h*w, L, (2r+1)^2, 2] unnormalised (ix, iy)  */
+  float *dbg_other_xy;                 /* optional, same shape, orthogonal branch                 */
+} pf_lookup_args;
+int pf_lookup_dual(const pf_lookup_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (c) on-the-fly lookup: same outputs as pf_lookup_dual but straight from the feature maps, no
+ * volume in memory.  Takes the place of the unshipped `alt_cuda_corr.forward(fmap1, fmap2_l,
+ * coords_l, r)` behind AlternateCorrBlock (core/corr.py:64-91) and keeps its operand convention:
+ * CHANNELS-LAST feature maps (core/corr.py:82-83).  Level l correlates fmap1 with avg-pooled fmap2
+ * (pooling is linear, so this equals the lookup into the pooled volume up to fp rounding).
+ */
+typedef struct pf_onthefly_args {
+  int batch, channels, h, w;                 /* channels % 128 == 0, <= 512                       */
+  int radius, num_levels;
+  int cyclic, div_mode;
+  const float *coords;                       /* [B, 2, h, w]                                      */
+  const float *fmap1_own;                    /* [B, h, w, C] query features of this view          */
+  const float *fmap2_own[PF_MAX_LEVELS];     /* [B, h>>l, w>>l, C] pooled target features         */
+  const float *fmap1_other;                  /* other view (NULL => single view)                  */
+  const float *fmap2_other[PF_MAX_LEVELS];
+  const float *grid_w2c, *grid_c2w;
+  long long grid_batch_stride;
+  float *out_own, *out_other, *scratch;      /* as in pf_lookup_args                              */
+} pf_onthefly_args;
+int pf_lookup_onthefly(const pf_onthefly_args *args, void *stream);
+/* Pooled feature pyramid helper: fmap [planes, H, W] -> levels[1..L-1] (levels[0] is ignored). */
+int pf_fmap_pyramid(const float *fmap, float *const *levels, int num_levels, long long planes, int H, int W,
+                    void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (d) ERP <-> orthogonal-view geometry.
+ */
+/* generate_samplegrid (core/utils/projection_prim_ortho.py:432-443 with :10-20, :397-411, :77-89,
+ * :247-261, :51-74, :413-429): out[b,0/1,n,m] = source pixel (m', n') of (m, n) under rotation R. */
+int pf_samplegrid(float *out /*[B,2,H,W]*/, int batch, int H, int W, const float *R_host /*9 floats, row-major, HOST*/,
+                  int div_mode, void *stream);
+
+/* Bilinear remap, zeros padding, align_corners=True, optional x % W.  Replaces
+ * cycle_bilinear_sampler (core/utils/utils.py:78-95), bilinear_sampler (:61-75) and img_rotate
+ * (core/utils/projection_prim_ortho.py:507-514 via :119-135).  Coordinates are read as
+ * x = coords[b*batch_stride + p*pixel_stride], y = coords[... + xy_stride], p = yo*Wo + xo, which covers
+ * both [B,Ho,Wo,2] (pixel_stride 2, xy_stride 1) and [B,2,Ho,Wo] (pixel_stride 1, xy_stride Ho*Wo). */
+typedef struct pf_remap_args {
+  int batch, channels, H, W;       /* src [B, C, H, W]                                              */
+  int Ho, Wo;                      /* out [B, C, Ho, Wo]                                            */
+  int cyclic, div_mode;
+  const float *src;
+  const float *coords;
+  long long coord_batch_stride, coord_pixel_stride, coord_xy_stride;
+  float *out;
+} pf_remap_args;
+int pf_remap(const pf_remap_args *args, void *stream);
+
+/* flo_rotate with both grids given (core/utils/projection_prim_ortho.py:531-546, flow2endpoint
+ * :200-218, u_clip :234-244, cycle_grid_sample / adjust_sample_m core/utils/my_cycle_sample.py:6-97),
+ * one fused launch.  flow, out: [B,2,H,W]; grids [B,2,H,W] with the given batch stride. */
+int pf_flo_rotate(const float *flow, const float *grid_w2c, const float *grid_c2w, long long grid_batch_stride,
+                  float *out, int batch, int H, int W, void *stream);
+
+/* Feature warp + group-wise correlation (core/prior_raft.py:173-174 + :77-83), fused:
+ * out[b,g,p] = mean_{c in group g} fmap1[b,c,p] * cycle_bilinear_sampler(fmap2, coords)[b,c,p]. */
+int pf_warp_groupcorr(const float *fmap1, const float *fmap2, const float *coords /*[B,2,h,w]*/, float *out /*[B,G,h,w]*/,
+                      int batch, int channels, int h, int w, int groups, int div_mode, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (e) backward kernels (training; coords and grids carry no gradient, core/prior_raft.py:171,176).
+ */
+/* d(lookup)/d(pyramids): scatter-add of grad_own / grad_other into zero-initialised (or running)
+ * gradient pyramids with the forward's coordinates.  grad_other is first pushed through the
+ * adjoint of img_rotate into `scratch`. */
+typedef struct pf_lookup_bwd_args {
+  pf_lookup_args fwd;                     /* same geometry/coords/grids as forward; own/other unused  */
+  const float *grad_own, *grad_other;     /* [B, L*(2r+1)^2, h, w]                                     */
+  float *dgrad_own[PF_MAX_LEVELS];        /* += ; [B*h*w, h2>>l, w2>>l]                                */
+  float *dgrad_other[PF_MAX_LEVELS];
+} pf_lookup_bwd_args;
+int pf_lookup_dual_bwd(const pf_lookup_bwd_args *args, void *stream);
+
+/* Adjoint of pf_remap w.r.t. src: dsrc += scatter(dout) (dsrc must be initialised by the caller). */
+int pf_remap_bwd(const pf_remap_args *args, const float *dout, float *dsrc, void *stream);
+
+/* Adjoint of the pyramid: folds the level gradients into level 0 in place,
+ * g0[n,y,x] += g1[n,y/2,x/2]/4 + g2[n,y/4,x/4]/16 + g3[n,y/8,x/8]/64. */
+int pf_pyramid_fold_bwd(float *const *glevel, int num_levels, long long planes, int H, int W, void *stream);
+
+/* Adjoint of pf_warp_groupcorr w.r.t. fmap1 and fmap2 (dfmap2 accumulated with atomics, caller zeroes). */
+int pf_warp_groupcorr_bwd(const float *fmap1, const float *fmap2, const float *coords, const float *dout,
+                          float *dfmap1, float *dfmap2, int batch, int channels, int h, int w, int groups,
+                          int div_mode, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRIORCORR_H_ */

@@ -1,0 +1,558 @@
+// (a) All-pairs correlation volume with the avg-pool pyramid fused into the epilogue —
+// tcgen05 / TMEM / TMA kernel for sm_100a.
+// Replaces PriOr_RAFT.corr (PriOr-RAFT/core/prior_raft.py:69-75: fp32 cuBLAS GEMM + a separate
+// full-volume `div` pass) and DCCL.build_pyramid (core/corr.py:99-111: three avg_pool2d passes).
+//
+// Arithmetic.  tcgen05 has no fp32-input kind, so the fp32 contraction is done as an fp16 hi/lo
+// split of both operands (x*s = hi + lo, s a power of two chosen from the tensor's absmax so that
+// hi never overflows fp16) and three kind::f16 MMAs into one fp32 TMEM accumulator:
+//     A*B ~= hi_a*hi_b + hi_a*lo_b + lo_a*hi_b          (dropped term lo*lo ~ 2^-22 relative)
+// fp16 carries the same 11 significant bits as TF32, so this is the "3xTF32" scheme at twice the
+// tensor rate and half the operand bytes.  PF_VOL_F16 issues the first product only.
+//
+// Structure (persistent, one CTA per SM, 6 warps):
+//   prep kernels : absmax -> power-of-two scale ; transpose [C, N] fp32 -> K-major [N, C] fp16 hi/lo
+//   warp 0       : TMA producer.  A tile = 128 query rows x 64 k (2-D map); B tile = 8x32 *patch*
+//                  of target pixels x 64 k (4-D map over [B, h, w, C]) — the N-tile is a spatial
+//                  patch so that the 2x2 / 4x4 / 8x8 pools are tile-local.  SWIZZLE_128B, 96 KB/stage.
+//   warp 1       : TMEM alloc (512 cols = 2 accumulator stages of 128 x 256 fp32) and the single
+//                  thread issuing tcgen05.mma (M128 N256 K16), tcgen05.commit -> mbarriers.
+//   warps 2..5   : epilogue.  tcgen05.ld (thread = query row, registers = one patch row of 32
+//                  targets), scale by 1/(sqrt(C) s_a s_b), level 0 staged in swizzled smem and
+//                  written with TMA (3-D map over [B*N, h, w]); levels 1..3 pooled in registers
+//                  in avg_pool2d's order ((a+b)+c+d)/4 from the rounded finer level and stored
+//                  as 64/32/16-byte row segments.
+// HBM traffic is the compulsory 1.33 x N^2 x 4 B of pyramid writes; the operands (fp16 planes,
+// 4 x 4 MiB per view at 512x1024) stay in L2.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "pf_common.cuh"
+
+namespace pf {
+
+constexpr int BM = 128;                 // query rows per tile == TMEM lanes
+constexpr int BN = 256;                 // target pixels per tile
+constexpr int PATCH_H = 8, PATCH_W = 32;
+constexpr int BK = 64;                  // fp16 per k-block: 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_PLANE = BM * BK * 2;    // 16 KiB
+constexpr int B_PLANE = BN * BK * 2;    // 32 KiB
+constexpr int OUT_STAGE = BM * 32 * 4;  // 16 KiB: 128 rows x one 32-float patch row
+constexpr int kOutStages = 2;
+constexpr int kTcThreads = 192;
+constexpr int kAccCols = BN;            // fp32 accumulator columns per stage
+constexpr uint32_t kTmemCols = 512;
+
+template <bool kSplit>
+struct Cfg {
+  static constexpr int kStages = kSplit ? 2 : 4;
+  static constexpr int kStageBytes = kSplit ? 2 * (A_PLANE + B_PLANE) : (A_PLANE + B_PLANE);
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutStages * OUT_STAGE + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must become a launch failure, not a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, 16-B units
+  d |= (uint64_t)1 << 16;                        // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // layout: SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, M = 128, N = 256.
+constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// Power-of-two scale that maps absmax into [2^13, 2^14): hi = fp16(x*s) cannot overflow.
+__device__ __forceinline__ float split_scale(uint32_t amax_bits) {
+  int e = (int)((amax_bits >> 23) & 0xff) - 127;  // floor(log2(absmax))
+  if ((amax_bits & 0x7fffffffu) == 0u) e = 13;    // all-zero tensor: s = 1
+  int se = 13 - e;
+  se = se < -100 ? -100 : (se > 100 ? 100 : se);
+  return __uint_as_float((uint32_t)(se + 127) << 23);
+}
+
+// ---------------------------------------------------------------------------------- prep kernels
+__global__ void absmax_kernel(const float *__restrict__ x, long long n, uint32_t *__restrict__ out) {
+  uint32_t m = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = max(m, __float_as_uint(fabsf(x[i])));
+  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// [B, C, N] fp32  ->  K-major [B, N, C] fp16 hi (and lo) planes.  64(c) x 32(n) tile through smem.
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float *__restrict__ x, __half *__restrict__ hi,
+                                                              __half *__restrict__ lo, int C, int N,
+                                                              const uint32_t *__restrict__ amax_bits, int want_lo) {
+  __shared__ float t[64][33];
+  const float s = split_scale(*amax_bits);
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float *xb = x + (long long)b * C * N;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + ty + i * 8;
+    t[ty + i * 8][tx] = (c < C && n0 + tx < N) ? xb[(long long)c * N + n0 + tx] * s : 0.f;
+  }
+  __syncthreads();
+  // each thread writes one half2 (channels 2*tx, 2*tx+1) for rows ty, ty+8, ...
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty + i * 8;
+    const int c = c0 + 2 * tx;
+    if (n < N && c + 1 < C) {
+      const float v0 = t[2 * tx][ty + i * 8], v1 = t[2 * tx + 1][ty + i * 8];
+      const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+      const long long o = ((long long)b * N + n) * C + c;
+      *reinterpret_cast<__half2 *>(hi + o) = __halves2half2(h0, h1);
+      if (want_lo)
+        *reinterpret_cast<__half2 *>(lo + o) =
+            __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- main kernel
+struct TcParams {
+  int B, C, N, h, w;
+  int num_levels;
+  int tiles_m, patches_x, patches_y;  // per batch
+  long long total_tiles;
+  float inv_sqrt_c;
+  const uint32_t *amax_bits;  // [2]: fmap1, fmap2
+  float *lvl1, *lvl2, *lvl3;
+};
+
+template <bool kSplit>
+__global__ void __launch_bounds__(kTcThreads, 1)
+volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                 const __grid_constant__ CUtensorMap map_out, const TcParams p) {
+  using C_ = Cfg<kSplit>;
+  constexpr int kStages = C_::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *out_stage = smem + kStages * C_::kStageBytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(out_stage + kOutStages * OUT_STAGE);
+  // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base address
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kStages);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * kStages), bar_tempty = smem_u32(bars + 2 * kStages + 2);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = p.C / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================= TMA producer (one thread)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int per_b = p.tiles_m * p.patches_x * p.patches_y;
+        const int b = (int)(tile / per_b);
+        int r = (int)(tile - (long long)b * per_b);
+        const int mt = r / (p.patches_x * p.patches_y);
+        r -= mt * p.patches_x * p.patches_y;
+        const int py = r / p.patches_x, px = r - py * p.patches_x;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_arrive_expect_tx(full, (uint32_t)C_::kStageBytes);
+          const uint32_t sbase = smem_u32(smem + stage * C_::kStageBytes);
+          const int row = b * p.N + mt * BM;
+          tma_load_2d(sbase, &map_a_hi, full, kb * BK, row);
+          tma_load_4d(sbase + A_PLANE, &map_b_hi, full, kb * BK, px * PATCH_W, py * PATCH_H, b);
+          if (kSplit) {
+            tma_load_2d(sbase + A_PLANE + B_PLANE, &map_a_lo, full, kb * BK, row);
+            tma_load_4d(sbase + 2 * A_PLANE + B_PLANE, &map_b_lo, full, kb * BK, px * PATCH_W, py * PATCH_H, b);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer (one thread)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, acc = 0, acc_phase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kAccCols;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(smem + stage * C_::kStageBytes);
+          const uint64_t a_hi = make_smem_desc(sbase), b_hi = make_smem_desc(sbase + A_PLANE);
+          const uint64_t a_lo = make_smem_desc(sbase + A_PLANE + B_PLANE);
+          const uint64_t b_lo = make_smem_desc(sbase + 2 * A_PLANE + B_PLANE);
+          if (kSplit) {
+            // small cross terms first, then the leading product
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, kIdesc, 1u);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, kIdesc, 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================================================================= epilogue (4 warps)
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;   // query row inside the tile
+    const bool leader = threadIdx.x == 64;
+    const float scale = p.inv_sqrt_c / (split_scale(p.amax_bits[0]) * split_scale(p.amax_bits[1]));
+    uint32_t acc = 0, acc_phase = 0;
+    const int w1 = p.w >> 1, h1 = p.h >> 1, w2 = p.w >> 2, h2 = p.h >> 2, w3 = p.w >> 3, h3 = p.h >> 3;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int per_b = p.tiles_m * p.patches_x * p.patches_y;
+      const int b = (int)(tile / per_b);
+      int r = (int)(tile - (long long)b * per_b);
+      const int mt = r / (p.patches_x * p.patches_y);
+      r -= mt * p.patches_x * p.patches_y;
+      const int py = r / p.patches_x, px = r - py * p.patches_x;
+      const long long qrow = (long long)b * p.N + mt * BM + row;  // global query index (plane index)
+
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * kAccCols + ((uint32_t)(quarter * 32) << 16);
+      float l1_prev[16], l2_prev[8];
+#pragma unroll
+      for (int cp = 0; cp < PATCH_H / 2; ++cp) {
+        uint32_t ua[32], ub[32];
+        tmem_ld32(taddr + (2 * cp) * 32, ua);
+        tmem_ld32(taddr + (2 * cp + 1) * 32, ub);
+        tmem_ld_wait();
+        if (cp == PATCH_H / 2 - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+        float va[32], vb[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          va[j] = __uint_as_float(ua[j]) * scale;
+          vb[j] = __uint_as_float(ub[j]) * scale;
+        }
+        // ---- level 0: two patch rows through swizzled staging + TMA store
+        if (leader) tma_store_wait_read0();
+        epi_bar_sync();
+        {
+          uint8_t *r0 = out_stage + row * 128, *r1 = r0 + OUT_STAGE;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int off = ((j ^ (row & 7)) << 4);
+            *reinterpret_cast<float4 *>(r0 + off) = make_float4(va[4 * j], va[4 * j + 1], va[4 * j + 2], va[4 * j + 3]);
+            *reinterpret_cast<float4 *>(r1 + off) = make_float4(vb[4 * j], vb[4 * j + 1], vb[4 * j + 2], vb[4 * j + 3]);
+          }
+        }
+        fence_async_smem();
+        epi_bar_sync();
+        if (leader) {
+          const int y = py * PATCH_H + 2 * cp, rowg = b * p.N + mt * BM;
+          tma_store_3d(&map_out, smem_u32(out_stage), px * PATCH_W, y, rowg);
+          tma_store_3d(&map_out, smem_u32(out_stage + OUT_STAGE), px * PATCH_W, y + 1, rowg);
+          tma_store_commit();
+        }
+        // ---- level 1: ((a + b) + c + d) / 4 over the 2x2 window, row-major order (avg_pool2d)
+        if (p.num_levels > 1) {
+          float l1[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            l1[j] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(va[2 * j], va[2 * j + 1]), vb[2 * j]), vb[2 * j + 1]), 0.25f);
+          float *d1 = p.lvl1 + (qrow * h1 + (py * (PATCH_H / 2) + cp)) * w1 + px * (PATCH_W / 2);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4 *>(d1 + 4 * j) = make_float4(l1[4 * j], l1[4 * j + 1], l1[4 * j + 2], l1[4 * j + 3]);
+          if (p.num_levels > 2) {
+            if (cp & 1) {
+              float l2[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                l2[j] = __fmul_rn(
+                    __fadd_rn(__fadd_rn(__fadd_rn(l1_prev[2 * j], l1_prev[2 * j + 1]), l1[2 * j]), l1[2 * j + 1]), 0.25f);
+              float *d2 = p.lvl2 + (qrow * h2 + (py * (PATCH_H / 4) + (cp >> 1))) * w2 + px * (PATCH_W / 4);
+              *reinterpret_cast<float4 *>(d2) = make_float4(l2[0], l2[1], l2[2], l2[3]);
+              *reinterpret_cast<float4 *>(d2 + 4) = make_float4(l2[4], l2[5], l2[6], l2[7]);
+              if (p.num_levels > 3) {
+                if (cp == 3) {
+                  float l3[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    l3[j] = __fmul_rn(
+                        __fadd_rn(__fadd_rn(__fadd_rn(l2_prev[2 * j], l2_prev[2 * j + 1]), l2[2 * j]), l2[2 * j + 1]),
+                        0.25f);
+                  float *d3 = p.lvl3 + (qrow * h3 + py) * w3 + px * (PATCH_W / 8);
+                  *reinterpret_cast<float4 *>(d3) = make_float4(l3[0], l3[1], l3[2], l3[3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) l2_prev[j] = l2[j];
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) l1_prev[j] = l1[j];
+            }
+          }
+        }
+      }
+      if ((acc ^= 1) == 0) acc_phase ^= 1;
+    }
+    if (leader) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int encode(CUtensorMap *m, CUtensorMapDataType dt, int rank, void *base, const cuuint64_t *dims,
+                  const cuuint64_t *strides_bytes, const cuuint32_t *box, const char *what) {
+  EncodeTiledFn fn = get_encode_fn();
+  PF_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, dt, (cuuint32_t)rank, base, dims, strides_bytes, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return 0;
+}
+
+static long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+long long volume_tc_workspace_bytes(int batch, int channels, int h, int w, int mode) {
+  const long long plane = align_up((long long)batch * h * w * channels * 2, 1024);
+  const int planes = (mode == PF_VOL_FP32_3XF16) ? 4 : 2;
+  return 1024 + planes * plane;
+}
+
+int volume_build_tc(const pf_volume_args *a, cudaStream_t st) {
+  const int B = a->batch, C = a->channels, h = a->h, w = a->w, N = h * w;
+  const bool split = a->mode == PF_VOL_FP32_3XF16;
+  PF_REQUIRE(w % PATCH_W == 0 && h % PATCH_H == 0 && N % BM == 0 && C % BK == 0,
+             "pf_volume_build(tcgen05): need w %% 32 == 0, h %% 8 == 0, h*w %% 128 == 0, C %% 64 == 0 (got %dx%d, C=%d); "
+             "use PF_VOL_FP32_SIMT for other shapes",
+             h, w, C);
+  PF_REQUIRE((long long)B * N < (1LL << 31), "pf_volume_build: batch*h*w too large");
+  const long long need = volume_tc_workspace_bytes(B, C, h, w, a->mode);
+  PF_REQUIRE(a->workspace && a->workspace_bytes >= need, "pf_volume_build: workspace too small (%lld < %lld bytes)",
+             a->workspace_bytes, need);
+  PF_REQUIRE(((uintptr_t)a->workspace & 1023) == 0, "pf_volume_build: workspace must be 1 KiB aligned");
+  for (int l = 0; l < a->num_levels; ++l)
+    PF_REQUIRE(((uintptr_t)a->level[l] & 15) == 0, "pf_volume_build: level[%d] must be 16-byte aligned", l);
+
+  uint8_t *ws = reinterpret_cast<uint8_t *>(a->workspace);
+  uint32_t *amax = reinterpret_cast<uint32_t *>(ws);
+  const long long plane = align_up((long long)B * N * C * 2, 1024);
+  __half *a_hi = reinterpret_cast<__half *>(ws + 1024);
+  __half *b_hi = reinterpret_cast<__half *>(ws + 1024 + plane);
+  __half *a_lo = split ? reinterpret_cast<__half *>(ws + 1024 + 2 * plane) : a_hi;
+  __half *b_lo = split ? reinterpret_cast<__half *>(ws + 1024 + 3 * plane) : b_hi;
+
+  // ---- operand preparation
+  if (cudaMemsetAsync(amax, 0, 2 * sizeof(uint32_t), st) != cudaSuccess) return check_launch("pf_volume_build(memset)");
+  const long long total = (long long)B * C * N;
+  const unsigned rblocks = (unsigned)((total + 1023) / 1024 < 1184 ? (total + 1023) / 1024 : 1184);
+  absmax_kernel<<<rblocks, 256, 0, st>>>(a->fmap1, total, amax);
+  absmax_kernel<<<rblocks, 256, 0, st>>>(a->fmap2, total, amax + 1);
+  dim3 tgrid(ceil_div(N, 32), ceil_div(C, 64), B);
+  split_transpose_kernel<<<tgrid, 256, 0, st>>>(a->fmap1, a_hi, a_lo, C, N, amax, split ? 1 : 0);
+  split_transpose_kernel<<<tgrid, 256, 0, st>>>(a->fmap2, b_hi, b_lo, C, N, amax + 1, split ? 1 : 0);
+  if (int e = check_launch("pf_volume_build(prep)")) return e;
+
+  // ---- tensor maps
+  CUtensorMap m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)B * N};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {BK, BM};
+    if (int e = encode(&m_a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a_hi, dims, strides, box, "A.hi")) return e;
+    if (int e = encode(&m_a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a_lo, dims, strides, box, "A.lo")) return e;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)w * C * 2, (cuuint64_t)h * w * C * 2};
+    cuuint32_t box[4] = {BK, PATCH_W, PATCH_H, 1};
+    if (int e = encode(&m_b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, b_hi, dims, strides, box, "B.hi")) return e;
+    if (int e = encode(&m_b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, b_lo, dims, strides, box, "B.lo")) return e;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B * N};
+    cuuint64_t strides[2] = {(cuuint64_t)w * 4, (cuuint64_t)h * w * 4};
+    cuuint32_t box[3] = {32, 1, BM};
+    if (int e = encode(&m_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a->level[0], dims, strides, box, "level0")) return e;
+  }
+
+  TcParams p;
+  p.B = B;
+  p.C = C;
+  p.N = N;
+  p.h = h;
+  p.w = w;
+  p.num_levels = a->num_levels;
+  p.tiles_m = N / BM;
+  p.patches_x = w / PATCH_W;
+  p.patches_y = h / PATCH_H;
+  p.total_tiles = (long long)B * p.tiles_m * p.patches_x * p.patches_y;
+  p.inv_sqrt_c = 1.0f / sqrtf((float)C);
+  p.amax_bits = amax;
+  p.lvl1 = a->num_levels > 1 ? a->level[1] : nullptr;
+  p.lvl2 = a->num_levels > 2 ? a->level[2] : nullptr;
+  p.lvl3 = a->num_levels > 3 ? a->level[3] : nullptr;
+
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)(p.total_tiles < sms ? p.total_tiles : sms);
+  if (split) {
+    auto kern = volume_tc_kernel<true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::kSmemBytes);
+    kern<<<grid, kTcThreads, Cfg<true>::kSmemBytes, st>>>(m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, p);
+  } else {
+    auto kern = volume_tc_kernel<false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::kSmemBytes);
+    kern<<<grid, kTcThreads, Cfg<false>::kSmemBytes, st>>>(m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, p);
+  }
+  return check_launch("pf_volume_build(tcgen05)");
+}
+
+}  // namespace pf

@@ -1,0 +1,513 @@
+"""Tensor-level entry points: thin PyTorch wrappers over the C ABI (include/priorcorr.h).
+
+PyTorch is plumbing here — device memory (caching allocator), the current stream, autograd
+bookkeeping.  Every function validates its inputs, allocates the outputs, and makes exactly one
+C-ABI call on `torch.cuda.current_stream()`.  There is no fallback path: a CPU tensor or a missing
+library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+_state = {"div_mode": _lib.DIV_ATEN_CUDA, "volume_mode": "fp32"}
+
+
+def set_div_mode(mode: str) -> None:
+    """"aten_cuda" (default): `tensor / scalar` multiplies by the fp32 reciprocal, as ATen's CUDA kernels
+    do — bit-exact coordinates against the reference running on a GPU.  "ieee": true division —
+    bit-exact against the reference running on CPU (what tests/golden holds)."""
+    _state["div_mode"] = {"aten_cuda": _lib.DIV_ATEN_CUDA, "ieee": _lib.DIV_IEEE}[mode]
+
+
+def get_div_mode() -> str:
+    return "aten_cuda" if _state["div_mode"] == _lib.DIV_ATEN_CUDA else "ieee"
+
+
+def set_volume_mode(mode: str) -> None:
+    if mode not in _lib.VOLUME_MODES:
+        raise ValueError(f"volume mode must be one of {sorted(_lib.VOLUME_MODES)}")
+    _state["volume_mode"] = mode
+
+
+def get_volume_mode() -> str:
+    return _state["volume_mode"]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, name: str, ndim: Optional[int] = None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise _lib.PriorCorrError(f"{name} is on {t.device}: prior_flow_b200 runs on CUDA (sm_100a) only, "
+                                  "there is no CPU fallback")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (got {t.dtype})")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name} must have {ndim} dims (got shape {tuple(t.shape)})")
+    return t
+
+
+def _grid_arg(g: torch.Tensor, name: str, B: int, H: int, W: int) -> Tuple[torch.Tensor, int]:
+    """Sample grids are [B,2,H,W]; batch-invariant grids may be passed expanded (batch stride 0)."""
+    _chk(g, name, 4)
+    if g.shape[1:] != (2, H, W) or g.shape[0] not in (1, B):
+        raise ValueError(f"{name} must be [{B} or 1, 2, {H}, {W}] (got {tuple(g.shape)})")
+    if g.stride()[1:] != (H * W, W, 1):
+        g = g.contiguous()
+    bs = 0 if (g.shape[0] == 1 or g.stride(0) == 0) else g.stride(0)
+    return g, bs
+
+
+# ------------------------------------------------------------------------------------------ (a)
+def volume_pyramid(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int = 4,
+                   mode: Optional[str] = None) -> List[torch.Tensor]:
+    """Fused corr volume + avg-pool pyramid (core/prior_raft.py:69-75 + core/corr.py:99-111).
+    Returns [level_l of shape [B*h*w, 1, h>>l, w>>l]] — the reference's pyramid layout."""
+    lib = _lib.load()
+    _chk(fmap1, "fmap1", 4), _chk(fmap2, "fmap2", 4)
+    if fmap1.shape != fmap2.shape:
+        raise ValueError("fmap1 and fmap2 must have the same shape")
+    fmap1, fmap2 = fmap1.contiguous(), fmap2.contiguous()
+    B, Cn, h, w = fmap1.shape
+    mode_id = _lib.VOLUME_MODES[mode or _state["volume_mode"]]
+    with torch.cuda.device(fmap1.device):
+        levels = [torch.empty((B * h * w, 1, h >> l, w >> l), device=fmap1.device, dtype=torch.float32)
+                  for l in range(num_levels)]
+        ws_bytes = lib.pf_volume_workspace_bytes(B, Cn, h, w, mode_id)
+        ws = torch.empty((max(ws_bytes, 1) + 1024,), device=fmap1.device, dtype=torch.uint8)
+        ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+        a = _lib.VolumeArgs(B, Cn, h, w, num_levels, mode_id, fmap1.data_ptr(), fmap2.data_ptr(),
+                            _lib.level_ptrs(levels), ws_ptr, ws_bytes)
+        _lib.check(lib.pf_volume_build(C.byref(a), _stream()), "pf_volume_build")
+        ws.record_stream(torch.cuda.current_stream())
+    return levels
+
+
+def avg_pool2x2(x: torch.Tensor) -> torch.Tensor:
+    """F.avg_pool2d(x, 2, stride=2) for [..., H, W] (core/corr.py:108)."""
+    lib = _lib.load()
+    _chk(x, "x")
+    x = x.contiguous()
+    H, W = x.shape[-2:]
+    out = torch.empty(x.shape[:-2] + (H // 2, W // 2), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.pf_avg_pool2x2(x.data_ptr(), out.data_ptr(), x.numel() // (H * W), H, W, _stream()),
+                   "pf_avg_pool2x2")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ (b)
+def lookup(coords: torch.Tensor, pyr_own: Sequence[torch.Tensor], pyr_other: Optional[Sequence[torch.Tensor]] = None,
+           grid_w2c: Optional[torch.Tensor] = None, grid_c2w: Optional[torch.Tensor] = None, radius: int = 4,
+           cyclic: bool = True, debug: bool = False):
+    """Pyramid lookup.  With `pyr_other` + grids: DCCL.__call__ (core/corr.py:113-144) -> (own, other);
+    without: the single-view lookup of CorrBlock.__call__ (core/corr.py:30-51) -> own.
+    debug=True additionally returns the unnormalised sample coordinates [B*h*w, L, k*k, 2] per branch."""
+    lib = _lib.load()
+    _chk(coords, "coords", 4)
+    coords = coords.contiguous()
+    B, two, h, w = coords.shape
+    if two != 2:
+        raise ValueError("coords must be [B,2,h,w]")
+    L = len(pyr_own)
+    own = [_chk(t, f"pyr_own[{l}]").contiguous() for l, t in enumerate(pyr_own)]
+    h2, w2 = own[0].shape[-2:]
+    for l, t in enumerate(own):
+        if t.numel() != B * h * w * (h2 >> l) * (w2 >> l):
+            raise ValueError(f"pyr_own[{l}] has {t.numel()} elements, expected [{B * h * w},1,{h2 >> l},{w2 >> l}]")
+    dual = pyr_other is not None
+    K2 = (2 * radius + 1) ** 2
+    dev = coords.device
+    with torch.cuda.device(dev):
+        out_own = torch.empty((B, L * K2, h, w), device=dev, dtype=torch.float32)
+        a = _lib.LookupArgs()
+        a.batch, a.h, a.w, a.h2, a.w2 = B, h, w, h2, w2
+        a.radius, a.num_levels, a.cyclic, a.div_mode = radius, L, int(cyclic), _state["div_mode"]
+        a.coords = coords.data_ptr()
+        a.own = _lib.level_ptrs(own)
+        a.out_own = out_own.data_ptr()
+        out_other = None
+        if dual:
+            other = [_chk(t, f"pyr_other[{l}]").contiguous() for l, t in enumerate(pyr_other)]
+            if len(other) != L or any(o.shape != t.shape for o, t in zip(other, own)):
+                raise ValueError("pyr_other must match pyr_own level by level")
+            gw, bs_w = _grid_arg(grid_w2c, "grid_w2c", B, h, w)
+            gc, bs_c = _grid_arg(grid_c2w, "grid_c2w", B, h, w)
+            if bs_w != bs_c:
+                gw, gc = gw.expand(B, 2, h, w).contiguous(), gc.expand(B, 2, h, w).contiguous()
+                bs_w = gw.stride(0)
+            out_other = torch.empty_like(out_own)
+            scratch = torch.empty_like(out_own)
+            a.other = _lib.level_ptrs(other)
+            a.grid_w2c, a.grid_c2w, a.grid_batch_stride = gw.data_ptr(), gc.data_ptr(), bs_w
+            a.out_other, a.scratch = out_other.data_ptr(), scratch.data_ptr()
+        dbg = None
+        if debug:
+            dbg = [torch.full((B * h * w, L, K2, 2), float("nan"), device=dev) for _ in range(2 if dual else 1)]
+            a.dbg_own_xy = dbg[0].data_ptr()
+            if dual:
+                a.dbg_other_xy = dbg[1].data_ptr()
+        _lib.check(lib.pf_lookup_dual(C.byref(a), _stream()), "pf_lookup_dual")
+    res = (out_own, out_other) if dual else out_own
+    if debug:
+        return res, dbg
+    return res
+
+
+# ------------------------------------------------------------------------------------------ (d)
+def samplegrid(size, R: torch.Tensor, device=None) -> torch.Tensor:
+    """generate_samplegrid (core/utils/projection_prim_ortho.py:432-443) -> [B,2,H,W]."""
+    lib = _lib.load()
+    B, _, H, W = (int(s) for s in size)
+    Rh = R.detach().to("cpu", torch.float32).contiguous().reshape(-1)
+    if Rh.numel() != 9:
+        raise ValueError("R must be 3x3")
+    dev = torch.device(device) if device is not None else (R.device if R.is_cuda else torch.device("cuda"))
+    if dev.type != "cuda":
+        raise _lib.PriorCorrError("samplegrid: CUDA device required (no CPU fallback)")
+    Rc = (C.c_float * 9)(*Rh.tolist())
+    with torch.cuda.device(dev):
+        out = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
+        _lib.check(lib.pf_samplegrid(out.data_ptr(), B, H, W, Rc, _state["div_mode"], _stream()), "pf_samplegrid")
+    return out
+
+
+def remap(src: torch.Tensor, coords: torch.Tensor, coords_layout: str, cyclic: bool = True) -> torch.Tensor:
+    """Bilinear remap with the reference wrappers' semantics (zeros padding, align_corners=True, optional
+    x % W).  coords_layout "BHW2": [B,Ho,Wo,2] (the samplers of core/utils/utils.py:61-95);
+    "B2HW": [B,2,Ho,Wo] sample grid (img_rotate, core/utils/projection_prim_ortho.py:507-514)."""
+    lib = _lib.load()
+    _chk(src, "src", 4), _chk(coords, "coords", 4)
+    src = src.contiguous()
+    B, Cn, H, W = src.shape
+    if coords_layout == "BHW2":
+        coords = coords.contiguous()
+        Bc, Ho, Wo, two = coords.shape
+        cbs, cps, cxs = Ho * Wo * 2, 2, 1
+    elif coords_layout == "B2HW":
+        Bc, two, Ho, Wo = coords.shape
+        coords, cbs = _grid_arg(coords, "coords", B, Ho, Wo)
+        cps, cxs = 1, Ho * Wo
+    else:
+        raise ValueError(coords_layout)
+    if two != 2 or Bc not in (1, B):
+        raise ValueError(f"bad coords shape {tuple(coords.shape)} for layout {coords_layout}")
+    if coords_layout == "BHW2" and Bc == 1 and B > 1:
+        cbs = 0
+    with torch.cuda.device(src.device):
+        out = torch.empty((B, Cn, Ho, Wo), device=src.device, dtype=torch.float32)
+        a = _lib.RemapArgs(B, Cn, H, W, Ho, Wo, int(cyclic), _state["div_mode"], src.data_ptr(), coords.data_ptr(),
+                           cbs, cps, cxs, out.data_ptr())
+        _lib.check(lib.pf_remap(C.byref(a), _stream()), "pf_remap")
+    return out
+
+
+def flo_rotate(flow: torch.Tensor, grid_w2c: torch.Tensor, grid_c2w: torch.Tensor) -> torch.Tensor:
+    """flo_rotate with both sample grids given (core/utils/projection_prim_ortho.py:531-546)."""
+    lib = _lib.load()
+    _chk(flow, "flow", 4)
+    flow = flow.contiguous()
+    B, two, H, W = flow.shape
+    if two != 2:
+        raise ValueError("flow must be [B,2,H,W]")
+    gw, bs_w = _grid_arg(grid_w2c, "grid_w2c", B, H, W)
+    gc, bs_c = _grid_arg(grid_c2w, "grid_c2w", B, H, W)
+    if bs_w != bs_c:
+        gw, gc = gw.expand(B, 2, H, W).contiguous(), gc.expand(B, 2, H, W).contiguous()
+        bs_w = gw.stride(0)
+    with torch.cuda.device(flow.device):
+        out = torch.empty_like(flow)
+        _lib.check(lib.pf_flo_rotate(flow.data_ptr(), gw.data_ptr(), gc.data_ptr(), bs_w, out.data_ptr(), B, H, W,
+                                     _stream()), "pf_flo_rotate")
+    return out
+
+
+def warp_groupcorr(fmap1: torch.Tensor, fmap2: torch.Tensor, coords: torch.Tensor, groups: int = 4) -> torch.Tensor:
+    """groupwise_corr(fmap1, cycle_bilinear_sampler(fmap2, coords)) fused (core/prior_raft.py:173-174,77-83).
+    coords [B,2,h,w] -> [B,groups,h,w]."""
+    lib = _lib.load()
+    _chk(fmap1, "fmap1", 4), _chk(fmap2, "fmap2", 4), _chk(coords, "coords", 4)
+    fmap1, fmap2, coords = fmap1.contiguous(), fmap2.contiguous(), coords.contiguous()
+    B, Cn, h, w = fmap1.shape
+    if fmap2.shape != fmap1.shape or coords.shape != (B, 2, h, w):
+        raise ValueError("shape mismatch in warp_groupcorr")
+    with torch.cuda.device(fmap1.device):
+        out = torch.empty((B, groups, h, w), device=fmap1.device, dtype=torch.float32)
+        _lib.check(lib.pf_warp_groupcorr(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr(), out.data_ptr(), B, Cn,
+                                         h, w, groups, _state["div_mode"], _stream()), "pf_warp_groupcorr")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ (c)
+def channels_last_pyramid(fmap: torch.Tensor, num_levels: int) -> List[torch.Tensor]:
+    """[B,C,h,w] -> [level l as [B, h>>l, w>>l, C]] (avg-pooled, channels-last): the operand layout of
+    the on-the-fly lookup (what AlternateCorrBlock feeds alt_cuda_corr, core/corr.py:66-72,82-83)."""
+    _chk(fmap, "fmap", 4)
+    levels, cur = [], fmap.contiguous()
+    for l in range(num_levels):
+        if l:
+            cur = avg_pool2x2(cur)
+        levels.append(cur.permute(0, 2, 3, 1).contiguous())
+    return levels
+
+
+def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence[torch.Tensor],
+                    f1_other: Optional[torch.Tensor] = None, f2_other: Optional[Sequence[torch.Tensor]] = None,
+                    grid_w2c: Optional[torch.Tensor] = None, grid_c2w: Optional[torch.Tensor] = None,
+                    radius: int = 4, cyclic: bool = True):
+    """Volume-free lookup.  f1_* are channels-last [B,h,w,C]; f2_* are channels_last_pyramid() lists."""
+    lib = _lib.load()
+    _chk(coords, "coords", 4)
+    coords = coords.contiguous()
+    B, _, h, w = coords.shape
+    L = len(f2_own)
+    Cn = f1_own.shape[-1]
+    _chk(f1_own, "f1_own", 4)
+    if tuple(f1_own.shape) != (B, h, w, Cn) or not f1_own.is_contiguous():
+        raise ValueError("f1_own must be contiguous channels-last [B,h,w,C]")
+    for l, t in enumerate(f2_own):
+        if tuple(t.shape) != (B, h >> l, w >> l, Cn) or not t.is_contiguous():
+            raise ValueError(f"f2_own[{l}] must be contiguous [B,{h >> l},{w >> l},{Cn}]")
+    dual = f1_other is not None
+    K2 = (2 * radius + 1) ** 2
+    dev = coords.device
+    with torch.cuda.device(dev):
+        out_own = torch.empty((B, L * K2, h, w), device=dev, dtype=torch.float32)
+        a = _lib.OnTheFlyArgs()
+        a.batch, a.channels, a.h, a.w = B, Cn, h, w
+        a.radius, a.num_levels, a.cyclic, a.div_mode = radius, L, int(cyclic), _state["div_mode"]
+        a.coords, a.fmap1_own, a.fmap2_own = coords.data_ptr(), f1_own.data_ptr(), _lib.level_ptrs(list(f2_own))
+        a.out_own = out_own.data_ptr()
+        out_other = None
+        if dual:
+            gw, bs_w = _grid_arg(grid_w2c, "grid_w2c", B, h, w)
+            gc, bs_c = _grid_arg(grid_c2w, "grid_c2w", B, h, w)
+            if bs_w != bs_c:
+                gw, gc = gw.expand(B, 2, h, w).contiguous(), gc.expand(B, 2, h, w).contiguous()
+                bs_w = gw.stride(0)
+            out_other, scratch = torch.empty_like(out_own), torch.empty_like(out_own)
+            a.fmap1_other, a.fmap2_other = f1_other.data_ptr(), _lib.level_ptrs(list(f2_other))
+            a.grid_w2c, a.grid_c2w, a.grid_batch_stride = gw.data_ptr(), gc.data_ptr(), bs_w
+            a.out_other, a.scratch = out_other.data_ptr(), scratch.data_ptr()
+        _lib.check(lib.pf_lookup_onthefly(C.byref(a), _stream()), "pf_lookup_onthefly")
+    return (out_own, out_other) if dual else out_own
+
+
+# ------------------------------------------------------------------------------------------ (e)
+def lookup_backward(coords, grad_own, grad_other, level_shapes, grid_w2c=None, grid_c2w=None, radius=4, cyclic=True,
+                    into_own=None, into_other=None):
+    """Adjoint of `lookup` w.r.t. the pyramids.  Returns (d_own levels, d_other levels); with `into_*` given the
+    gradients are accumulated (+=) into those tensors instead of fresh zero tensors."""
+    lib = _lib.load()
+    coords = _chk(coords, "coords", 4).contiguous()
+    B, _, h, w = coords.shape
+    L = len(level_shapes)
+    h2, w2 = level_shapes[0][-2:]
+    dual = grad_other is not None
+    K2 = (2 * radius + 1) ** 2
+    dev = coords.device
+    with torch.cuda.device(dev):
+        d_own = into_own if into_own is not None else [torch.zeros(s, device=dev, dtype=torch.float32) for s in level_shapes]
+        d_other = None
+        ba = _lib.LookupBwdArgs()
+        a = ba.fwd
+        a.batch, a.h, a.w, a.h2, a.w2 = B, h, w, h2, w2
+        a.radius, a.num_levels, a.cyclic, a.div_mode = radius, L, int(cyclic), _state["div_mode"]
+        a.coords = coords.data_ptr()
+        grad_own = _chk(grad_own, "grad_own", 4).contiguous()
+        ba.grad_own = grad_own.data_ptr()
+        ba.dgrad_own = _lib.level_ptrs(d_own)
+        if dual:
+            d_other = into_other if into_other is not None else [torch.zeros(s, device=dev, dtype=torch.float32)
+                                                                 for s in level_shapes]
+            grad_other = _chk(grad_other, "grad_other", 4).contiguous()
+            gw, bs_w = _grid_arg(grid_w2c, "grid_w2c", B, h, w)
+            gc, bs_c = _grid_arg(grid_c2w, "grid_c2w", B, h, w)
+            if bs_w != bs_c:
+                gw, gc = gw.expand(B, 2, h, w).contiguous(), gc.expand(B, 2, h, w).contiguous()
+                bs_w = gw.stride(0)
+            scratch = torch.empty((B, L * K2, h, w), device=dev, dtype=torch.float32)
+            a.grid_w2c, a.grid_c2w, a.grid_batch_stride, a.scratch = gw.data_ptr(), gc.data_ptr(), bs_w, scratch.data_ptr()
+            ba.grad_other = grad_other.data_ptr()
+            ba.dgrad_other = _lib.level_ptrs(d_other)
+        _lib.check(lib.pf_lookup_dual_bwd(C.byref(ba), _stream()), "pf_lookup_dual_bwd")
+    return d_own, d_other
+
+
+def remap_backward(dout: torch.Tensor, coords: torch.Tensor, coords_layout: str, src_shape, cyclic: bool = True):
+    """Adjoint of `remap` w.r.t. src."""
+    lib = _lib.load()
+    dout = _chk(dout, "dout", 4).contiguous()
+    B, Cn, H, W = src_shape
+    Ho, Wo = dout.shape[-2:]
+    if coords_layout == "BHW2":
+        coords = _chk(coords, "coords", 4).contiguous()
+        cbs, cps, cxs = (0 if coords.shape[0] == 1 and B > 1 else Ho * Wo * 2), 2, 1
+    else:
+        coords, cbs = _grid_arg(coords, "coords", B, Ho, Wo)
+        cps, cxs = 1, Ho * Wo
+    with torch.cuda.device(dout.device):
+        dsrc = torch.zeros((B, Cn, H, W), device=dout.device, dtype=torch.float32)
+        a = _lib.RemapArgs(B, Cn, H, W, Ho, Wo, int(cyclic), _state["div_mode"], None, coords.data_ptr(), cbs, cps, cxs, None)
+        _lib.check(lib.pf_remap_bwd(C.byref(a), dout.data_ptr(), dsrc.data_ptr(), _stream()), "pf_remap_bwd")
+    return dsrc
+
+
+def pyramid_fold_backward(grads: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Folds level gradients [planes,1,H>>l,W>>l] into level 0 (in place on grads[0]) and returns it."""
+    lib = _lib.load()
+    g0 = grads[0]
+    H, W = g0.shape[-2:]
+    planes = g0.numel() // (H * W)
+    ptrs = (C.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+    with torch.cuda.device(g0.device):
+        _lib.check(lib.pf_pyramid_fold_bwd(ptrs, len(grads), planes, H, W, _stream()), "pf_pyramid_fold_bwd")
+    return g0
+
+
+def warp_groupcorr_backward(fmap1, fmap2, coords, dout, groups: int = 4):
+    lib = _lib.load()
+    fmap1, fmap2, coords, dout = (t.contiguous() for t in (fmap1, fmap2, coords, dout))
+    B, Cn, h, w = fmap1.shape
+    with torch.cuda.device(fmap1.device):
+        df1 = torch.empty_like(fmap1)
+        df2 = torch.zeros_like(fmap2)
+        _lib.check(lib.pf_warp_groupcorr_bwd(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr(), dout.data_ptr(),
+                                             df1.data_ptr(), df2.data_ptr(), B, Cn, h, w, groups, _state["div_mode"],
+                                             _stream()), "pf_warp_groupcorr_bwd")
+    return df1, df2
+
+
+# ------------------------------------------------------------------------------------------ autograd
+class _VolumePyramidFn(torch.autograd.Function):
+    """volume_pyramid with gradients to the feature maps: fold the level gradients into level 0
+    (pf_pyramid_fold_bwd), then dF1 = dV F2^T / sqrt(C) and dF2 = dV^T F1 / sqrt(C) — two plain library
+    GEMMs (cuBLAS through torch.matmul)."""
+
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, num_levels, mode):
+        ctx.save_for_backward(fmap1, fmap2)
+        ctx.num_levels = num_levels
+        return tuple(volume_pyramid(fmap1, fmap2, num_levels, mode))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        fmap1, fmap2 = ctx.saved_tensors
+        B, Cn, h, w = fmap1.shape
+        N = h * w
+        gs = []
+        for l, g in enumerate(grads):
+            if g is None:
+                gs.append(torch.zeros((B * N, 1, h >> l, w >> l), device=fmap1.device))
+            else:
+                gs.append(g.contiguous().clone() if l == 0 else g.contiguous())  # level 0 is folded into in place
+        g0 = pyramid_fold_backward(gs).view(B, N, N)
+        scale = 1.0 / (Cn ** 0.5)
+        f1 = fmap1.reshape(B, Cn, N)
+        f2 = fmap2.reshape(B, Cn, N)
+        d1 = torch.matmul(f2, g0.transpose(1, 2)).mul_(scale).view_as(fmap1) if ctx.needs_input_grad[0] else None
+        d2 = torch.matmul(f1, g0).mul_(scale).view_as(fmap2) if ctx.needs_input_grad[1] else None
+        return d1, d2, None, None
+
+
+def volume_pyramid_autograd(fmap1, fmap2, num_levels=4, mode=None):
+    if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+        return list(_VolumePyramidFn.apply(fmap1, fmap2, num_levels, mode))
+    return volume_pyramid(fmap1, fmap2, num_levels, mode)
+
+
+class _DualLookupFn(torch.autograd.Function):
+    """DCCL lookup with gradients to both pyramids (coords and grids carry none, prior_raft.py:171,176)."""
+
+    @staticmethod
+    def forward(ctx, coords, grid_w2c, grid_c2w, radius, num_levels, *levels):
+        own, other = levels[:num_levels], levels[num_levels:]
+        out_own, out_other = lookup(coords, own, other, grid_w2c, grid_c2w, radius)
+        ctx.save_for_backward(coords, grid_w2c, grid_c2w)
+        ctx.meta = (radius, num_levels, [tuple(t.shape) for t in own])
+        return out_own, out_other
+
+    @staticmethod
+    def backward(ctx, g_own, g_other):
+        coords, grid_w2c, grid_c2w = ctx.saved_tensors
+        radius, L, shapes = ctx.meta
+        if g_own is None:
+            g_own = torch.zeros((coords.shape[0], L * (2 * radius + 1) ** 2) + tuple(coords.shape[2:]), device=coords.device)
+        if g_other is None:
+            g_other = torch.zeros_like(g_own)
+        d_own, d_other = lookup_backward(coords, g_own, g_other, shapes, grid_w2c, grid_c2w, radius)
+        return (None, None, None, None, None, *d_own, *d_other)
+
+
+class _SingleLookupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coords, radius, cyclic, *levels):
+        out = lookup(coords, levels, None, None, None, radius, cyclic)
+        ctx.save_for_backward(coords)
+        ctx.meta = (radius, cyclic, [tuple(t.shape) for t in levels])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (coords,) = ctx.saved_tensors
+        radius, cyclic, shapes = ctx.meta
+        d_own, _ = lookup_backward(coords, g, None, shapes, None, None, radius, cyclic)
+        return (None, None, None, *d_own)
+
+
+def lookup_autograd(coords, pyr_own, pyr_other=None, grid_w2c=None, grid_c2w=None, radius=4, cyclic=True):
+    needs = torch.is_grad_enabled() and any(t.requires_grad for t in list(pyr_own) + list(pyr_other or []))
+    if not needs:
+        return lookup(coords, pyr_own, pyr_other, grid_w2c, grid_c2w, radius, cyclic)
+    if pyr_other is None:
+        return _SingleLookupFn.apply(coords.detach(), radius, cyclic, *pyr_own)
+    return _DualLookupFn.apply(coords.detach(), grid_w2c.detach(), grid_c2w.detach(), radius, len(pyr_own), *pyr_own,
+                               *pyr_other)
+
+
+class _RemapFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, coords, layout, cyclic):
+        ctx.save_for_backward(coords)
+        ctx.meta = (layout, cyclic, tuple(src.shape))
+        return remap(src, coords, layout, cyclic)
+
+    @staticmethod
+    def backward(ctx, g):
+        (coords,) = ctx.saved_tensors
+        layout, cyclic, shape = ctx.meta
+        return remap_backward(g, coords, layout, shape, cyclic), None, None, None
+
+
+def remap_autograd(src, coords, layout, cyclic=True):
+    if torch.is_grad_enabled() and src.requires_grad:
+        return _RemapFn.apply(src, coords.detach(), layout, cyclic)
+    return remap(src, coords, layout, cyclic)
+
+
+class _WarpGroupCorrFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, coords, groups):
+        ctx.save_for_backward(fmap1, fmap2, coords)
+        ctx.groups = groups
+        return warp_groupcorr(fmap1, fmap2, coords, groups)
+
+    @staticmethod
+    def backward(ctx, g):
+        fmap1, fmap2, coords = ctx.saved_tensors
+        d1, d2 = warp_groupcorr_backward(fmap1, fmap2, coords, g, ctx.groups)
+        return d1, d2, None, None
+
+
+def warp_groupcorr_autograd(fmap1, fmap2, coords, groups=4):
+    if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+        return _WarpGroupCorrFn.apply(fmap1, fmap2, coords.detach(), groups)
+    return warp_groupcorr(fmap1, fmap2, coords, groups)

@@ -1,0 +1,111 @@
+"""Per-kernel timings of the hot path at BASELINE config 2 (512x1024 -> 64x128, C=256), CUDA events, L2 flushed
+between iterations.  Prints one JSON line per kernel with achieved GB/s (or TFLOP/s) against MEASURED_PEAKS.json.
+Usage (GPU box): python scripts/kbench.py [--iters 20] [--h 64 --w 128]"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from prior_flow_b200 import ops  # noqa: E402
+from oracle import torch_oracle as TO  # noqa: E402  (timed beside ours as the eager-PyTorch GPU bar)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return p["hbm_gbs"], p["bf16_tflops"], "measured"
+    except Exception:
+        return 6650.0, 1590.0, "fallback"
+
+
+def timeit(fn, iters, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--h", type=int, default=64)
+    ap.add_argument("--w", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--skip-torch", action="store_true")
+    a = ap.parse_args()
+    B, h, w, C = a.batch, a.h, a.w, 256
+    N = h * w
+    hbm, tflops, src = peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    fm = [torch.randn(B, C, h, w, device="cuda", generator=g) * 1.45 for _ in range(4)]
+    coords = TO.coords_grid(B, h, w, "cuda") + torch.randn(B, 2, h, w, device="cuda", generator=g) * 5
+    Ra, Rb = TO.rotation_matrix([0., 0., -np.pi / 2], device="cuda"), TO.rotation_matrix([0., 0., np.pi / 2], device="cuda")
+    gw = ops.samplegrid((1, 3, h, w), Ra.T.contiguous())
+    gc = ops.samplegrid((1, 3, h, w), Rb)
+    img = torch.rand(B, 6, 8 * h, 8 * w, device="cuda")
+    gfull = ops.samplegrid((1, 3, 8 * h, 8 * w), Ra)
+    rows = []
+
+    def rec(name, fn, bytes_=None, flops=None, torch_fn=None):
+        med, best = timeit(fn, a.iters, flush)
+        r = {"kernel": name, "ms_median": round(med, 4), "ms_best": round(best, 4)}
+        if bytes_:
+            r["GBps"] = round(bytes_ / med / 1e6, 1)
+            r["frac_hbm"] = round(bytes_ / med / 1e6 / hbm, 3)
+        if flops:
+            r["TFLOPs"] = round(flops / med / 1e9, 1)
+            r["frac_bf16_peak"] = round(flops / med / 1e9 / tflops, 3)
+        if torch_fn is not None and not a.skip_torch:
+            r["torch_eager_ms"] = round(timeit(torch_fn, max(3, a.iters // 4), flush)[0], 4)
+        r["peaks"] = src
+        rows.append(r)
+        print(json.dumps(r), flush=True)
+
+    pyr_bytes = sum(B * N * (h >> l) * (w >> l) * 4 for l in range(4))
+    vol_bytes = pyr_bytes + 2 * B * C * N * 4
+    vol_flops = 2.0 * B * N * N * C
+    for mode in ("fp32", "f16", "fp32_simt"):
+        rec(f"volume_pyramid[{mode}]", lambda m=mode: ops.volume_pyramid(fm[0], fm[1], 4, m), vol_bytes, vol_flops,
+            (lambda: TO.build_pyramid(TO.corr_volume(fm[0], fm[1]))) if mode == "fp32" else None)
+    pa, pb = ops.volume_pyramid(fm[0], fm[1], 4), ops.volume_pyramid(fm[2], fm[3], 4)
+    K2 = 81
+    look_bytes = B * N * 2 * 4 * 100 * 4 + 2 * B * N * 4 * K2 * 4 + 3 * B * 2 * N * 4
+    rec("lookup_dual", lambda: ops.lookup(coords, pa, pb, gw, gc, 4), look_bytes, None,
+        lambda: TO.dccl_lookup(coords, pa, pb, gw.expand(B, -1, -1, -1), gc.expand(B, -1, -1, -1), 4))
+    rec("lookup_single", lambda: ops.lookup(coords, pa, radius=4, cyclic=True), look_bytes // 2)
+    flow = coords - TO.coords_grid(B, h, w, "cuda")
+    rec("flo_rotate", lambda: ops.flo_rotate(flow, gw, gc), 4 * B * 2 * N * 4, None,
+        lambda: TO.flo_rotate(flow, gw.expand(B, -1, -1, -1), gc.expand(B, -1, -1, -1)))
+    rec("warp_groupcorr", lambda: ops.warp_groupcorr(fm[0], fm[1], coords, 4), 2 * B * C * N * 4 + B * 6 * N * 4, None,
+        lambda: TO.warp_groupcorr(fm[0], fm[1], coords, 4))
+    rec("img_rotate_fullres", lambda: ops.remap(img, gfull, "B2HW", True), (2 * 6 + 2) * B * 64 * N * 4, None,
+        lambda: TO.img_rotate(img, gfull.expand(B, -1, -1, -1)))
+    rec("samplegrid_fullres", lambda: ops.samplegrid((1, 3, 8 * h, 8 * w), Ra), 2 * 64 * N * 4, None,
+        lambda: TO.generate_samplegrid((1, 3, 8 * h, 8 * w), Ra))
+    cl = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    f1a, f2a, f1b, f2b = cl(fm[0]), ops.channels_last_pyramid(fm[1], 4), cl(fm[2]), ops.channels_last_pyramid(fm[3], 4)
+    rec("lookup_onthefly", lambda: ops.lookup_onthefly(coords, f1a, f2a, f1b, f2b, gw, gc, 4))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "kbench.json"), "w") as fh:
+        json.dump(rows, fh, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,143 @@
+"""GPU, full size (BASELINE config 2: 512x1024 ERP -> 64x128 features, C = 256): the CUDA path against the same
+ATen CUDA kernels the reference would execute (oracle/torch_oracle.py run on the device).  This is where the
+"aten_cuda" coordinate flavour (tensor / scalar == multiply by the fp32 reciprocal) is pinned: sample coordinates
+must be bit-identical to what torch computes on the GPU; values within 1e-5 of max|ref| on the fp32 path.
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import rel_to_max
+from oracle import torch_oracle as TO
+
+pytestmark = pytest.mark.gpu
+H8, W8, C = 64, 128, 256
+
+
+def host(t):
+    return t.detach().float().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def scene():
+    from prior_flow_b200 import ops
+    assert ops.get_div_mode() == "aten_cuda"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    fm = [torch.randn(1, C, H8, W8, device="cuda", generator=g) * 1.45 for _ in range(4)]
+    coords = TO.coords_grid(1, H8, W8, "cuda") + torch.randn(1, 2, H8, W8, device="cuda", generator=g) * 5.0
+    R_a2b = TO.rotation_matrix([0., 0., -np.pi / 2], device="cuda")
+    R_b2a = TO.rotation_matrix([0., 0., np.pi / 2], device="cuda")
+    grids = dict(a2b_8x=TO.generate_samplegrid((1, 3, H8, W8), R_a2b),
+                 a2b_w2c_8x=TO.generate_samplegrid((1, 3, H8, W8), R_a2b.T.contiguous()),
+                 b2a_8x=TO.generate_samplegrid((1, 3, H8, W8), R_b2a),
+                 b2a_w2c_8x=TO.generate_samplegrid((1, 3, H8, W8), R_b2a.T.contiguous()))
+    pyr_a = TO.build_pyramid(TO.corr_volume(fm[0], fm[1]))
+    pyr_b = TO.build_pyramid(TO.corr_volume(fm[2], fm[3]))
+    return dict(fm=fm, coords=coords, grids=grids, pyr_a=pyr_a, pyr_b=pyr_b, R_a2b=R_a2b, R_b2a=R_b2a)
+
+
+def test_aten_cuda_division_is_reciprocal_multiply():
+    """The premise of div_mode 'aten_cuda' (ATen's div_true_kernel_cuda with a CPU scalar)."""
+    x = torch.randn(1 << 16, device="cuda") * 100
+    for s in (127.0, 63.0, 2 * np.pi, np.pi, 255.0):
+        inv = torch.tensor(1.0, dtype=torch.float32) / torch.tensor(s, dtype=torch.float32)
+        assert torch.equal(x / s, x * inv.item())
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-5), ("fp32_simt", 1e-5), ("f16", 2e-3)])
+def test_volume_full_size(scene, mode, tol):
+    from prior_flow_b200 import ops
+    fm = scene["fm"]
+    pyr = ops.volume_pyramid(fm[0], fm[1], 4, mode)
+    for l in range(4):
+        assert pyr[l].shape == scene["pyr_a"][l].shape
+        assert rel_to_max(host(pyr[l]), host(scene["pyr_a"][l])) < tol, (mode, l)
+    # also against an fp64 contraction: the fp32 path must be as accurate as cuBLAS fp32 itself
+    if mode == "fp32":
+        ref64 = torch.matmul(fm[0].double().view(1, C, -1).transpose(1, 2), fm[1].double().view(1, C, -1)) / 16.0
+        err_ours = (pyr[0].view(1, H8 * W8, -1).double() - ref64).abs().max().item()
+        err_cublas = (scene["pyr_a"][0].view(1, H8 * W8, -1).double() - ref64).abs().max().item()
+        assert err_ours < 4 * err_cublas + 1e-6, (err_ours, err_cublas)
+
+
+def test_lookup_coordinates_match_aten_cuda(scene):
+    from prior_flow_b200 import ops
+    c = scene["coords"]
+    g = scene["grids"]
+    (_, _), (d_own, d_other) = ops.lookup(c, scene["pyr_a"], scene["pyr_b"], g["a2b_w2c_8x"], g["b2a_8x"], 4, debug=True)
+    for lvl in range(4):
+        Hl, Wl = H8 >> lvl, W8 >> lvl
+        win = TO._window(c, lvl, 4)                                   # [N,9,9,2]
+        x = win[..., 0] % Wl
+        ix = ((2 * x / (Wl - 1) - 1) + 1) / 2 * (Wl - 1)
+        iy = ((2 * win[..., 1] / (Hl - 1) - 1) + 1) / 2 * (Hl - 1)
+        assert torch.equal(d_own[:, lvl, :, 0], ix.reshape(-1, 81)), lvl
+        assert torch.equal(d_own[:, lvl, :, 1], iy.reshape(-1, 81)), lvl
+        mapped = TO.sample_px(g["a2b_w2c_8x"], win.reshape(1, H8 * W8, 81, 2), True)     # [1,2,N,81]
+        qx, qy = mapped[0, 0] % Wl, mapped[0, 1]
+        jx = ((2 * qx / (Wl - 1) - 1) + 1) / 2 * (Wl - 1)
+        jy = ((2 * qy / (Hl - 1) - 1) + 1) / 2 * (Hl - 1)
+        assert torch.equal(d_other[:, lvl, :, 0], jx), lvl
+        assert torch.equal(d_other[:, lvl, :, 1], jy), lvl
+
+
+def test_dual_lookup_full_size(scene):
+    from prior_flow_b200 import ops
+    g = scene["grids"]
+    for coords, own_p, oth_p, gw, gc in ((scene["coords"], scene["pyr_a"], scene["pyr_b"], g["a2b_w2c_8x"], g["b2a_8x"]),
+                                         (scene["coords"].flip(3), scene["pyr_b"], scene["pyr_a"], g["b2a_w2c_8x"], g["a2b_8x"])):
+        own, other = ops.lookup(coords, own_p, oth_p, gw, gc, 4)
+        want_own, want_other = TO.dccl_lookup(coords, own_p, oth_p, gw, gc, 4)
+        assert rel_to_max(host(own), host(want_own)) < 1e-5
+        assert rel_to_max(host(other), host(want_other)) < 1e-5
+        assert torch.equal(own, want_own)
+        assert torch.equal(other, want_other)
+
+
+def test_lookup_on_tcgen05_pyramid_end_to_end(scene):
+    """Volume (tcgen05) -> lookup, against matmul -> avg_pool -> grid_sample: 1e-5 of max|ref|."""
+    from prior_flow_b200 import ops
+    fm, g = scene["fm"], scene["grids"]
+    pa, pb = ops.volume_pyramid(fm[0], fm[1], 4, "fp32"), ops.volume_pyramid(fm[2], fm[3], 4, "fp32")
+    own, other = ops.lookup(scene["coords"], pa, pb, g["a2b_w2c_8x"], g["b2a_8x"], 4)
+    want_own, want_other = TO.dccl_lookup(scene["coords"], scene["pyr_a"], scene["pyr_b"], g["a2b_w2c_8x"], g["b2a_8x"], 4)
+    assert rel_to_max(host(own), host(want_own)) < 1e-5
+    assert rel_to_max(host(other), host(want_other)) < 1e-5
+
+
+def test_samplegrids_full_size(scene):
+    from prior_flow_b200 import ops
+    for R in (scene["R_a2b"], scene["R_b2a"], scene["R_a2b"].T.contiguous()):
+        for (H, W) in ((H8, W8), (512, 1024)):
+            got = ops.samplegrid((1, 3, H, W), R)
+            want = TO.generate_samplegrid((1, 3, H, W), R)
+            # same libdevice functions and op order as ATen: at most an ulp of the pixel coordinate apart
+            assert (got - want).abs().max().item() <= 1.3e-4 * (W / 1024 + 0.06), (H, W)
+
+
+def test_flo_rotate_and_warp_full_size(scene):
+    from prior_flow_b200 import ops
+    g = scene["grids"]
+    flow = scene["coords"] - TO.coords_grid(1, H8, W8, "cuda")
+    assert torch.equal(ops.flo_rotate(flow, g["b2a_w2c_8x"], g["b2a_8x"]), TO.flo_rotate(flow, g["b2a_w2c_8x"], g["b2a_8x"]))
+    fm = scene["fm"]
+    got = ops.warp_groupcorr(fm[0], fm[1], scene["coords"], 4)
+    assert rel_to_max(host(got), host(TO.warp_groupcorr(fm[0], fm[1], scene["coords"], 4))) < 1e-5
+    warped = ops.remap(fm[1], scene["coords"].permute(0, 2, 3, 1).contiguous(), "BHW2", True)
+    assert torch.equal(warped, TO.cycle_bilinear_sampler(fm[1], scene["coords"].permute(0, 2, 3, 1)))
+    img = torch.rand(1, 6, 512, 1024, device="cuda") * 2 - 1
+    grid = TO.generate_samplegrid((1, 3, 512, 1024), scene["R_a2b"])
+    assert torch.equal(ops.remap(img, grid, "B2HW", True), TO.img_rotate(img, grid))
+
+
+def test_onthefly_full_size(scene):
+    from prior_flow_b200 import ops
+    fm, g = scene["fm"], scene["grids"]
+    want_own, want_other = TO.dccl_lookup(scene["coords"], scene["pyr_a"], scene["pyr_b"], g["a2b_w2c_8x"], g["b2a_8x"], 4)
+    cl = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    own, other = ops.lookup_onthefly(scene["coords"], cl(fm[0]), ops.channels_last_pyramid(fm[1], 4), cl(fm[2]),
+                                     ops.channels_last_pyramid(fm[3], 4), g["a2b_w2c_8x"], g["b2a_8x"], 4)
+    assert rel_to_max(host(own), host(want_own)) < 1e-5
+    assert rel_to_max(host(other), host(want_other)) < 1e-5
