@@ -1,0 +1,130 @@
+"""Host-side mirror of PriOr-RAFT/core/corr.py: `DCCL`, `CorrBlock`, `AlternateCorrBlock` with the
+reference's constructor and call signatures, backed by the sm_100a kernels.
+
+`PriOr_RAFT.forward` never inspects what `self.corr(...)` or `build_pyramid(...)` return
+(core/prior_raft.py:151-159), so both are opaque handles here:
+
+  corr(fmap1, fmap2)          -> CostVolume   (lazy: just the two feature maps)
+  DCCL.build_pyramid(volume)  -> Pyramid      (fused tcgen05 GEMM + pooling)  or
+                                 FeaturePyramid (on-the-fly mode: pooled channels-last fmaps, O(N*C) memory)
+  DCCL.__call__(coords, pyr_own, pyr_other, grid_W2C_8x, grid_C2W_8x) -> (out_own, out_other)
+
+A materialised [B,h,w,h,w] tensor is still accepted by build_pyramid (it is pooled with the
+avg-pool kernel), and `CostVolume.materialize()` gives that tensor to callers that want it.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+
+# Above this many query pixels the O(N^2) volume stops paying (4 GiB/view at 1024x2048) and DCCL switches to
+# the on-the-fly lookup unless told otherwise.
+ONTHEFLY_MIN_PIXELS = 128 * 256
+
+
+class CostVolume:
+    """Lazy all-pairs volume: what `PriOr_RAFT.corr` returns (core/prior_raft.py:69-75)."""
+
+    def __init__(self, fmap1: torch.Tensor, fmap2: torch.Tensor, mode: Optional[str] = None):
+        if fmap1.shape != fmap2.shape or fmap1.dim() != 4:
+            raise ValueError("fmap1/fmap2 must be [B,C,h,w] with equal shapes")
+        self.fmap1, self.fmap2, self.mode = fmap1.float(), fmap2.float(), mode
+
+    @property
+    def shape(self):
+        B, _, h, w = self.fmap1.shape
+        return torch.Size((B, h, w, h, w))
+
+    def materialize(self) -> torch.Tensor:
+        """The reference's tensor: [B, h, w, h, w] fp32."""
+        B, _, h, w = self.fmap1.shape
+        return ops.volume_pyramid_autograd(self.fmap1, self.fmap2, 1, self.mode)[0].view(B, h, w, h, w)
+
+
+class Pyramid(list):
+    """Materialised pyramid: a list of [B*h*w, 1, h>>l, w>>l] tensors (the reference's layout, core/corr.py:99-111)."""
+
+
+class FeaturePyramid:
+    """On-the-fly operands: channels-last query features and the pooled channels-last target pyramid."""
+
+    def __init__(self, fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int):
+        self.f1 = fmap1.permute(0, 2, 3, 1).contiguous()
+        self.f2 = ops.channels_last_pyramid(fmap2, num_levels)
+        self.num_levels = num_levels
+
+    def __len__(self):
+        return self.num_levels
+
+
+def corr(fmap1: torch.Tensor, fmap2: torch.Tensor) -> CostVolume:
+    """Drop-in for PriOr_RAFT.corr (core/prior_raft.py:69-75)."""
+    return CostVolume(fmap1, fmap2)
+
+
+class DCCL:
+    """Dual-cost correlation lookup — core/corr.py:94-144."""
+
+    def __init__(self, num_levels: int = 4, radius: int = 4, mode: str = "auto", volume_mode: Optional[str] = None):
+        if mode not in ("auto", "materialized", "onthefly"):
+            raise ValueError("mode must be auto | materialized | onthefly")
+        self.num_levels, self.radius, self.mode, self.volume_mode = num_levels, radius, mode, volume_mode
+
+    def _use_onthefly(self, h: int, w: int) -> bool:
+        return self.mode == "onthefly" or (self.mode == "auto" and h * w >= ONTHEFLY_MIN_PIXELS)
+
+    def build_pyramid(self, cost_volume_8):
+        if isinstance(cost_volume_8, CostVolume):
+            f1, f2 = cost_volume_8.fmap1, cost_volume_8.fmap2
+            if self._use_onthefly(f1.shape[2], f1.shape[3]):
+                if torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad):
+                    raise NotImplementedError("the on-the-fly lookup is inference-only; use mode='materialized' to train")
+                return FeaturePyramid(f1, f2, self.num_levels)
+            return Pyramid(ops.volume_pyramid_autograd(f1, f2, self.num_levels, cost_volume_8.mode or self.volume_mode))
+        # a materialised [B,h,w,h,w] tensor, as the reference passes (core/corr.py:102-109)
+        B, h1, w1, h2, w2 = cost_volume_8.shape
+        lvl = cost_volume_8.reshape(B * h1 * w1, 1, h2, w2).float()
+        pyr = Pyramid([lvl])
+        for _ in range(self.num_levels - 1):
+            lvl = ops.avg_pool2x2(lvl) if not lvl.requires_grad else torch.nn.functional.avg_pool2d(lvl, 2, stride=2)
+            pyr.append(lvl)
+        return pyr
+
+    def __call__(self, coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x):
+        coords = coords.float()
+        if isinstance(corr_pyramid_A, FeaturePyramid):
+            return ops.lookup_onthefly(coords, corr_pyramid_A.f1, corr_pyramid_A.f2, corr_pyramid_B.f1, corr_pyramid_B.f2,
+                                       sample_grid_A2B_W2C_8x, sample_grid_B2A_8x, self.radius, cyclic=True)
+        return ops.lookup_autograd(coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x,
+                                   self.radius, cyclic=True)
+
+
+class CorrBlock:
+    """Plain RAFT correlation block — core/corr.py:13-61 (dead code in PriOr_RAFT.forward, kept for the signature)."""
+
+    def __init__(self, fmap1, fmap2, num_levels: int = 4, radius: int = 4):
+        self.num_levels, self.radius = num_levels, radius
+        self.corr_pyramid = Pyramid(ops.volume_pyramid_autograd(fmap1.float(), fmap2.float(), num_levels))
+
+    def __call__(self, coords):
+        return ops.lookup_autograd(coords.float(), self.corr_pyramid, radius=self.radius, cyclic=False)
+
+    @staticmethod
+    def corr(fmap1, fmap2):
+        B, _, h, w = fmap1.shape
+        return CostVolume(fmap1, fmap2).materialize().view(B, h, w, 1, h, w)
+
+
+class AlternateCorrBlock:
+    """Memory-efficient block — core/corr.py:64-91.  The reference calls the unshipped `alt_cuda_corr`; here the
+    on-the-fly kernel computes the same quantity as CorrBlock (non-cyclic sampler) without the volume."""
+
+    def __init__(self, fmap1, fmap2, num_levels: int = 4, radius: int = 4):
+        self.num_levels, self.radius = num_levels, radius
+        self.pyramid = FeaturePyramid(fmap1.float(), fmap2.float(), num_levels)
+
+    def __call__(self, coords):
+        return ops.lookup_onthefly(coords.float(), self.pyramid.f1, self.pyramid.f2, radius=self.radius, cyclic=False)

@@ -17,6 +17,9 @@ namespace pf {
 
 void set_error(const char *fmt, ...);
 int check_launch(const char *what);
+// pf_lookup.cu: img_rotate of a channels-last [B, N, L*K2] map into [B, L*K2, N]
+int rotate_forward(int batch, int h, int w, int num_levels, int radius, int div_mode, const float *grid_c2w,
+                   long long grid_bs, const float *raw, float *out, cudaStream_t st);
 
 #define PF_REQUIRE(cond, ...)            \
   do {                                   \
@@ -29,8 +32,16 @@ int check_launch(const char *what);
 static inline unsigned ceil_div(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
 // torch.remainder(x, m) for m > 0: fmod, then + m when the result is negative (may return m itself
-// for tiny negative x — SURVEY.md §A.2).
+// for tiny negative x — SURVEY.md §A.2).  The three fast paths are exact restatements of
+// fmodf + fix-up for |x| < 2m (fmod is exact; x - m is exact by Sterbenz for m <= x < 2m) and
+// cover every coordinate a sane flow produces; anything else takes the library fmodf.
 __device__ __forceinline__ float remainder_pos(float x, float m) {
+  if (x >= 0.f) {
+    if (x < m) return x;
+    if (x < __fadd_rn(m, m)) return __fsub_rn(x, m);
+  } else if (x > -m) {
+    return __fadd_rn(x, m);
+  }
   float r = fmodf(x, m);
   if (r != 0.f && r < 0.f) r = __fadd_rn(r, m);
   return r;
@@ -96,6 +107,37 @@ __device__ __forceinline__ float blend_zeros(const float *__restrict__ plane, in
   acc = __fmaf_rn(v_ne, t.ne, acc);
   acc = __fmaf_rn(v_sw, t.sw, acc);
   acc = __fmaf_rn(v_se, t.se, acc);
+  return acc;
+}
+
+// Branch-free form of the zero-padded blend for channel loops: out-of-bounds taps get weight 0
+// and a clamped (valid) offset, so `fma(v, 0, acc) == acc` reproduces ATen's skipped tap exactly
+// for finite data.  Offsets are relative to the plane base.
+struct Taps4 {
+  int o_nw, o_ne, o_sw, o_se;
+  float nw, ne, sw, se;
+};
+__device__ __forceinline__ Taps4 clamp_taps(const Taps &t, int H, int W) {
+  Taps4 c;
+  const bool xin0 = (unsigned)t.x0 < (unsigned)W, xin1 = (unsigned)(t.x0 + 1) < (unsigned)W;
+  const bool yin0 = (unsigned)t.y0 < (unsigned)H, yin1 = (unsigned)(t.y0 + 1) < (unsigned)H;
+  const int x0 = min(max(t.x0, 0), W - 1), x1 = min(max(t.x0 + 1, 0), W - 1);
+  const int y0 = min(max(t.y0, 0), H - 1), y1 = min(max(t.y0 + 1, 0), H - 1);
+  c.o_nw = y0 * W + x0;
+  c.o_ne = y0 * W + x1;
+  c.o_sw = y1 * W + x0;
+  c.o_se = y1 * W + x1;
+  c.nw = (yin0 && xin0) ? t.nw : 0.f;
+  c.ne = (yin0 && xin1) ? t.ne : 0.f;
+  c.sw = (yin1 && xin0) ? t.sw : 0.f;
+  c.se = (yin1 && xin1) ? t.se : 0.f;
+  return c;
+}
+__device__ __forceinline__ float blend4(const float *__restrict__ plane, const Taps4 &c) {
+  float acc = __fmul_rn(__ldg(plane + c.o_nw), c.nw);
+  acc = __fmaf_rn(__ldg(plane + c.o_ne), c.ne, acc);
+  acc = __fmaf_rn(__ldg(plane + c.o_sw), c.sw, acc);
+  acc = __fmaf_rn(__ldg(plane + c.o_se), c.se, acc);
   return acc;
 }
 

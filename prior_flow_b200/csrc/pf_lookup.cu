@@ -1,20 +1,25 @@
 // (b) Dual-cost pyramid lookup — DCCL.__call__ (PriOr-RAFT/core/corr.py:113-144) and
-// CorrBlock.__call__ (core/corr.py:30-51) as one bandwidth-bound launch plus one remap launch.
+// CorrBlock.__call__ (core/corr.py:30-51): one gather launch serving both views + one rotate launch.
 //
-// Work decomposition (one launch serves both views):
-//   grid = (ceil(N/32) query chunks, levels x branches, batch), 256 threads.
-//   A CTA owns 32 consecutive query pixels of one level of one branch.  Each warp walks 4 queries;
-//   its lanes are the (2r+1)^2 window taps ordered y-major (x fastest across lanes) so that one
-//   warp-wide load touches ~4 rows of <=10 contiguous floats of the query's private plane: the
-//   plane rows are the only HBM traffic and every sector is fetched once (L1 serves the four-tap
-//   overlap).  Results are transposed through shared memory so that the [B, L*81, h, w] output is
-//   written as full 128-byte rows.
-//   Branch 0 (own view):   sample pyr_own[l][n] at (c/2^l + d).
-//   Branch 1 (other view): map (c/2^l + d) through the LEVEL-0 rotation grid, sample
-//                          pyr_other[l][n] there (scale mixing is the reference's, SURVEY.md §0
-//                          fact 9), write the pre-rotation map to `scratch`; pf_remap then applies
-//                          img_rotate(., grid_c2w) (a cross-pixel gather, hence the second pass —
-//                          the 10.6 MB intermediate stays in the 126 MB L2).
+// lookup_kernel — grid = (ceil(N/32) query chunks, levels x branches, batch), 256 threads.
+//   A CTA owns 32 consecutive query pixels of one level of one branch; each warp walks 4 queries.
+//   * Window coordinates are separable: the 2r+1 x-coordinates and 2r+1 y-coordinates of a window
+//     go through the (remainder, normalise, unnormalise, floor) chain once each, on lanes 0..2k-1,
+//     and the (2r+1)^2 taps fetch theirs with warp shuffles.  That chain — not memory — was the
+//     limiter of the first version (ncu r01a: 76 % issue-slot utilisation, 13 % DRAM).
+//   * Branch 0 (own view): taps are ordered y-major across lanes (x fastest), so a warp-wide load
+//     touches ~4 rows of <=10 contiguous floats of the query's private plane; L1 serves the
+//     four-corner overlap and every DRAM sector is fetched once.  Results are transposed through
+//     shared memory and written as full 128-byte rows of the [B, L*81, h, w] output.
+//   * Branch 1 (other view): the window is mapped through the LEVEL-0 rotation grid (8 L1-resident
+//     loads), then pyr_other[l][n] is sampled at the mapped point (scale mixing is the
+//     reference's).  The pre-rotation map goes to `scratch` CHANNELS-LAST
+//     ([B, N, L*81]) so that rotate_kernel reads whole 1296-byte vectors.
+// rotate_kernel — img_rotate(., grid_c2w) of that map (core/corr.py:137-138): a cross-pixel
+//   gather, hence a second pass; 32 output pixels x one level per CTA, lanes across channels, four
+//   coalesced vector reads per pixel (the 10.6 MB intermediate stays in L2), shared-memory
+//   transpose, 128-byte output rows.
+// Both kernels have a kBwd instantiation (scatter instead of gather) for training.
 // Coordinates are bit-exact restatements (pf_common.cuh); values are ATen's FMA chain.
 #include "pf_common.cuh"
 
@@ -35,7 +40,8 @@ struct LookupParams {
   Axis ax_gw, ax_gh;  // axes of the rotation grid (query resolution)
   const float *grid_w2c;
   long long grid_bs;
-  float *out_own, *out_raw;            // forward: outputs.  backward: the incoming gradients (read only)
+  float *out_own;                      // forward: [B, L*K2, N] output.  backward: incoming gradient (read only)
+  float *raw;                          // forward: [B, N, L*K2] pre-rotation map.  backward: its gradient (read only)
   float *dbg_own, *dbg_other;
   float *d_own[PF_MAX_LEVELS];         // backward: gradient pyramids (+=)
   float *d_other[PF_MAX_LEVELS];
@@ -58,7 +64,7 @@ __global__ void __launch_bounds__(kLookupThreads) lookup_kernel(const LookupPara
   const int r = (R > 0) ? R : p.radius;
   const int k = 2 * r + 1;
   const int K2 = k * k;
-  extern __shared__ float tile[];  // [K2][33]
+  extern __shared__ float tile[];  // [K2][33], own-view branch only
   const int lvl = blockIdx.y % p.L;
   const int branch = blockIdx.y / p.L;
   const int b = blockIdx.z;
@@ -71,75 +77,166 @@ __global__ void __launch_bounds__(kLookupThreads) lookup_kernel(const LookupPara
   const float *gridx = p.grid_w2c + (long long)b * p.grid_bs;
   const float *gridy = gridx + p.N;
   float *dbg = branch ? p.dbg_other : p.dbg_own;
-  float *io = (branch ? p.out_raw : p.out_own) + ((long long)b * p.L + lvl) * K2 * (long long)p.N + n0;
-  if constexpr (kBwd) {  // stage the incoming gradient tile [K2][32 queries] with coalesced row reads
-    if (n0 + lane < p.N)
-      for (int ch = warp; ch < K2; ch += kLookupThreads / 32) tile[ch * 33 + lane] = io[(long long)ch * p.N + lane];
-    __syncthreads();
+  float *io = p.out_own + ((long long)b * p.L + lvl) * K2 * (long long)p.N + n0;
+  if constexpr (kBwd) {  // own branch: stage the incoming gradient tile [K2][32 queries], coalesced rows
+    if (branch == 0) {
+      if (n0 + lane < p.N)
+        for (int ch = warp; ch < K2; ch += kLookupThreads / 32) tile[ch * 33 + lane] = io[(long long)ch * p.N + lane];
+      __syncthreads();
+    }
   }
+  // this lane's window axis: lanes [0,k) hold x offsets, lanes [k,2k) y offsets
+  const bool is_x = lane < k;
+  const int off = (is_x ? lane : lane - k) - r;
+  const Axis ax1 = branch ? (is_x ? p.ax_gw : p.ax_gh) : (is_x ? axW : axH);  // first sampler's axis
+  const bool wrap1 = is_x && (branch || p.cyclic);
 
 #pragma unroll 1
   for (int qi = 0; qi < kQueriesPerWarp; ++qi) {
     const int q = warp * kQueriesPerWarp + qi;
     const int n = n0 + q;
     if (n >= p.N) break;
-    const float cx = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + 0) * p.N + n), inv_scale);
-    const float cy = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + 1) * p.N + n), inv_scale);
+    const float c = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + (is_x ? 0 : 1)) * p.N + n), inv_scale);
+    // core/corr.py:123-126 then the sampler's coordinate chain, once per window row / column
+    float pc = __fadd_rn(c, (float)off);
+    if (wrap1) pc = remainder_pos(pc, ax1.size);
+    const float sc = to_sample_coord(pc, ax1, p.div_mode);
+    const float fl = floorf(sc);
+    const int i0 = (int)fl;
+    const float w_hi = __fsub_rn(sc, fl);                  // ix - ix_nw
+    const float w_lo = __fsub_rn(__fadd_rn(fl, 1.f), sc);  // ix_se - ix
     const long long plane_off = ((long long)b * p.N + n) * (long long)(Hl * Wl);
     const float *plane = kBwd ? nullptr : vol + plane_off;
     float *dplane = kBwd ? (branch ? p.d_other[lvl] : p.d_own[lvl]) + plane_off : nullptr;
+    float *rawq = p.raw + (((long long)b * p.N + n) * p.L + lvl) * K2;
+
     auto do_tap = [&](int t) {
-      const int bb = t / k, aa = t - bb * k;  // lanes walk x fastest
-      const float px = __fadd_rn(cx, (float)(aa - r));
-      const float py = __fadd_rn(cy, (float)(bb - r));
-      float sx, sy;
-      if (branch == 0) {
-        sx = px;
-        sy = py;
-      } else {
-        // core/corr.py:132-133 — cycle_bilinear_sampler(sample_grid_W2C_8x, coords_lvl)
-        const float gx = to_sample_coord(remainder_pos(px, p.ax_gw.size), p.ax_gw, p.div_mode);
-        const float gy = to_sample_coord(py, p.ax_gh, p.div_mode);
-        const Taps tg = make_taps(gx, gy);
-        sx = blend_zeros(gridx, p.h, p.w, tg);
-        sy = blend_zeros(gridy, p.h, p.w, tg);
-      }
-      const float x = p.cyclic ? remainder_pos(sx, axW.size) : sx;
-      const float ix = to_sample_coord(x, axW, p.div_mode);
-      const float iy = to_sample_coord(sy, axH, p.div_mode);
-      const int ch = aa * k + bb;  // x-major channel order of the reference
-      if constexpr (kBwd) {
-        scatter_zeros(dplane, Hl, Wl, make_taps(ix, iy), tile[ch * 33 + q]);
-        return;
-      } else {
-        tile[ch * 33 + q] = blend_zeros(plane, Hl, Wl, make_taps(ix, iy));
-      }
+      const bool live = t < K2;
+      const int tt = live ? t : 0;
+      // own view: lanes walk x fastest (coalesced plane rows); other view: lanes walk the output channel
+      const int hi = tt / k, lo = tt - hi * k;
+      const int aa = branch ? hi : lo, bb = branch ? lo : hi;
+      Taps tp;
+      tp.x0 = __shfl_sync(0xffffffffu, i0, aa);
+      tp.y0 = __shfl_sync(0xffffffffu, i0, k + bb);
+      const float dxe = __shfl_sync(0xffffffffu, w_lo, aa), dxw = __shfl_sync(0xffffffffu, w_hi, aa);
+      const float dys = __shfl_sync(0xffffffffu, w_lo, k + bb), dyn = __shfl_sync(0xffffffffu, w_hi, k + bb);
+      float ix = 0.f, iy = 0.f;
       if (dbg != nullptr) {
-        float *d = dbg + ((((long long)b * p.N + n) * p.L + lvl) * K2 + ch) * 2;
-        d[0] = ix;
-        d[1] = iy;
+        ix = __shfl_sync(0xffffffffu, sc, aa);
+        iy = __shfl_sync(0xffffffffu, sc, k + bb);
+      }
+      if (!live) return;
+      tp.nw = __fmul_rn(dxe, dys);
+      tp.ne = __fmul_rn(dxw, dys);
+      tp.sw = __fmul_rn(dxe, dyn);
+      tp.se = __fmul_rn(dxw, dyn);
+      const int ch = aa * k + bb;  // x-major channel order of the reference
+      if (branch) {
+        // core/corr.py:132-136 — map through the level-0 rotation grid, then index the level-l volume
+        const Taps4 tg = clamp_taps(tp, p.h, p.w);
+        const float sx = blend4(gridx, tg), sy = blend4(gridy, tg);
+        ix = to_sample_coord(remainder_pos(sx, axW.size), axW, p.div_mode);
+        iy = to_sample_coord(sy, axH, p.div_mode);
+        tp = make_taps(ix, iy);
+      }
+      if constexpr (kBwd) {
+        scatter_zeros(dplane, Hl, Wl, tp, branch ? __ldg(rawq + ch) : tile[ch * 33 + q]);
+      } else {
+        const float val = blend4(plane, clamp_taps(tp, Hl, Wl));
+        if (branch)
+          rawq[ch] = val;
+        else
+          tile[ch * 33 + q] = val;
+        if (dbg != nullptr) {
+          float *d = dbg + ((((long long)b * p.N + n) * p.L + lvl) * K2 + ch) * 2;
+          d[0] = ix;
+          d[1] = iy;
+        }
       }
     };
     if constexpr (R > 0) {
 #pragma unroll
-      for (int it = 0; it < (K2 + 31) / 32; ++it) {
-        const int t = it * 32 + lane;
-        if (t < K2) do_tap(t);
+      for (int it = 0; it < (K2 + 31) / 32; ++it) do_tap(it * 32 + lane);
+    } else {
+      for (int t0 = 0; t0 < K2; t0 += 32) do_tap(t0 + lane);
+    }
+  }
+  if constexpr (!kBwd) {
+    if (branch == 0) {
+      __syncthreads();
+      if (n0 + lane < p.N)
+        for (int ch = warp; ch < K2; ch += kLookupThreads / 32) io[(long long)ch * p.N + lane] = tile[ch * 33 + lane];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// img_rotate of the channels-last pre-rotation map: out[b, c, p] = sum_t w_t(p) raw[b, src_t(p), c].
+constexpr int kRotThreads = 256;
+constexpr int kRotPixels = 32;
+
+struct RotateParams {
+  int B, N, h, w, L, K2, div_mode;
+  Axis axW, axH;
+  const float *grid_c2w;
+  long long grid_bs;
+  const float *raw;   // fwd: [B, N, L*K2] in.   bwd: unused
+  float *out;         // fwd: [B, L*K2, N] out.  bwd: incoming gradient (read only)
+  float *draw;        // bwd: [B, N, L*K2] (+=)
+};
+
+template <bool kBwd>
+__global__ void __launch_bounds__(kRotThreads) rotate_kernel(const RotateParams p) {
+  extern __shared__ float tile[];  // [K2][33]
+  const int lvl = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * kRotPixels;
+  const int C = p.L * p.K2;
+  float *io = p.out + ((long long)b * C + (long long)lvl * p.K2) * p.N + n0;
+  if constexpr (kBwd) {
+    if (n0 + lane < p.N)
+      for (int ch = warp; ch < p.K2; ch += kRotThreads / 32) tile[ch * 33 + lane] = io[(long long)ch * p.N + lane];
+    __syncthreads();
+  }
+  const float *gx = p.grid_c2w + (long long)b * p.grid_bs;
+#pragma unroll 1
+  for (int qi = 0; qi < kRotPixels / (kRotThreads / 32); ++qi) {
+    const int q = warp * (kRotPixels / (kRotThreads / 32)) + qi;
+    const int n = n0 + q;
+    if (n >= p.N) break;
+    // module-local cyclic sampler of projection_prim_ortho.py:119-135 on the [.., h, w] map
+    const float x = remainder_pos(__ldg(gx + n), p.axW.size);
+    const float y = __ldg(gx + p.N + n);
+    const Taps4 t = clamp_taps(make_taps(to_sample_coord(x, p.axW, p.div_mode), to_sample_coord(y, p.axH, p.div_mode)),
+                               p.h, p.w);
+    const long long base = (long long)b * p.N * C + (long long)lvl * p.K2;
+    if constexpr (kBwd) {
+      float *d = p.draw + base;
+      for (int ch = lane; ch < p.K2; ch += 32) {
+        const float g = tile[ch * 33 + q];
+        if (t.nw != 0.f) atomicAdd(d + (long long)t.o_nw * C + ch, g * t.nw);
+        if (t.ne != 0.f) atomicAdd(d + (long long)t.o_ne * C + ch, g * t.ne);
+        if (t.sw != 0.f) atomicAdd(d + (long long)t.o_sw * C + ch, g * t.sw);
+        if (t.se != 0.f) atomicAdd(d + (long long)t.o_se * C + ch, g * t.se);
       }
     } else {
-      for (int t = lane; t < K2; t += 32) do_tap(t);
+      const float *s = p.raw + base;
+      for (int ch = lane; ch < p.K2; ch += 32) {
+        float acc = __fmul_rn(__ldg(s + (long long)t.o_nw * C + ch), t.nw);
+        acc = __fmaf_rn(__ldg(s + (long long)t.o_ne * C + ch), t.ne, acc);
+        acc = __fmaf_rn(__ldg(s + (long long)t.o_sw * C + ch), t.sw, acc);
+        acc = __fmaf_rn(__ldg(s + (long long)t.o_se * C + ch), t.se, acc);
+        tile[ch * 33 + q] = acc;
+      }
     }
   }
   if constexpr (!kBwd) {
     __syncthreads();
     if (n0 + lane < p.N)
-      for (int ch = warp; ch < K2; ch += kLookupThreads / 32) io[(long long)ch * p.N + lane] = tile[ch * 33 + lane];
+      for (int ch = warp; ch < p.K2; ch += kRotThreads / 32) io[(long long)ch * p.N + lane] = tile[ch * 33 + lane];
   }
 }
-
-}  // namespace pf
-
-namespace pf {
 
 static int fill_lookup_params(const pf_lookup_args *a, LookupParams &p, bool dual, const char *who) {
   PF_REQUIRE(a->batch > 0 && a->h > 0 && a->w > 0 && a->h2 > 0 && a->w2 > 0, "%s: bad shape", who);
@@ -172,7 +269,7 @@ static int fill_lookup_params(const pf_lookup_args *a, LookupParams &p, bool dua
   p.grid_w2c = a->grid_w2c;
   p.grid_bs = a->grid_batch_stride;
   p.out_own = a->out_own;
-  p.out_raw = a->scratch;
+  p.raw = a->scratch;
   p.dbg_own = a->dbg_own_xy;
   p.dbg_other = a->dbg_other_xy;
   if (dual) {
@@ -182,20 +279,58 @@ static int fill_lookup_params(const pf_lookup_args *a, LookupParams &p, bool dua
   return 0;
 }
 
-static void fill_rotate_args(const pf_lookup_args *a, pf_remap_args &ra) {
+static void fill_rotate_params(const pf_lookup_args *a, RotateParams &rp) {
   const int k = 2 * a->radius + 1;
-  ra.batch = a->batch;
-  ra.channels = a->num_levels * k * k;
-  ra.H = ra.Ho = a->h;
-  ra.W = ra.Wo = a->w;
-  ra.cyclic = 1;
-  ra.div_mode = a->div_mode;
-  ra.src = a->scratch;
-  ra.coords = a->grid_c2w;
-  ra.coord_batch_stride = a->grid_batch_stride;
-  ra.coord_pixel_stride = 1;
-  ra.coord_xy_stride = (long long)a->h * a->w;
-  ra.out = a->out_other;
+  rp.B = a->batch;
+  rp.N = a->h * a->w;
+  rp.h = a->h;
+  rp.w = a->w;
+  rp.L = a->num_levels;
+  rp.K2 = k * k;
+  rp.div_mode = a->div_mode;
+  rp.axW = make_axis(a->w);
+  rp.axH = make_axis(a->h);
+  rp.grid_c2w = a->grid_c2w;
+  rp.grid_bs = a->grid_batch_stride;
+  rp.raw = a->scratch;
+  rp.out = a->out_other;
+  rp.draw = nullptr;
+}
+
+template <bool kBwd>
+static int launch_lookup(const LookupParams &p, int radius, bool dual, cudaStream_t st, const char *who) {
+  const int k = 2 * radius + 1, K2 = k * k;
+  dim3 grid(ceil_div(p.N, kQueriesPerCta), p.L * (dual ? 2 : 1), p.B);
+  const size_t smem = (size_t)K2 * 33 * sizeof(float);
+  if (radius == 4)
+    lookup_kernel<4, kBwd><<<grid, kLookupThreads, smem, st>>>(p);
+  else
+    lookup_kernel<0, kBwd><<<grid, kLookupThreads, smem, st>>>(p);
+  return check_launch(who);
+}
+
+// img_rotate of a channels-last pre-rotation map, shared with the on-the-fly path (pf_onthefly.cu).
+int rotate_forward(int batch, int h, int w, int num_levels, int radius, int div_mode, const float *grid_c2w,
+                   long long grid_bs, const float *raw, float *out, cudaStream_t st) {
+  const int k = 2 * radius + 1;
+  RotateParams rp;
+  rp.B = batch;
+  rp.N = h * w;
+  rp.h = h;
+  rp.w = w;
+  rp.L = num_levels;
+  rp.K2 = k * k;
+  rp.div_mode = div_mode;
+  rp.axW = make_axis(w);
+  rp.axH = make_axis(h);
+  rp.grid_c2w = grid_c2w;
+  rp.grid_bs = grid_bs;
+  rp.raw = raw;
+  rp.out = out;
+  rp.draw = nullptr;
+  dim3 grid(ceil_div(rp.N, kRotPixels), rp.L, rp.B);
+  rotate_kernel<false><<<grid, kRotThreads, (size_t)rp.K2 * 33 * sizeof(float), st>>>(rp);
+  return check_launch("rotate_kernel");
 }
 
 }  // namespace pf
@@ -212,28 +347,20 @@ extern "C" int pf_lookup_dual(const pf_lookup_args *a, void *stream) {
     PF_REQUIRE(a->own[l] != nullptr, "pf_lookup_dual: own[%d] is null", l);
     PF_REQUIRE(!dual || a->other[l] != nullptr, "pf_lookup_dual: other[%d] is null", l);
   }
-  const int k = 2 * a->radius + 1, K2 = k * k;
-  dim3 grid(ceil_div(p.N, kQueriesPerCta), p.L * (dual ? 2 : 1), p.B);
-  size_t smem = (size_t)K2 * 33 * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->radius == 4)
-    lookup_kernel<4, false><<<grid, kLookupThreads, smem, st>>>(p);
-  else
-    lookup_kernel<0, false><<<grid, kLookupThreads, smem, st>>>(p);
-  if (int e = check_launch("pf_lookup_dual")) return e;
+  if (int e = launch_lookup<false>(p, a->radius, dual, st, "pf_lookup_dual")) return e;
   if (dual) {
     // core/corr.py:137-138 — img_rotate of the [B, L*81, h, w] map with grid_c2w.
-    pf_remap_args ra;
-    fill_rotate_args(a, ra);
-    return pf_remap(&ra, stream);
+    return rotate_forward(a->batch, a->h, a->w, a->num_levels, a->radius, a->div_mode, a->grid_c2w,
+                          a->grid_batch_stride, a->scratch, a->out_other, st);
   }
   return 0;
 }
 
 // (e) d(lookup)/d(pyramids).  The orthogonal branch first runs the adjoint of img_rotate
-// (scatter of grad_other into the zeroed scratch map), then both branches scatter through the
-// forward's coordinates.  A query's plane is private to it, so the atomics only ever collide
-// between taps of one window.
+// (scatter of grad_other into the zeroed channels-last scratch map), then both branches scatter
+// through the forward's coordinates.  A query's plane is private to it, so the atomics only ever
+// collide between taps of one window.
 extern "C" int pf_lookup_dual_bwd(const pf_lookup_bwd_args *ba, void *stream) {
   using namespace pf;
   PF_REQUIRE(ba != nullptr, "pf_lookup_dual_bwd: null args");
@@ -251,20 +378,16 @@ extern "C" int pf_lookup_dual_bwd(const pf_lookup_bwd_args *ba, void *stream) {
   p.dbg_own = p.dbg_other = nullptr;
   p.out_own = const_cast<float *>(ba->grad_own);
   cudaStream_t st = (cudaStream_t)stream;
-  const int k = 2 * a->radius + 1, K2 = k * k;
   if (dual) {
-    const size_t bytes = (size_t)a->batch * p.L * K2 * p.N * sizeof(float);
+    RotateParams rp;
+    fill_rotate_params(a, rp);
+    const size_t bytes = (size_t)a->batch * rp.L * rp.K2 * rp.N * sizeof(float);
     if (cudaMemsetAsync(a->scratch, 0, bytes, st) != cudaSuccess) return check_launch("pf_lookup_dual_bwd(memset)");
-    pf_remap_args ra;
-    fill_rotate_args(a, ra);
-    ra.out = nullptr;
-    if (int e = pf_remap_bwd(&ra, ba->grad_other, a->scratch, stream)) return e;
+    rp.out = const_cast<float *>(ba->grad_other);
+    rp.draw = a->scratch;
+    dim3 grid(ceil_div(rp.N, kRotPixels), rp.L, rp.B);
+    rotate_kernel<true><<<grid, kRotThreads, (size_t)rp.K2 * 33 * sizeof(float), st>>>(rp);
+    if (int e = check_launch("pf_lookup_dual_bwd(rotate)")) return e;
   }
-  dim3 grid(ceil_div(p.N, kQueriesPerCta), p.L * (dual ? 2 : 1), p.B);
-  size_t smem = (size_t)K2 * 33 * sizeof(float);
-  if (a->radius == 4)
-    lookup_kernel<4, true><<<grid, kLookupThreads, smem, st>>>(p);
-  else
-    lookup_kernel<0, true><<<grid, kLookupThreads, smem, st>>>(p);
-  return check_launch("pf_lookup_dual_bwd");
+  return launch_lookup<true>(p, a->radius, dual, st, "pf_lookup_dual_bwd");
 }

@@ -171,11 +171,19 @@ __global__ void __launch_bounds__(kOtfThreads) onthefly_kernel(const OtfParams p
     }
     __syncthreads();
   }
-  // ---- write [K2][8 queries]: 32-byte row segments of the [B, L*K2, N] output
-  float *out = (branch ? p.out_raw : p.out_own) + ((long long)b * p.L + lvl) * K2 * (long long)p.N + n0;
-  for (int i = threadIdx.x; i < K2 * kOtfQueries; i += kOtfThreads) {
-    const int ch = i / kOtfQueries, q = i - ch * kOtfQueries;
-    if (n0 + q < p.N) out[(long long)ch * p.N + q] = s_out[ch][q];
+  // ---- own view: [K2][8 queries] = 32-byte row segments of the [B, L*K2, N] output;
+  //      other view: channels-last [B, N, L*K2] pre-rotation map (contiguous per query), see pf_lookup.cu
+  if (branch == 0) {
+    float *out = p.out_own + ((long long)b * p.L + lvl) * K2 * (long long)p.N + n0;
+    for (int i = threadIdx.x; i < K2 * kOtfQueries; i += kOtfThreads) {
+      const int ch = i / kOtfQueries, q = i - ch * kOtfQueries;
+      if (n0 + q < p.N) out[(long long)ch * p.N + q] = s_out[ch][q];
+    }
+  } else {
+    for (int i = threadIdx.x; i < K2 * kOtfQueries; i += kOtfThreads) {
+      const int q = i / K2, ch = i - q * K2;
+      if (n0 + q < p.N) p.out_raw[(((long long)b * p.N + n0 + q) * p.L + lvl) * K2 + ch] = s_out[ch][q];
+    }
   }
 }
 
@@ -230,25 +238,11 @@ extern "C" int pf_lookup_onthefly(const pf_onthefly_args *a, void *stream) {
                "pf_lookup_onthefly: dual lookup needs grid_w2c, grid_c2w, out_other and scratch");
     PF_REQUIRE(a->cyclic, "pf_lookup_onthefly: the dual (DCCL) lookup is defined for the cyclic sampler only");
   }
-  const int k = 2 * a->radius + 1, K2 = k * k;
   dim3 grid(ceil_div(p.N, kOtfQueries), p.L * (dual ? 2 : 1), p.B);
   onthefly_kernel<<<grid, kOtfThreads, 0, (cudaStream_t)stream>>>(p);
   if (int e = check_launch("pf_lookup_onthefly")) return e;
-  if (dual) {
-    pf_remap_args ra;
-    ra.batch = a->batch;
-    ra.channels = p.L * K2;
-    ra.H = ra.Ho = a->h;
-    ra.W = ra.Wo = a->w;
-    ra.cyclic = 1;
-    ra.div_mode = a->div_mode;
-    ra.src = a->scratch;
-    ra.coords = a->grid_c2w;
-    ra.coord_batch_stride = a->grid_batch_stride;
-    ra.coord_pixel_stride = 1;
-    ra.coord_xy_stride = (long long)a->h * a->w;
-    ra.out = a->out_other;
-    return pf_remap(&ra, stream);
-  }
+  if (dual)
+    return rotate_forward(a->batch, a->h, a->w, a->num_levels, a->radius, a->div_mode, a->grid_c2w,
+                          a->grid_batch_stride, a->scratch, a->out_other, (cudaStream_t)stream);
   return 0;
 }

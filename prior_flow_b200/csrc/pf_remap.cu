@@ -87,13 +87,14 @@ __global__ void __launch_bounds__(kRemapThreads) remap_kernel(const RemapParams 
   const float *cp = p.coords + (long long)b * p.cbs + (long long)pix * p.cps;
   float x = __ldg(cp), y = __ldg(cp + p.cxs);
   if (p.cyclic) x = remainder_pos(x, p.axW.size);
-  const Taps t = make_taps(to_sample_coord(x, p.axW, p.div_mode), to_sample_coord(y, p.axH, p.div_mode));
+  const Taps4 t = clamp_taps(make_taps(to_sample_coord(x, p.axW, p.div_mode), to_sample_coord(y, p.axH, p.div_mode)),
+                             p.H, p.W);
   const long long plane = (long long)p.H * p.W;
   const float *src = p.src + ((long long)b * p.C + c0) * plane;
   float *out = p.out + ((long long)b * p.C + c0) * p.P + pix;
   const int cn = min(kRemapChannelsPerThread, p.C - c0);
-#pragma unroll 4
-  for (int c = 0; c < cn; ++c) out[(long long)c * p.P] = blend_zeros(src + c * plane, p.H, p.W, t);
+#pragma unroll 8
+  for (int c = 0; c < cn; ++c) out[(long long)c * p.P] = blend4(src + c * plane, t);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -182,10 +183,11 @@ __global__ void flo_rotate_kernel(const float *__restrict__ flow, const float *_
 
 // ------------------------------------------------------------------------------------------------
 // Feature warp + group-wise correlation — core/prior_raft.py:173-174 with :77-83.
-// CTA = 32 consecutive pixels x 16 warps; warp j owns channels [j*C/16, (j+1)*C/16); lanes are
-// pixels, so fmap1 loads and the 4 warp taps of fmap2 are coalesced rows.  Partial sums of the
-// C/groups channels of a group are combined through shared memory in a fixed order.
-constexpr int kWgcWarps = 16;
+// CTA = 32 consecutive pixels x one channel group; its 4 warps split the group's channels; lanes are
+// pixels, so fmap1 loads and the 4 warp taps of fmap2 are coalesced rows.  The bilinear taps are
+// resolved once per pixel (clamped offsets + zero weights), the channel loop is 5 loads + 5 FMAs.
+// Partial sums are combined through shared memory in a fixed order.
+constexpr int kWgcWarps = 4;
 
 __global__ void __launch_bounds__(kWgcWarps * 32) warp_groupcorr_kernel(
     const float *__restrict__ f1, const float *__restrict__ f2, const float *__restrict__ coords,
@@ -194,25 +196,26 @@ __global__ void __launch_bounds__(kWgcWarps * 32) warp_groupcorr_kernel(
   const int HW = H * W;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pix = blockIdx.x * 32 + lane;
-  const int b = blockIdx.y;
-  const int cpw = C / kWgcWarps;  // channels per warp (host guarantees divisibility)
+  const int g = blockIdx.y, b = blockIdx.z;
+  const int cpg = C / G, cpw = cpg / kWgcWarps;  // host guarantees divisibility
   float acc = 0.f;
   if (pix < HW) {
     const float x = remainder_pos(__ldg(coords + 2LL * b * HW + pix), axW.size);
     const float y = __ldg(coords + 2LL * b * HW + HW + pix);
-    const Taps t = make_taps(to_sample_coord(x, axW, div_mode), to_sample_coord(y, axH, div_mode));
-    const float *p1 = f1 + ((long long)b * C + warp * cpw) * HW + pix;
-    const float *p2 = f2 + ((long long)b * C + warp * cpw) * HW;
-#pragma unroll 4
-    for (int c = 0; c < cpw; ++c) acc = __fmaf_rn(__ldg(p1 + (long long)c * HW), blend_zeros(p2 + (long long)c * HW, H, W, t), acc);
+    const Taps4 t = clamp_taps(make_taps(to_sample_coord(x, axW, div_mode), to_sample_coord(y, axH, div_mode)), H, W);
+    const long long c0 = (long long)b * C + g * cpg + warp * cpw;
+    const float *p1 = f1 + c0 * HW + pix;
+    const float *p2 = f2 + c0 * HW;
+#pragma unroll 8
+    for (int c = 0; c < cpw; ++c) acc = __fmaf_rn(__ldg(p1 + (long long)c * HW), blend4(p2 + (long long)c * HW, t), acc);
   }
   part[warp][lane] = acc;
   __syncthreads();
-  const int wpg = kWgcWarps / G;  // warps per group
-  if (warp < G && pix < HW) {
+  if (warp == 0 && pix < HW) {
     float s = 0.f;
-    for (int j = 0; j < wpg; ++j) s += part[warp * wpg + j][lane];
-    out[((long long)b * G + warp) * HW + pix] = s / (float)(C / G);
+#pragma unroll
+    for (int j = 0; j < kWgcWarps; ++j) s += part[j][lane];
+    out[((long long)b * G + g) * HW + pix] = s / (float)cpg;
   }
 }
 
@@ -285,10 +288,10 @@ int pf_warp_groupcorr(const float *fmap1, const float *fmap2, const float *coord
                       int h, int w, int groups, int div_mode, void *stream) {
   using namespace pf;
   PF_REQUIRE(fmap1 && fmap2 && coords && out, "pf_warp_groupcorr: null pointer");
-  PF_REQUIRE(groups > 0 && kWgcWarps % groups == 0 && channels % kWgcWarps == 0 && channels % groups == 0,
-             "pf_warp_groupcorr: need groups | %d and %d | channels (got C=%d, G=%d)", kWgcWarps, kWgcWarps, channels,
+  PF_REQUIRE(groups > 0 && channels % groups == 0 && (channels / groups) % kWgcWarps == 0,
+             "pf_warp_groupcorr: need groups | channels and %d | channels/groups (got C=%d, G=%d)", kWgcWarps, channels,
              groups);
-  dim3 grid(ceil_div((long long)h * w, 32), batch);
+  dim3 grid(ceil_div((long long)h * w, 32), groups, batch);
   warp_groupcorr_kernel<<<grid, kWgcWarps * 32, 0, (cudaStream_t)stream>>>(fmap1, fmap2, coords, out, channels, h, w,
                                                                            groups, make_axis(w), make_axis(h), div_mode);
   return check_launch("pf_warp_groupcorr");

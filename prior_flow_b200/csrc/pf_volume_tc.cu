@@ -153,21 +153,36 @@ __device__ __forceinline__ float split_scale(uint32_t amax_bits) {
 }
 
 // ---------------------------------------------------------------------------------- prep kernels
-__global__ void absmax_kernel(const float *__restrict__ x, long long n, uint32_t *__restrict__ out) {
+// blockIdx.y selects the operand (0: fmap1, 1: fmap2); float4 loads, one atomicMax per warp.
+__global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ x0, const float *__restrict__ x1, long long n,
+                                                      uint32_t *__restrict__ out) {
+  const float *x = blockIdx.y ? x1 : x0;
+  const float4 *x4 = reinterpret_cast<const float4 *>(x);
+  const long long n4 = n >> 2;
   uint32_t m = 0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    m = max(m, __float_as_uint(fabsf(x[i])));
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x4 + i);
+    m = max(max(m, __float_as_uint(fabsf(v.x))), __float_as_uint(fabsf(v.y)));
+    m = max(max(m, __float_as_uint(fabsf(v.z))), __float_as_uint(fabsf(v.w)));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) m = max(m, __float_as_uint(fabsf(x[(n4 << 2) + threadIdx.x])));
   for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out + blockIdx.y, m);
 }
 
-// [B, C, N] fp32  ->  K-major [B, N, C] fp16 hi (and lo) planes.  64(c) x 32(n) tile through smem.
-__global__ void __launch_bounds__(256) split_transpose_kernel(const float *__restrict__ x, __half *__restrict__ hi,
-                                                              __half *__restrict__ lo, int C, int N,
-                                                              const uint32_t *__restrict__ amax_bits, int want_lo) {
+// [B, C, N] fp32  ->  K-major [B, N, C] fp16 hi (and lo) planes.  64(c) x 32(n) tile through smem;
+// blockIdx.z = operand * B + batch.
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float *__restrict__ x0, const float *__restrict__ x1,
+                                                              __half *__restrict__ hi0, __half *__restrict__ lo0,
+                                                              __half *__restrict__ hi1, __half *__restrict__ lo1, int B,
+                                                              int C, int N, const uint32_t *__restrict__ amax_bits,
+                                                              int want_lo) {
   __shared__ float t[64][33];
-  const float s = split_scale(*amax_bits);
-  const int b = blockIdx.z, c0 = blockIdx.y * 64, n0 = blockIdx.x * 32;
+  const int which = blockIdx.z / B, b = blockIdx.z - which * B;
+  const float *x = which ? x1 : x0;
+  __half *hi = which ? hi1 : hi0, *lo = which ? lo1 : lo0;
+  const float s = split_scale(amax_bits[which]);
+  const int c0 = blockIdx.y * 64, n0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const float *xb = x + (long long)b * C * N;
 #pragma unroll
@@ -491,12 +506,11 @@ int volume_build_tc(const pf_volume_args *a, cudaStream_t st) {
   // ---- operand preparation
   if (cudaMemsetAsync(amax, 0, 2 * sizeof(uint32_t), st) != cudaSuccess) return check_launch("pf_volume_build(memset)");
   const long long total = (long long)B * C * N;
-  const unsigned rblocks = (unsigned)((total + 1023) / 1024 < 1184 ? (total + 1023) / 1024 : 1184);
-  absmax_kernel<<<rblocks, 256, 0, st>>>(a->fmap1, total, amax);
-  absmax_kernel<<<rblocks, 256, 0, st>>>(a->fmap2, total, amax + 1);
-  dim3 tgrid(ceil_div(N, 32), ceil_div(C, 64), B);
-  split_transpose_kernel<<<tgrid, 256, 0, st>>>(a->fmap1, a_hi, a_lo, C, N, amax, split ? 1 : 0);
-  split_transpose_kernel<<<tgrid, 256, 0, st>>>(a->fmap2, b_hi, b_lo, C, N, amax + 1, split ? 1 : 0);
+  PF_REQUIRE((((uintptr_t)a->fmap1 | (uintptr_t)a->fmap2) & 15) == 0, "pf_volume_build: fmaps must be 16-byte aligned");
+  const unsigned rblocks = (unsigned)((total / 4 + 255) / 256 < 592 ? (total / 4 + 255) / 256 : 592);
+  absmax_kernel<<<dim3(rblocks, 2), 256, 0, st>>>(a->fmap1, a->fmap2, total, amax);
+  dim3 tgrid(ceil_div(N, 32), ceil_div(C, 64), 2 * B);
+  split_transpose_kernel<<<tgrid, 256, 0, st>>>(a->fmap1, a->fmap2, a_hi, a_lo, b_hi, b_lo, B, C, N, amax, split ? 1 : 0);
   if (int e = check_launch("pf_volume_build(prep)")) return e;
 
   // ---- tensor maps

@@ -1,0 +1,295 @@
+"""PriOr-RAFT with the correlation hot path on the sm_100a kernels — the caller either side of the path.
+
+The hot path has no parameters; what surrounds it (feature/context encoders, the two GRU update blocks) stays on
+PyTorch/cuDNN, as BASELINE.json's north_star prescribes.  This module exists because the reference checkout is not
+available at run time on the GPU box, so `bench.py`, `smoke()` and the end-to-end parity test need a network to
+drive the path with.  Parameter names and shapes are those of the reference (`fnet.*`, `cnet.*`, `ODDC.*`,
+`update_block.*`; PriOr-RAFT/core/prior_raft.py:37-41, core/extractor.py:98-158, core/update.py:117-201), so its
+checkpoints load with `load_state_dict(strict=True)` — including the DataParallel `module.` prefix handling of
+`load_reference_checkpoint`.  Forward semantics follow core/prior_raft.py:107-215 line for line; the differences are
+all in *how* the hot-path lines are executed:
+
+  * the eight sample grids come from a per-device cache instead of 8 x 51 eager launches per forward (:115-125);
+  * volume + pyramid is one fused tcgen05 launch per view (:151-159), or nothing at all in on-the-fly mode;
+  * each DCCL call is 2 launches instead of 168, flo_rotate 1 instead of 123, warp + groupwise_corr 1 instead of 11;
+  * in test_mode the convex upsampling runs once, on the last iteration — the reference computes and discards
+    the other eleven (:193-213).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import geometry as geo
+from . import ops
+from .corr import DCCL, CostVolume
+
+
+# --------------------------------------------------------------------------------------- encoders
+def _norm(kind: str, ch: int) -> nn.Module:
+    if kind == "batch":
+        return nn.BatchNorm2d(ch)
+    if kind == "instance":
+        return nn.InstanceNorm2d(ch)
+    if kind == "group":
+        return nn.GroupNorm(num_groups=ch // 8, num_channels=ch)
+    return nn.Sequential()
+
+
+class ResidualBlock(nn.Module):
+    def __init__(self, cin: int, cout: int, norm_fn: str, stride: int = 1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1, stride=stride)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.relu = nn.ReLU(inplace=True)
+        self.norm1, self.norm2 = _norm(norm_fn, cout), _norm(norm_fn, cout)
+        self.downsample = None
+        if stride != 1:
+            self.norm3 = _norm(norm_fn, cout)   # registered under both names, like the reference's state_dict
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride), self.norm3)
+
+    def forward(self, x):
+        y = self.relu(self.norm1(self.conv1(x)))
+        y = self.relu(self.norm2(self.conv2(y)))
+        return self.relu((x if self.downsample is None else self.downsample(x)) + y)
+
+
+class Encoder(nn.Module):
+    """BasicEncoder: 7x7/2 stem, three 2-block stages (64, 96/2, 128/2), 1x1 head -> 1/8 resolution."""
+
+    def __init__(self, output_dim: int, norm_fn: str, dropout: float = 0.0):
+        super().__init__()
+        self.norm1 = _norm(norm_fn, 64) if norm_fn != "group" else nn.GroupNorm(8, 64)
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3)
+        self.relu1 = nn.ReLU(inplace=True)
+        stages, cin = [], 64
+        for cout, stride in ((64, 1), (96, 2), (128, 2)):
+            stages.append(nn.Sequential(ResidualBlock(cin, cout, norm_fn, stride), ResidualBlock(cout, cout, norm_fn, 1)))
+            cin = cout
+        self.layer1, self.layer2, self.layer3 = stages
+        self.conv2 = nn.Conv2d(128, output_dim, 1)
+        self.dropout = nn.Dropout2d(dropout) if dropout > 0 else None
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, (nn.BatchNorm2d, nn.InstanceNorm2d, nn.GroupNorm)) and m.weight is not None:
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+    def forward(self, x):
+        many = isinstance(x, (tuple, list))
+        if many:
+            n = x[0].shape[0]
+            x = torch.cat(x, dim=0)
+        x = self.relu1(self.norm1(self.conv1(x)))
+        x = self.conv2(self.layer3(self.layer2(self.layer1(x))))
+        if self.training and self.dropout is not None:
+            x = self.dropout(x)
+        return torch.split(x, n, dim=0) if many else x
+
+
+# --------------------------------------------------------------------------------------- update blocks
+class FlowHead(nn.Module):
+    def __init__(self, cin: int = 128, hidden: int = 256):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, hidden, 3, padding=1)
+        self.conv2 = nn.Conv2d(hidden, 2, 3, padding=1)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x):
+        return self.conv2(self.relu(self.conv1(x)))
+
+
+class SepConvGRU(nn.Module):
+    def __init__(self, hidden: int = 128, cin: int = 320):
+        super().__init__()
+        for tag, k, p in (("1", (1, 5), (0, 2)), ("2", (5, 1), (2, 0))):
+            for gate in "zrq":
+                setattr(self, f"conv{gate}{tag}", nn.Conv2d(hidden + cin, hidden, k, padding=p))
+
+    def _pass(self, h, x, tag):
+        hx = torch.cat([h, x], dim=1)
+        z = torch.sigmoid(getattr(self, "convz" + tag)(hx))
+        r = torch.sigmoid(getattr(self, "convr" + tag)(hx))
+        q = torch.tanh(getattr(self, "convq" + tag)(torch.cat([r * h, x], dim=1)))
+        return (1 - z) * h + z * q
+
+    def forward(self, h, x):
+        return self._pass(self._pass(h, x, "1"), x, "2")
+
+
+class MotionEncoder(nn.Module):
+    """BasicMotionEncoder (core/update.py:81-99): consumer of the orthogonal view's [B,324,h,w] lookup."""
+
+    def __init__(self, cor_planes: int):
+        super().__init__()
+        self.convc1 = nn.Conv2d(cor_planes, 256, 1)
+        self.convc2 = nn.Conv2d(256, 192, 3, padding=1)
+        self.convf1 = nn.Conv2d(2, 128, 7, padding=3)
+        self.convf2 = nn.Conv2d(128, 64, 3, padding=1)
+        self.conv = nn.Conv2d(64 + 192, 128 - 2, 3, padding=1)
+
+    def forward(self, flow, corr):
+        cor = F.relu(self.convc2(F.relu(self.convc1(corr))))
+        flo = F.relu(self.convf2(F.relu(self.convf1(flow))))
+        return torch.cat([F.relu(self.conv(torch.cat([cor, flo], dim=1))), flow], dim=1)
+
+
+class DualMotionEncoder(nn.Module):
+    """BasicMultiMotionEncoder (core/update.py:162-201): own lookup + own/rotated flows + the two 4-ch flaw maps."""
+
+    def __init__(self, cor_planes: int):
+        super().__init__()
+        self.convc1_A = nn.Conv2d(cor_planes, 256, 1)
+        self.convc2_A = nn.Conv2d(256, 128, 3, padding=1)
+        self.convf1_A = nn.Conv2d(2, 128, 7, padding=3)
+        self.convf2_A = nn.Conv2d(128, 64, 3, padding=1)
+        self.convf1_B = nn.Conv2d(2, 128, 7, padding=3)
+        self.convf2_B = nn.Conv2d(128, 64, 3, padding=1)
+        self.conv_conf1 = nn.Conv2d(8, 32, 3, padding=1)
+        self.conv_conf2 = nn.Conv2d(32, 16, 3, padding=1)
+        self.conv_A = nn.Conv2d(128 + 64 + 64 + 16, 128 - 4, 3, padding=1)
+
+    def forward(self, flow_A, corr_A, flaw_A, flow_B_A, flaw_B_A):
+        cor = F.relu(self.convc2_A(F.relu(self.convc1_A(corr_A))))
+        fa = F.relu(self.convf2_A(F.relu(self.convf1_A(flow_A))))
+        fb = F.relu(self.convf2_B(F.relu(self.convf1_B(flow_B_A))))
+        conf = F.relu(self.conv_conf2(F.relu(self.conv_conf1(torch.cat([flaw_A, flaw_B_A], dim=1)))))
+        out = F.relu(self.conv_A(torch.cat([cor, fa, fb, conf], dim=1)))
+        return torch.cat([out, flow_A, flow_B_A], dim=1)
+
+
+class _UpdateBase(nn.Module):
+    def __init__(self, encoder: nn.Module, hidden: int):
+        super().__init__()
+        self.encoder = encoder
+        self.gru = SepConvGRU(hidden, 128 + hidden)
+        self.flow_head = FlowHead(hidden, 256)
+        self.mask = nn.Sequential(nn.Conv2d(hidden, 256, 3, padding=1), nn.ReLU(inplace=True), nn.Conv2d(256, 64 * 9, 1))
+
+    def _step(self, net, inp, motion, want_mask=True):
+        net = self.gru(net, torch.cat([inp, motion], dim=1))
+        mask = 0.25 * self.mask(net) if want_mask else None
+        return net, mask, self.flow_head(net)
+
+
+class UpdateBlock(_UpdateBase):          # BasicUpdateBlock, core/update.py:117-136
+    def __init__(self, cor_planes: int, hidden: int = 128):
+        super().__init__(MotionEncoder(cor_planes), hidden)
+
+    def forward(self, net, inp, corr, flow, want_mask=True):
+        return self._step(net, inp, self.encoder(flow, corr), want_mask)
+
+
+class DualUpdateBlock(_UpdateBase):      # BasicMultiUpdateBlock ("ODDC"), core/update.py:139-159
+    def __init__(self, cor_planes: int, hidden: int = 128):
+        super().__init__(DualMotionEncoder(cor_planes), hidden)
+
+    def forward(self, net, inp, flow_A, corr_A, flaw_A, flow_B_A, flaw_B_A, want_mask=True):
+        return self._step(net, inp, self.encoder(flow_A, corr_A, flaw_A, flow_B_A, flaw_B_A), want_mask)
+
+
+# --------------------------------------------------------------------------------------- the model
+def convex_upsample(flow: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """core/prior_raft.py:58-67 — [B,2,h,w] -> [B,2,8h,8w] as a convex combination of the 3x3 neighbourhood."""
+    B, _, h, w = flow.shape
+    mask = torch.softmax(mask.view(B, 1, 9, 8, 8, h, w), dim=2)
+    nb = F.unfold(8 * flow, [3, 3], padding=1).view(B, 2, 9, 1, 1, h, w)
+    up = torch.sum(mask * nb, dim=2).permute(0, 1, 4, 2, 5, 3)
+    return up.reshape(B, 2, 8 * h, 8 * w)
+
+
+class PriOrRAFT(nn.Module):
+    def __init__(self, mixed_precision: bool = False, dropout: float = 0.0, corr_mode: str = "auto",
+                 volume_mode: Optional[str] = None):
+        super().__init__()
+        self.args = SimpleNamespace(mixed_precision=mixed_precision, dropout=dropout, corr_levels=4, corr_radius=4)
+        self.hidden_dim = self.context_dim = 128
+        self.corr_mode, self.volume_mode = corr_mode, volume_mode
+        cor_planes = 4 * 9 * 9
+        self.fnet = Encoder(256, "instance", dropout)
+        self.cnet = Encoder(256, "batch", dropout)
+        self.ODDC = DualUpdateBlock(cor_planes, 128)
+        self.update_block = UpdateBlock(cor_planes, 128)
+
+    def freeze_bn(self):
+        for m in self.modules():
+            if isinstance(m, (nn.BatchNorm2d, nn.SyncBatchNorm)):
+                m.eval()
+
+    def load_reference_checkpoint(self, path: str, strict: bool = True):
+        sd = torch.load(path, map_location="cpu")
+        sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+        return self.load_state_dict(sd, strict=strict)
+
+    # ---- hot-path geometry: input independent, cached per (size, device)
+    def _grids(self, H: int, W: int, device):
+        out = {}
+        for tag, angles in (("A2B", geo.A2B), ("B2A", geo.B2A)):
+            R = geo.rotation_matrix_host(list(angles))
+            Rt = R.T.contiguous()
+            out[tag] = geo.samplegrid_cached(H, W, R, device)
+            out[tag + "_8x"] = geo.samplegrid_cached(H // 8, W // 8, R, device)
+            out[tag + "_W2C_8x"] = geo.samplegrid_cached(H // 8, W // 8, Rt, device)
+        return out
+
+    def forward(self, image1, image2, iters: int = 12, init_flow=None, test_mode: bool = False):
+        amp = lambda: torch.autocast("cuda", enabled=self.args.mixed_precision)
+        image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
+        image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
+        B, _, H, W = image1.shape
+        g = self._grids(H, W, image1.device)
+
+        # orthogonal view of both frames: one 6-channel remap (prior_raft.py:127)
+        both_B = geo.img_rotate(torch.cat([image1, image2], dim=1), sample_grid=g["A2B"])
+        image1_B, image2_B = both_B[:, :3].contiguous(), both_B[:, 3:].contiguous()
+
+        with amp():
+            cA, cB = self.cnet([image1, image1_B])
+            net_A, inp_A = torch.tanh(cA[:, :128]), torch.relu(cA[:, 128:])
+            net_B, inp_B = torch.tanh(cB[:, :128]), torch.relu(cB[:, 128:])
+            f1A, f2A, f1B, f2B = (f.float() for f in self.fnet([image1, image2, image1_B, image2_B]))
+
+        lookup = DCCL(4, 4, mode=self.corr_mode, volume_mode=self.volume_mode)
+        pyr_A = lookup.build_pyramid(CostVolume(f1A, f2A))
+        pyr_B = lookup.build_pyramid(CostVolume(f1B, f2B))
+
+        h, w = H // 8, W // 8
+        coords0 = geo.coords_grid(B, h, w, image1.device)
+        coords1_A, coords1_B = coords0.clone(), coords0.clone()
+        if init_flow is not None:
+            coords1_A = coords1_A + init_flow
+            coords1_B = coords1_B + geo.flo_rotate(init_flow, sample_grid_W2C=g["A2B_W2C_8x"], sample_grid_C2W=g["A2B_8x"])
+
+        preds_A: List[torch.Tensor] = []
+        preds_B: List[torch.Tensor] = []
+        up_A = None
+        for it in range(iters):
+            last = it == iters - 1
+            want_up = last or not test_mode
+            coords1_A, coords1_B = coords1_A.detach(), coords1_B.detach()
+            flow_A, flow_B = coords1_A - coords0, coords1_B - coords0
+            flaw_A = ops.warp_groupcorr_autograd(f1A, f2A, coords1_A, 4)
+            flow_B_A = geo.flo_rotate(flow_B, sample_grid_W2C=g["B2A_W2C_8x"], sample_grid_C2W=g["B2A_8x"])
+            flaw_B_A = ops.warp_groupcorr_autograd(f1A, f2A, coords0 + flow_B_A, 4)
+            with amp():
+                corr_A, corr_B_A = lookup(coords1_A, pyr_A, pyr_B, g["A2B_W2C_8x"], g["B2A_8x"])
+                corr_B, corr_A_B = lookup(coords1_B, pyr_B, pyr_A, g["B2A_W2C_8x"], g["A2B_8x"])
+                net_A, mask_A, d_A = self.ODDC(net_A, inp_A, flow_A, corr_A + corr_B_A, flaw_A, flow_B_A, flaw_B_A,
+                                               want_mask=want_up)
+                net_B, mask_B, d_B = self.update_block(net_B, inp_B, corr_B + corr_A_B, flow_B,
+                                                       want_mask=want_up and not test_mode)
+            coords1_A = coords1_A + d_A
+            coords1_B = coords1_B + d_B
+            if want_up:
+                up_A = convex_upsample(coords1_A - coords0, mask_A)
+                if not test_mode:
+                    preds_A.append(up_A)
+                    preds_B.append(convex_upsample(coords1_B - coords0, mask_B))
+        if test_mode:
+            return up_A
+        return preds_A, preds_B

@@ -14,7 +14,20 @@ import torch
 
 from . import _lib
 
-_state = {"div_mode": _lib.DIV_ATEN_CUDA, "volume_mode": "fp32"}
+_state = {"div_mode": _lib.DIV_ATEN_CUDA, "volume_mode": "fp32", "launches": 0}
+
+
+def _count(n: int) -> None:
+    """Kernels of ours launched so far (bench.py reports them as `gpu_launches`)."""
+    _state["launches"] += n
+
+
+def reset_launch_count() -> None:
+    _state["launches"] = 0
+
+
+def launch_count() -> int:
+    return _state["launches"]
 
 
 def set_div_mode(mode: str) -> None:
@@ -87,6 +100,7 @@ def volume_pyramid(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int = 4
         a = _lib.VolumeArgs(B, Cn, h, w, num_levels, mode_id, fmap1.data_ptr(), fmap2.data_ptr(),
                             _lib.level_ptrs(levels), ws_ptr, ws_bytes)
         _lib.check(lib.pf_volume_build(C.byref(a), _stream()), "pf_volume_build")
+        _count(num_levels if mode_id == _lib.VOL_FP32_SIMT else 3)   # simt: gemm + pools; tcgen05: absmax, split, gemm
         ws.record_stream(torch.cuda.current_stream())
     return levels
 
@@ -101,6 +115,7 @@ def avg_pool2x2(x: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(x.device):
         _lib.check(lib.pf_avg_pool2x2(x.data_ptr(), out.data_ptr(), x.numel() // (H * W), H, W, _stream()),
                    "pf_avg_pool2x2")
+        _count(1)
     return out
 
 
@@ -156,6 +171,7 @@ def lookup(coords: torch.Tensor, pyr_own: Sequence[torch.Tensor], pyr_other: Opt
             if dual:
                 a.dbg_other_xy = dbg[1].data_ptr()
         _lib.check(lib.pf_lookup_dual(C.byref(a), _stream()), "pf_lookup_dual")
+        _count(2 if dual else 1)
     res = (out_own, out_other) if dual else out_own
     if debug:
         return res, dbg
@@ -177,6 +193,7 @@ def samplegrid(size, R: torch.Tensor, device=None) -> torch.Tensor:
     with torch.cuda.device(dev):
         out = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
         _lib.check(lib.pf_samplegrid(out.data_ptr(), B, H, W, Rc, _state["div_mode"], _stream()), "pf_samplegrid")
+        _count(1)
     return out
 
 
@@ -207,6 +224,7 @@ def remap(src: torch.Tensor, coords: torch.Tensor, coords_layout: str, cyclic: b
         a = _lib.RemapArgs(B, Cn, H, W, Ho, Wo, int(cyclic), _state["div_mode"], src.data_ptr(), coords.data_ptr(),
                            cbs, cps, cxs, out.data_ptr())
         _lib.check(lib.pf_remap(C.byref(a), _stream()), "pf_remap")
+        _count(1)
     return out
 
 
@@ -227,6 +245,7 @@ def flo_rotate(flow: torch.Tensor, grid_w2c: torch.Tensor, grid_c2w: torch.Tenso
         out = torch.empty_like(flow)
         _lib.check(lib.pf_flo_rotate(flow.data_ptr(), gw.data_ptr(), gc.data_ptr(), bs_w, out.data_ptr(), B, H, W,
                                      _stream()), "pf_flo_rotate")
+        _count(1)
     return out
 
 
@@ -243,6 +262,7 @@ def warp_groupcorr(fmap1: torch.Tensor, fmap2: torch.Tensor, coords: torch.Tenso
         out = torch.empty((B, groups, h, w), device=fmap1.device, dtype=torch.float32)
         _lib.check(lib.pf_warp_groupcorr(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr(), out.data_ptr(), B, Cn,
                                          h, w, groups, _state["div_mode"], _stream()), "pf_warp_groupcorr")
+        _count(1)
     return out
 
 
@@ -298,6 +318,7 @@ def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence
             a.grid_w2c, a.grid_c2w, a.grid_batch_stride = gw.data_ptr(), gc.data_ptr(), bs_w
             a.out_other, a.scratch = out_other.data_ptr(), scratch.data_ptr()
         _lib.check(lib.pf_lookup_onthefly(C.byref(a), _stream()), "pf_lookup_onthefly")
+        _count(2 if dual else 1)
     return (out_own, out_other) if dual else out_own
 
 

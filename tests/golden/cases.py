@@ -63,3 +63,36 @@ def small_sampler_case(seed=11):
     pts[0, 0, :6, 0] = [7.0, 7.5, -1e-8, 8.0, 0.0, -0.5]
     pts[0, 1, :6, 1] = [-1.0, -0.5, 5.0, 5.5, 6.0, 0.0]
     return img, pts
+
+
+def seeded_state_dict(template):
+    """Deterministic parameters for the end-to-end golden: every tensor of `template` (a state_dict: name -> tensor
+    with the reference's names/shapes) is filled from a numpy stream seeded by crc32(name), so the reference model
+    (build container, CPU) and prior_flow_b200.model.PriOrRAFT (GPU box) get bit-identical weights without
+    shipping a 33 MB checkpoint.  Conv weights ~ N(0, 2/fan_in); biases ~ N(0, 0.01^2); norm weights ~ 1."""
+    import zlib
+    import torch
+    out = {}
+    for name in sorted(template):
+        t = template[name]
+        rs = np.random.RandomState(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+        shape = tuple(t.shape)
+        if name.endswith("num_batches_tracked"):
+            out[name] = torch.zeros(shape, dtype=t.dtype)
+        elif name.endswith("running_mean"):
+            out[name] = torch.from_numpy((rs.randn(*shape) * 0.05).astype(F))
+        elif name.endswith("running_var"):
+            out[name] = torch.from_numpy((1.0 + 0.1 * rs.rand(*shape)).astype(F))
+        elif len(shape) >= 2:
+            fan_in = int(np.prod(shape[1:]))
+            out[name] = torch.from_numpy((rs.randn(*shape) * np.sqrt(2.0 / fan_in)).astype(F))
+        elif name.endswith("weight"):
+            out[name] = torch.from_numpy((1.0 + 0.05 * rs.randn(*shape)).astype(F))
+        else:
+            out[name] = torch.from_numpy((0.01 * rs.randn(*shape)).astype(F))
+    return out
+
+
+def e2e_images(seed=8, H=128, W=256):
+    rs = np.random.RandomState(seed)
+    return (rs.rand(1, 3, H, W) * 255).astype(F), (rs.rand(1, 3, H, W) * 255).astype(F)

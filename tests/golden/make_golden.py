@@ -102,6 +102,18 @@ def main():
     end_w = ppo.flow2endpoint(ppo.generate_plane_grid(fl.shape), fl, stack=False)
     end_c = ref.mcs.cycle_grid_sample(gw.clone(), end_w.clone(), is_grid=True)
     save("flo_rotate.npz", out=N(out), out_big=N(out_big), end_w=N(end_w), end_c=N(end_c))
+    # ---- end to end: the reference model (prior_raft.py:107-215) with seeded weights, 128x256, 4 iterations
+    from argparse import Namespace
+    model = model_cls(Namespace(mixed_precision=False, dropout=0.0)).eval()
+    model.load_state_dict(cases.seeded_state_dict(model.state_dict()), strict=True)
+    im1, im2 = (T(x) for x in cases.e2e_images())
+    flow4 = model(im1, im2, iters=4, test_mode=True)
+    init = T(cases.flow(seed=9, B=1, sigma=2.0))
+    flow_init = model(im1, im2, iters=2, init_flow=init, test_mode=True)
+    model.train()  # BatchNorm in cnet uses batch statistics; predictions for every iteration, both views
+    model.freeze_bn()
+    pa, pb = model(im1, im2, iters=2)
+    save("e2e.npz", flow4=N(flow4), flow_init=N(flow_init), train_A1=N(pa[1]), train_B1=N(pb[1]))
     print("golden files written to", HERE)
 
 

@@ -1,0 +1,109 @@
+"""GPU: end-to-end flow of the model driven by the CUDA hot path.
+Bar (BASELINE.json north_star): final flow within 1e-3 px mean EPE of the reference — here against (1) golden flows
+produced by the UNMODIFIED reference model on CPU with seeded weights (tests/golden/e2e.npz) and (2) the same network
+with the hot path on eager ATen ops on the same GPU (oracle/cpu_model.py)."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def mean_epe(a, b):
+    return float(np.sqrt(((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2).sum(1)).mean())
+
+
+@pytest.fixture(scope="module")
+def models():
+    from prior_flow_b200.model import PriOrRAFT
+    from oracle.cpu_model import EagerPriOrRAFT
+    torch.backends.cudnn.allow_tf32 = False        # the golden flows are fp32 CPU convolutions
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ours, eager = PriOrRAFT().cuda().eval(), EagerPriOrRAFT().cuda().eval()
+    sd = cases.seeded_state_dict(ours.state_dict())
+    ours.load_state_dict(sd, strict=True)
+    eager.load_state_dict(sd, strict=True)
+    im1, im2 = (torch.from_numpy(x).cuda() for x in cases.e2e_images())
+    return ours, eager, im1, im2
+
+
+@pytest.mark.parametrize("volume_mode,tol", [("fp32", 1e-3), ("fp32_simt", 1e-3)])
+def test_flow_matches_reference_golden(models, volume_mode, tol):
+    ours, _, im1, im2 = models
+    ours.volume_mode = volume_mode
+    g = golden("e2e")
+    with torch.no_grad():
+        flow = ours(im1, im2, iters=4, test_mode=True)
+        flow_init = ours(im1, im2, iters=2, init_flow=torch.from_numpy(cases.flow(seed=9, B=1, sigma=2.0)).cuda(), test_mode=True)
+    ours.volume_mode = None
+    assert flow.shape == g["flow4"].shape
+    assert mean_epe(flow.cpu().numpy(), g["flow4"]) < tol
+    assert mean_epe(flow_init.cpu().numpy(), g["flow_init"]) < tol
+
+
+def test_train_mode_predictions_match_golden(models):
+    ours, _, im1, im2 = models
+    g = golden("e2e")
+    ours.train()
+    ours.freeze_bn()
+    try:
+        pa, pb = ours(im1, im2, iters=2)
+    finally:
+        ours.eval()
+    assert len(pa) == 2 and len(pb) == 2
+    assert mean_epe(pa[1].detach().cpu().numpy(), g["train_A1"]) < 1e-3
+    assert mean_epe(pb[1].detach().cpu().numpy(), g["train_B1"]) < 1e-3
+
+
+def test_flow_matches_eager_path_on_same_gpu(models):
+    ours, eager, im1, im2 = models
+    with torch.no_grad():
+        a = ours(im1, im2, iters=12, test_mode=True)
+        b = eager(im1, im2, iters=12, test_mode=True)
+    assert mean_epe(a.cpu().numpy(), b.cpu().numpy()) < 1e-3
+
+
+def test_fast_volume_mode_is_separately_toleranced(models):
+    """f16 single-product volume (TF32-class): stated tolerance 5e-3 px mean EPE at 4 iterations."""
+    ours, _, im1, im2 = models
+    ours.volume_mode = "f16"
+    try:
+        with torch.no_grad():
+            flow = ours(im1, im2, iters=4, test_mode=True)
+    finally:
+        ours.volume_mode = None
+    assert mean_epe(flow.cpu().numpy(), golden("e2e")["flow4"]) < 5e-3
+
+
+def test_onthefly_mode_matches_materialised(models):
+    ours, _, im1, im2 = models
+    with torch.no_grad():
+        a = ours(im1, im2, iters=3, test_mode=True)
+        ours.corr_mode = "onthefly"
+        try:
+            b = ours(im1, im2, iters=3, test_mode=True)
+        finally:
+            ours.corr_mode = "auto"
+    assert mean_epe(a.cpu().numpy(), b.cpu().numpy()) < 1e-3
+
+
+def test_training_step_backward_runs_and_matches_eager(models):
+    """One optimisation-free training step: loss on all predictions, gradients through lookup / volume / warp kernels
+    vs the eager path's autograd on the same GPU (fnet conv1 weight gradient, relative to its max)."""
+    ours, eager, im1, im2 = models
+    grads = []
+    for m in (ours, eager):
+        m.train()
+        m.freeze_bn()
+        m.zero_grad(set_to_none=True)
+        pa, pb = m(im1, im2, iters=2)
+        loss = sum(p.abs().mean() for p in pa) + sum(p.abs().mean() for p in pb)
+        loss.backward()
+        grads.append([m.fnet.conv1.weight.grad.detach().cpu().numpy().copy(), m.fnet.conv2.weight.grad.detach().cpu().numpy().copy()])
+        m.eval()
+    for ga, gb in zip(*grads):
+        assert np.isfinite(ga).all()
+        assert np.abs(ga - gb).max() / np.abs(gb).max() < 1e-3

@@ -2,6 +2,15 @@
 ATen CUDA kernels the reference would execute (oracle/torch_oracle.py run on the device).  This is where the
 "aten_cuda" coordinate flavour (tensor / scalar == multiply by the fp32 reciprocal) is pinned: sample coordinates
 must be bit-identical to what torch computes on the GPU; values within 1e-5 of max|ref| on the fp32 path.
+
+Measured fact (round 1, B200, torch 2.11): on CUDA `F.grid_sample(bilinear, zeros, align_corners=True)` of a 4-D
+input dispatches to cuDNN's spatial-transformer sampler, not to ATen's grid_sampler_2d kernel.  cuDNN's blend
+differs from ATen's (CPU build and native CUDA kernel, which agree with each other and with our kernels bit for bit)
+in the last ulp.  For single samplers that is < 1e-6 of max|ref|; for the orthogonal branch of DCCL the first
+sampler's output is the second sampler's *coordinate*, so one ulp of a coordinate near 128 (7.6e-6 px) becomes
+~1.3e-5 of max|ref| in the value.  Hence: with cuDNN disabled (ATen native kernel) everything is bit-exact; with
+cuDNN enabled (torch's default) the stated tolerance is 1e-5 for the own-view branch and 5e-5 for the orthogonal
+branch — the same gap the reference itself has between its CPU and GPU executions.
 """
 import numpy as np
 import pytest
@@ -62,7 +71,17 @@ def test_volume_full_size(scene, mode, tol):
         assert err_ours < 4 * err_cublas + 1e-6, (err_ours, err_cublas)
 
 
+def native_aten():
+    """ATen's own grid_sampler_2d CUDA kernel instead of cuDNN's sampler."""
+    return torch.backends.cudnn.flags(enabled=False)
+
+
 def test_lookup_coordinates_match_aten_cuda(scene):
+    with native_aten():
+        _check_lookup_coordinates(scene)
+
+
+def _check_lookup_coordinates(scene):
     from prior_flow_b200 import ops
     c = scene["coords"]
     g = scene["grids"]
@@ -89,9 +108,11 @@ def test_dual_lookup_full_size(scene):
     for coords, own_p, oth_p, gw, gc in ((scene["coords"], scene["pyr_a"], scene["pyr_b"], g["a2b_w2c_8x"], g["b2a_8x"]),
                                          (scene["coords"].flip(3), scene["pyr_b"], scene["pyr_a"], g["b2a_w2c_8x"], g["a2b_8x"])):
         own, other = ops.lookup(coords, own_p, oth_p, gw, gc, 4)
-        want_own, want_other = TO.dccl_lookup(coords, own_p, oth_p, gw, gc, 4)
+        want_own, want_other = TO.dccl_lookup(coords, own_p, oth_p, gw, gc, 4)       # cuDNN sampler (torch default)
         assert rel_to_max(host(own), host(want_own)) < 1e-5
-        assert rel_to_max(host(other), host(want_other)) < 1e-5
+        assert rel_to_max(host(other), host(want_other)) < 5e-5
+        with native_aten():                                                           # ATen grid_sampler_2d kernel
+            want_own, want_other = TO.dccl_lookup(coords, own_p, oth_p, gw, gc, 4)
         assert torch.equal(own, want_own)
         assert torch.equal(other, want_other)
 
@@ -102,7 +123,8 @@ def test_lookup_on_tcgen05_pyramid_end_to_end(scene):
     fm, g = scene["fm"], scene["grids"]
     pa, pb = ops.volume_pyramid(fm[0], fm[1], 4, "fp32"), ops.volume_pyramid(fm[2], fm[3], 4, "fp32")
     own, other = ops.lookup(scene["coords"], pa, pb, g["a2b_w2c_8x"], g["b2a_8x"], 4)
-    want_own, want_other = TO.dccl_lookup(scene["coords"], scene["pyr_a"], scene["pyr_b"], g["a2b_w2c_8x"], g["b2a_8x"], 4)
+    with native_aten():
+        want_own, want_other = TO.dccl_lookup(scene["coords"], scene["pyr_a"], scene["pyr_b"], g["a2b_w2c_8x"], g["b2a_8x"], 4)
     assert rel_to_max(host(own), host(want_own)) < 1e-5
     assert rel_to_max(host(other), host(want_other)) < 1e-5
 
@@ -125,17 +147,23 @@ def test_flo_rotate_and_warp_full_size(scene):
     fm = scene["fm"]
     got = ops.warp_groupcorr(fm[0], fm[1], scene["coords"], 4)
     assert rel_to_max(host(got), host(TO.warp_groupcorr(fm[0], fm[1], scene["coords"], 4))) < 1e-5
-    warped = ops.remap(fm[1], scene["coords"].permute(0, 2, 3, 1).contiguous(), "BHW2", True)
-    assert torch.equal(warped, TO.cycle_bilinear_sampler(fm[1], scene["coords"].permute(0, 2, 3, 1)))
+    pts = scene["coords"].permute(0, 2, 3, 1).contiguous()
+    warped = ops.remap(fm[1], pts, "BHW2", True)
     img = torch.rand(1, 6, 512, 1024, device="cuda") * 2 - 1
     grid = TO.generate_samplegrid((1, 3, 512, 1024), scene["R_a2b"])
-    assert torch.equal(ops.remap(img, grid, "B2HW", True), TO.img_rotate(img, grid))
+    rotated = ops.remap(img, grid, "B2HW", True)
+    assert rel_to_max(host(warped), host(TO.cycle_bilinear_sampler(fm[1], pts))) < 1e-6       # vs cuDNN's sampler
+    assert rel_to_max(host(rotated), host(TO.img_rotate(img, grid))) < 1e-6
+    with native_aten():                                                                        # vs ATen's kernel
+        assert torch.equal(warped, TO.cycle_bilinear_sampler(fm[1], pts))
+        assert torch.equal(rotated, TO.img_rotate(img, grid))
 
 
 def test_onthefly_full_size(scene):
     from prior_flow_b200 import ops
     fm, g = scene["fm"], scene["grids"]
-    want_own, want_other = TO.dccl_lookup(scene["coords"], scene["pyr_a"], scene["pyr_b"], g["a2b_w2c_8x"], g["b2a_8x"], 4)
+    with native_aten():
+        want_own, want_other = TO.dccl_lookup(scene["coords"], scene["pyr_a"], scene["pyr_b"], g["a2b_w2c_8x"], g["b2a_8x"], 4)
     cl = lambda t: t.permute(0, 2, 3, 1).contiguous()
     own, other = ops.lookup_onthefly(scene["coords"], cl(fm[0]), ops.channels_last_pyramid(fm[1], 4), cl(fm[2]),
                                      ops.channels_last_pyramid(fm[3], 4), g["a2b_w2c_8x"], g["b2a_8x"], 4)

@@ -1,0 +1,87 @@
+"""CPU: host-side logic that needs neither a GPU nor the CUDA library — drop-in installation into the unmodified
+reference (container only), state-dict compatibility of the surrounding network, sharding, and a 2-rank gloo run
+of the multi-process plumbing bench.py uses."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import ref_shim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+needs_reference = pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not mounted (GPU box)")
+
+
+@needs_reference
+def test_install_patches_every_name_prior_raft_resolves():
+    import prior_flow_b200 as pfb
+    ref = ref_shim.load()
+    orig_dccl, orig_corr = ref.prior_raft.DCCL, ref.prior_raft.PriOr_RAFT.corr
+    try:
+        counts = pfb.install()
+        assert pfb.installed() and sum(counts.values()) >= 19
+        assert ref.prior_raft.DCCL is pfb.DCCL and ref.corr.DCCL is pfb.DCCL and ref.corr.CorrBlock is pfb.CorrBlock
+        assert ref.prior_raft.cycle_bilinear_sampler is pfb.cycle_bilinear_sampler
+        assert ref.ppo.generate_samplegrid is pfb.generate_samplegrid and ref.ppo.flo_rotate is pfb.flo_rotate
+        assert ref.ppo.img_rotate is pfb.img_rotate and ref.utils.bilinear_sampler is pfb.bilinear_sampler
+        vol = ref.prior_raft.PriOr_RAFT.corr(None, torch.zeros(1, 256, 8, 32), torch.zeros(1, 256, 8, 32))
+        assert isinstance(vol, pfb.CostVolume) and tuple(vol.shape) == (1, 8, 32, 8, 32)
+        assert pfb.install() == {}                      # idempotent
+    finally:
+        pfb.uninstall()
+    assert ref.prior_raft.DCCL is orig_dccl and ref.prior_raft.PriOr_RAFT.corr is orig_corr and not pfb.installed()
+
+
+@needs_reference
+def test_network_is_state_dict_compatible_with_the_reference():
+    from argparse import Namespace
+    from prior_flow_b200.model import PriOrRAFT
+    ref = ref_shim.load()
+    theirs = ref.prior_raft.PriOr_RAFT(Namespace(mixed_precision=False, dropout=0.0)).state_dict()
+    mine = PriOrRAFT()
+    assert {k: tuple(v.shape) for k, v in theirs.items()} == {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+    mine.load_state_dict({"module." + k: v for k, v in theirs.items()} if False else theirs, strict=True)
+    assert sum(p.numel() for p in mine.parameters()) == 8337646
+
+
+def test_eager_network_reproduces_reference_golden_on_cpu():
+    """The network around the hot path (oracle/cpu_model.py = model.py's modules + eager ATen hot path) against the
+    unmodified reference's end-to-end flows: identical op sequence on the same device type -> bit-exact."""
+    from oracle.cpu_model import EagerPriOrRAFT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "e2e.npz"))
+    m = EagerPriOrRAFT().eval()
+    m.load_state_dict(cases.seeded_state_dict(m.state_dict()), strict=True)
+    im1, im2 = (torch.from_numpy(x) for x in cases.e2e_images())
+    with torch.no_grad():
+        flow = m(im1, im2, iters=4, test_mode=True).numpy()
+    assert np.array_equal(flow, g["flow4"])
+
+
+def test_rotation_matrix_host_matches_golden(geo):
+    from prior_flow_b200 import geometry
+    assert np.array_equal(geometry.rotation_matrix_host([0., 0., -np.pi / 2]).numpy(), geo["R_a2b"])
+    assert np.array_equal(geometry.rotation_matrix_host([0.3, -0.7, 1.1]).numpy(), geo["R_gen"])
+    assert np.array_equal(geometry.coords_grid(2, 5, 7, "cpu").numpy(), np.load(os.path.join(ROOT, "tests/golden/samplers.npz"))["coords_grid"])
+
+
+def test_shard_pairs_partitions_the_batch():
+    from prior_flow_b200.distributed import shard_pairs
+    for total, world in ((64, 8), (10, 4), (3, 8), (0, 2)):
+        parts = [shard_pairs(total, r, world) for r in range(world)]
+        assert sum(len(p) for p in parts) == total
+        assert sorted(i for p in parts for i in p) == list(range(total))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_two_rank_gloo_plumbing():
+    """world_size 2 over gloo: rank/shard bookkeeping, max-over-ranks timing reduce, DDP loss scaling."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", PYTHONPATH=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "gloo_worker.py")]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "rank0 ok" in out.stdout and "rank1 ok" in out.stdout
