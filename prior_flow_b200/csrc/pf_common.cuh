@@ -31,6 +31,15 @@ int rotate_forward(int batch, int h, int w, int num_levels, int radius, int div_
 
 static inline unsigned ceil_div(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
+// Makes a pointer opaque to the optimiser so that `base + int_offset` stays one IMAD.WIDE per access
+// instead of being re-derived from the kernel parameters with 64-bit multiplies at every load
+// (ncu r01b: half of the lookup kernel's instructions were such address arithmetic).
+template <typename T>
+__device__ __forceinline__ T *opaque(T *p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+
 // torch.remainder(x, m) for m > 0: fmod, then + m when the result is negative (may return m itself
 // for tiny negative x — SURVEY.md §A.2).  The three fast paths are exact restatements of
 // fmodf + fix-up for |x| < 2m (fmod is exact; x - m is exact by Sterbenz for m <= x < 2m) and

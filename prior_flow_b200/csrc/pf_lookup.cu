@@ -4,9 +4,11 @@
 // lookup_kernel — grid = (ceil(N/32) query chunks, levels x branches, batch), 256 threads.
 //   A CTA owns 32 consecutive query pixels of one level of one branch; each warp walks 4 queries.
 //   * Window coordinates are separable: the 2r+1 x-coordinates and 2r+1 y-coordinates of a window
-//     go through the (remainder, normalise, unnormalise, floor) chain once each, on lanes 0..2k-1,
-//     and the (2r+1)^2 taps fetch theirs with warp shuffles.  That chain — not memory — was the
-//     limiter of the first version (ncu r01a: 76 % issue-slot utilisation, 13 % DRAM).
+//     go through the (remainder, normalise, unnormalise, floor, clamp) chain once each, on lanes
+//     0..2k-1, into a per-warp shared-memory table of {clamped offsets, validity-folded weights};
+//     a tap is then two 16-byte table reads, four adds and four multiplies away from its loads.
+//     Instruction issue — not memory — limited the earlier versions (ncu r01a: 76 % issue-slot
+//     utilisation at 13 % DRAM; r01b: 25 instructions per load, half of them integer address math).
 //   * Branch 0 (own view): taps are ordered y-major across lanes (x fastest), so a warp-wide load
 //     touches ~4 rows of <=10 contiguous floats of the query's private plane; L1 serves the
 //     four-corner overlap and every DRAM sector is fetched once.  Results are transposed through
@@ -59,23 +61,57 @@ __device__ __forceinline__ void scatter_zeros(float *__restrict__ plane, int H, 
   if (yin1 && xin1) atomicAdd(r1 + 1, g * t.se);
 }
 
-template <int R, bool kBwd>
-__global__ void __launch_bounds__(kLookupThreads) lookup_kernel(const LookupParams p) {
+// One axis of one window, resolved once per query: clamped element offsets of the two taps and their
+// weights with the zero-padding validity folded in (0 * finite == 0 reproduces ATen's skipped tap, and
+// nw = w0x * w0y is the same rounded product as (ix_se - ix) * (iy_se - iy) when both taps are valid).
+struct AxisEntry {
+  int o0, o1;      // clamp(i0) * stride, clamp(i0 + 1) * stride
+  float w0, w1;    // (i0+1 - s) if i0 in range else 0 ; (s - i0) if i0+1 in range else 0
+};
+
+template <int kDiv>
+__device__ __forceinline__ float sample_coord(float p, const Axis ax) {   // to_sample_coord, div mode resolved at compile time
+  const float t = __fmul_rn(2.f, p);
+  float g = (kDiv == PF_DIV_ATEN_CUDA) ? __fmul_rn(t, ax.inv_m1) : __fdiv_rn(t, ax.size_m1);
+  g = __fsub_rn(g, 1.f);
+  float v = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), ax.size_m1);
+  if (!(fabsf(v) <= 2147483648.f)) v = -100.f;   // non-finite or outside the int range (safe_downgrade_to_int_range)
+  return v;
+}
+
+__device__ __forceinline__ AxisEntry make_axis_entry(float s, int size, int stride) {
+  const float fl = floorf(s);
+  const int i0 = (int)fl;
+  AxisEntry e;
+  e.w1 = ((unsigned)(i0 + 1) < (unsigned)size) ? __fsub_rn(s, fl) : 0.f;
+  e.w0 = ((unsigned)i0 < (unsigned)size) ? __fsub_rn(__fadd_rn(fl, 1.f), s) : 0.f;
+  e.o0 = min(max(i0, 0), size - 1) * stride;
+  e.o1 = min(max(i0 + 1, 0), size - 1) * stride;
+  return e;
+}
+
+template <int R, bool kBwd, int kDiv>
+__global__ void __launch_bounds__(kLookupThreads, 5) lookup_kernel(const LookupParams p) {
   const int r = (R > 0) ? R : p.radius;
   const int k = 2 * r + 1;
   const int K2 = k * k;
-  extern __shared__ float tile[];  // [K2][33], own-view branch only
+  constexpr int kRounds = (R > 0) ? ((2 * R + 1) * (2 * R + 1) + 31) / 32 : 8;  // radius <= 7 -> <= 225 taps
+  extern __shared__ float4 smem4[];
+  // [8 warps][2 buffers][32] axis entries, then the [K2][33] transpose tile (own-view branch only)
+  AxisEntry *tab = reinterpret_cast<AxisEntry *>(smem4) + (threadIdx.x >> 5) * 64;
+  float *tile = reinterpret_cast<float *>(smem4 + (kLookupThreads / 32) * 64);
+  float *dbg_tab = tile + K2 * 33 + (threadIdx.x >> 5) * 32;   // sample coordinates for the debug dump
   const int lvl = blockIdx.y % p.L;
   const int branch = blockIdx.y / p.L;
   const int b = blockIdx.z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
   const int n0 = blockIdx.x * kQueriesPerCta;
   const int Hl = p.Hl[lvl], Wl = p.Wl[lvl];
   const Axis axW = p.axW[lvl], axH = p.axH[lvl];
   const float inv_scale = 1.0f / (float)(1 << lvl);  // `coords / 2**i` is exact either way
   const float *vol = branch ? p.other[lvl] : p.own[lvl];
-  const float *gridx = p.grid_w2c + (long long)b * p.grid_bs;
-  const float *gridy = gridx + p.N;
+  const float *gridx = opaque(p.grid_w2c + (long long)b * p.grid_bs);
+  const float *gridy = opaque(gridx + p.N);
   float *dbg = branch ? p.dbg_other : p.dbg_own;
   float *io = p.out_own + ((long long)b * p.L + lvl) * K2 * (long long)p.N + n0;
   if constexpr (kBwd) {  // own branch: stage the incoming gradient tile [K2][32 queries], coalesced rows
@@ -87,80 +123,104 @@ __global__ void __launch_bounds__(kLookupThreads) lookup_kernel(const LookupPara
   }
   // this lane's window axis: lanes [0,k) hold x offsets, lanes [k,2k) y offsets
   const bool is_x = lane < k;
-  const int off = (is_x ? lane : lane - k) - r;
+  const float off = (float)((is_x ? lane : lane - k) - r);
   const Axis ax1 = branch ? (is_x ? p.ax_gw : p.ax_gh) : (is_x ? axW : axH);  // first sampler's axis
+  const int size1 = branch ? (is_x ? p.w : p.h) : (is_x ? Wl : Hl);
+  const int stride1 = is_x ? 1 : (branch ? p.w : Wl);
   const bool wrap1 = is_x && (branch || p.cyclic);
+  // tap -> (window column a, window row b, output channel), fixed per lane and round.
+  // own view: lanes walk x fastest (coalesced plane rows); other view: lanes walk the output channel.
+  int t_a[kRounds], t_b[kRounds];
+#pragma unroll
+  for (int it = 0; it < kRounds; ++it) {
+    const int t = it * 32 + lane;
+    const int tt = t < K2 ? t : 0;
+    const int hi = tt / k, lo = tt - hi * k;
+    t_a[it] = branch ? hi : lo;
+    t_b[it] = branch ? lo : hi;
+  }
 
 #pragma unroll 1
   for (int qi = 0; qi < kQueriesPerWarp; ++qi) {
     const int q = warp * kQueriesPerWarp + qi;
     const int n = n0 + q;
     if (n >= p.N) break;
-    const float c = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + (is_x ? 0 : 1)) * p.N + n), inv_scale);
-    // core/corr.py:123-126 then the sampler's coordinate chain, once per window row / column
-    float pc = __fadd_rn(c, (float)off);
-    if (wrap1) pc = remainder_pos(pc, ax1.size);
-    const float sc = to_sample_coord(pc, ax1, p.div_mode);
-    const float fl = floorf(sc);
-    const int i0 = (int)fl;
-    const float w_hi = __fsub_rn(sc, fl);                  // ix - ix_nw
-    const float w_lo = __fsub_rn(__fadd_rn(fl, 1.f), sc);  // ix_se - ix
+    AxisEntry *T = tab + (qi & 1) * 32;
+    {
+      // core/corr.py:123-126 then the sampler's coordinate chain, once per window row / column
+      const float c = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + (is_x ? 0 : 1)) * p.N + n), inv_scale);
+      float pc = __fadd_rn(c, off);
+      if (wrap1) pc = remainder_pos(pc, ax1.size);
+      const float sc = sample_coord<kDiv>(pc, ax1);
+      T[lane] = make_axis_entry(sc, size1, stride1);
+      if (dbg != nullptr) dbg_tab[lane] = sc;
+    }
+    __syncwarp();
     const long long plane_off = ((long long)b * p.N + n) * (long long)(Hl * Wl);
-    const float *plane = kBwd ? nullptr : vol + plane_off;
-    float *dplane = kBwd ? (branch ? p.d_other[lvl] : p.d_own[lvl]) + plane_off : nullptr;
-    float *rawq = p.raw + (((long long)b * p.N + n) * p.L + lvl) * K2;
+    const float *plane = kBwd ? nullptr : opaque(vol + plane_off);
+    float *dplane = kBwd ? opaque((branch ? p.d_other[lvl] : p.d_own[lvl]) + plane_off) : nullptr;
+    float *rawq = opaque(p.raw + (((long long)b * p.N + n) * p.L + lvl) * K2);
 
-    auto do_tap = [&](int t) {
-      const bool live = t < K2;
-      const int tt = live ? t : 0;
-      // own view: lanes walk x fastest (coalesced plane rows); other view: lanes walk the output channel
-      const int hi = tt / k, lo = tt - hi * k;
-      const int aa = branch ? hi : lo, bb = branch ? lo : hi;
-      Taps tp;
-      tp.x0 = __shfl_sync(0xffffffffu, i0, aa);
-      tp.y0 = __shfl_sync(0xffffffffu, i0, k + bb);
-      const float dxe = __shfl_sync(0xffffffffu, w_lo, aa), dxw = __shfl_sync(0xffffffffu, w_hi, aa);
-      const float dys = __shfl_sync(0xffffffffu, w_lo, k + bb), dyn = __shfl_sync(0xffffffffu, w_hi, k + bb);
-      float ix = 0.f, iy = 0.f;
-      if (dbg != nullptr) {
-        ix = __shfl_sync(0xffffffffu, sc, aa);
-        iy = __shfl_sync(0xffffffffu, sc, k + bb);
-      }
-      if (!live) return;
-      tp.nw = __fmul_rn(dxe, dys);
-      tp.ne = __fmul_rn(dxw, dys);
-      tp.sw = __fmul_rn(dxe, dyn);
-      tp.se = __fmul_rn(dxw, dyn);
-      const int ch = aa * k + bb;  // x-major channel order of the reference
-      if (branch) {
-        // core/corr.py:132-136 — map through the level-0 rotation grid, then index the level-l volume
-        const Taps4 tg = clamp_taps(tp, p.h, p.w);
-        const float sx = blend4(gridx, tg), sy = blend4(gridy, tg);
-        ix = to_sample_coord(remainder_pos(sx, axW.size), axW, p.div_mode);
-        iy = to_sample_coord(sy, axH, p.div_mode);
-        tp = make_taps(ix, iy);
-      }
-      if constexpr (kBwd) {
-        scatter_zeros(dplane, Hl, Wl, tp, branch ? __ldg(rawq + ch) : tile[ch * 33 + q]);
-      } else {
-        const float val = blend4(plane, clamp_taps(tp, Hl, Wl));
-        if (branch)
-          rawq[ch] = val;
-        else
-          tile[ch * 33 + q] = val;
-        if (dbg != nullptr) {
-          float *d = dbg + ((((long long)b * p.N + n) * p.L + lvl) * K2 + ch) * 2;
-          d[0] = ix;
-          d[1] = iy;
+#pragma unroll
+    for (int it = 0; it < kRounds; ++it) {
+      if (it * 32 >= K2) break;
+      if (it * 32 + lane < K2) {
+        const int aa = t_a[it], bb = t_b[it];
+        const int ch = aa * k + bb;  // x-major channel order of the reference
+        const AxisEntry ex = T[aa], ey = T[k + bb];
+        int o_nw = ey.o0 + ex.o0, o_ne = ey.o0 + ex.o1, o_sw = ey.o1 + ex.o0, o_se = ey.o1 + ex.o1;
+        float w_nw = __fmul_rn(ex.w0, ey.w0), w_ne = __fmul_rn(ex.w1, ey.w0);
+        float w_sw = __fmul_rn(ex.w0, ey.w1), w_se = __fmul_rn(ex.w1, ey.w1);
+        float ix = 0.f, iy = 0.f;
+        if (branch) {
+          // core/corr.py:132-136 — map through the level-0 rotation grid, then index the level-l volume
+          float sx = __fmul_rn(__ldg(gridx + o_nw), w_nw), sy = __fmul_rn(__ldg(gridy + o_nw), w_nw);
+          sx = __fmaf_rn(__ldg(gridx + o_ne), w_ne, sx);
+          sy = __fmaf_rn(__ldg(gridy + o_ne), w_ne, sy);
+          sx = __fmaf_rn(__ldg(gridx + o_sw), w_sw, sx);
+          sy = __fmaf_rn(__ldg(gridy + o_sw), w_sw, sy);
+          sx = __fmaf_rn(__ldg(gridx + o_se), w_se, sx);
+          sy = __fmaf_rn(__ldg(gridy + o_se), w_se, sy);
+          ix = sample_coord<kDiv>(remainder_pos(sx, axW.size), axW);
+          iy = sample_coord<kDiv>(sy, axH);
+          const AxisEntry fx = make_axis_entry(ix, Wl, 1), fy = make_axis_entry(iy, Hl, Wl);
+          o_nw = fy.o0 + fx.o0, o_ne = fy.o0 + fx.o1, o_sw = fy.o1 + fx.o0, o_se = fy.o1 + fx.o1;
+          w_nw = __fmul_rn(fx.w0, fy.w0), w_ne = __fmul_rn(fx.w1, fy.w0);
+          w_sw = __fmul_rn(fx.w0, fy.w1), w_se = __fmul_rn(fx.w1, fy.w1);
+        }
+        if constexpr (kBwd) {
+          const float g = branch ? __ldg(rawq + ch) : tile[ch * 33 + q];
+          if (w_nw != 0.f) atomicAdd(dplane + o_nw, g * w_nw);
+          if (w_ne != 0.f) atomicAdd(dplane + o_ne, g * w_ne);
+          if (w_sw != 0.f) atomicAdd(dplane + o_sw, g * w_sw);
+          if (w_se != 0.f) atomicAdd(dplane + o_se, g * w_se);
+        } else {
+          // a tap that falls entirely outside the plane (most of levels 2-3 of the orthogonal branch, whose
+          // level-0-unit coordinates index a 16x32 / 8x16 plane) contributes an exact 0: skip its DRAM round trip
+          float val = 0.f;
+          if (!branch || fmaxf(fmaxf(w_nw, w_ne), fmaxf(w_sw, w_se)) > 0.f) {
+            val = __fmul_rn(__ldg(plane + o_nw), w_nw);
+            val = __fmaf_rn(__ldg(plane + o_ne), w_ne, val);
+            val = __fmaf_rn(__ldg(plane + o_sw), w_sw, val);
+            val = __fmaf_rn(__ldg(plane + o_se), w_se, val);
+          }
+          if (branch)
+            rawq[ch] = val;
+          else
+            tile[ch * 33 + q] = val;
+          if (dbg != nullptr) {
+            if (!branch) {
+              ix = dbg_tab[aa];
+              iy = dbg_tab[k + bb];
+            }
+            float *d = dbg + ((((long long)b * p.N + n) * p.L + lvl) * K2 + ch) * 2;
+            d[0] = ix;
+            d[1] = iy;
+          }
         }
       }
-    };
-    if constexpr (R > 0) {
-#pragma unroll
-      for (int it = 0; it < (K2 + 31) / 32; ++it) do_tap(it * 32 + lane);
-    } else {
-      for (int t0 = 0; t0 < K2; t0 += 32) do_tap(t0 + lane);
     }
+    if (dbg != nullptr) __syncwarp();   // dbg_tab is single-buffered
   }
   if constexpr (!kBwd) {
     if (branch == 0) {
@@ -188,45 +248,51 @@ struct RotateParams {
 
 template <bool kBwd>
 __global__ void __launch_bounds__(kRotThreads) rotate_kernel(const RotateParams p) {
-  extern __shared__ float tile[];  // [K2][33]
+  extern __shared__ float tile[];  // [K2][33] transpose tile, then one Taps4 per pixel
+  Taps4 *taps = reinterpret_cast<Taps4 *>(tile + p.K2 * 33 + (p.K2 & 1));
   const int lvl = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * kRotPixels;
   const int C = p.L * p.K2;
   float *io = p.out + ((long long)b * C + (long long)lvl * p.K2) * p.N + n0;
+  if (threadIdx.x < kRotPixels && n0 + threadIdx.x < p.N) {
+    // module-local cyclic sampler of projection_prim_ortho.py:119-135 on the [.., h, w] map
+    const float *gx = p.grid_c2w + (long long)b * p.grid_bs;
+    const int n = n0 + threadIdx.x;
+    const float x = remainder_pos(__ldg(gx + n), p.axW.size);
+    const float y = __ldg(gx + p.N + n);
+    Taps4 t = clamp_taps(make_taps(to_sample_coord(x, p.axW, p.div_mode), to_sample_coord(y, p.axH, p.div_mode)), p.h, p.w);
+    t.o_nw *= C, t.o_ne *= C, t.o_sw *= C, t.o_se *= C;   // element offsets into the channels-last map
+    taps[threadIdx.x] = t;
+  }
   if constexpr (kBwd) {
     if (n0 + lane < p.N)
       for (int ch = warp; ch < p.K2; ch += kRotThreads / 32) tile[ch * 33 + lane] = io[(long long)ch * p.N + lane];
-    __syncthreads();
   }
-  const float *gx = p.grid_c2w + (long long)b * p.grid_bs;
+  __syncthreads();
+  const long long base = (long long)b * p.N * C + (long long)lvl * p.K2;
+  const float *src = kBwd ? nullptr : opaque(p.raw + base);
+  float *dst = kBwd ? opaque(p.draw + base) : nullptr;
 #pragma unroll 1
   for (int qi = 0; qi < kRotPixels / (kRotThreads / 32); ++qi) {
     const int q = warp * (kRotPixels / (kRotThreads / 32)) + qi;
-    const int n = n0 + q;
-    if (n >= p.N) break;
-    // module-local cyclic sampler of projection_prim_ortho.py:119-135 on the [.., h, w] map
-    const float x = remainder_pos(__ldg(gx + n), p.axW.size);
-    const float y = __ldg(gx + p.N + n);
-    const Taps4 t = clamp_taps(make_taps(to_sample_coord(x, p.axW, p.div_mode), to_sample_coord(y, p.axH, p.div_mode)),
-                               p.h, p.w);
-    const long long base = (long long)b * p.N * C + (long long)lvl * p.K2;
+    if (n0 + q >= p.N) break;
+    const Taps4 t = taps[q];
     if constexpr (kBwd) {
-      float *d = p.draw + base;
       for (int ch = lane; ch < p.K2; ch += 32) {
         const float g = tile[ch * 33 + q];
-        if (t.nw != 0.f) atomicAdd(d + (long long)t.o_nw * C + ch, g * t.nw);
-        if (t.ne != 0.f) atomicAdd(d + (long long)t.o_ne * C + ch, g * t.ne);
-        if (t.sw != 0.f) atomicAdd(d + (long long)t.o_sw * C + ch, g * t.sw);
-        if (t.se != 0.f) atomicAdd(d + (long long)t.o_se * C + ch, g * t.se);
+        if (t.nw != 0.f) atomicAdd(dst + t.o_nw + ch, g * t.nw);
+        if (t.ne != 0.f) atomicAdd(dst + t.o_ne + ch, g * t.ne);
+        if (t.sw != 0.f) atomicAdd(dst + t.o_sw + ch, g * t.sw);
+        if (t.se != 0.f) atomicAdd(dst + t.o_se + ch, g * t.se);
       }
     } else {
-      const float *s = p.raw + base;
+#pragma unroll 3
       for (int ch = lane; ch < p.K2; ch += 32) {
-        float acc = __fmul_rn(__ldg(s + (long long)t.o_nw * C + ch), t.nw);
-        acc = __fmaf_rn(__ldg(s + (long long)t.o_ne * C + ch), t.ne, acc);
-        acc = __fmaf_rn(__ldg(s + (long long)t.o_sw * C + ch), t.sw, acc);
-        acc = __fmaf_rn(__ldg(s + (long long)t.o_se * C + ch), t.se, acc);
+        float acc = __fmul_rn(__ldg(src + t.o_nw + ch), t.nw);
+        acc = __fmaf_rn(__ldg(src + t.o_ne + ch), t.ne, acc);
+        acc = __fmaf_rn(__ldg(src + t.o_sw + ch), t.sw, acc);
+        acc = __fmaf_rn(__ldg(src + t.o_se + ch), t.se, acc);
         tile[ch * 33 + q] = acc;
       }
     }
@@ -236,6 +302,10 @@ __global__ void __launch_bounds__(kRotThreads) rotate_kernel(const RotateParams 
     if (n0 + lane < p.N)
       for (int ch = warp; ch < p.K2; ch += kRotThreads / 32) io[(long long)ch * p.N + lane] = tile[ch * 33 + lane];
   }
+}
+
+static size_t rotate_smem_bytes(int K2) {
+  return ((size_t)K2 * 33 + (K2 & 1)) * sizeof(float) + kRotPixels * sizeof(Taps4);
 }
 
 static int fill_lookup_params(const pf_lookup_args *a, LookupParams &p, bool dual, const char *who) {
@@ -301,11 +371,19 @@ template <bool kBwd>
 static int launch_lookup(const LookupParams &p, int radius, bool dual, cudaStream_t st, const char *who) {
   const int k = 2 * radius + 1, K2 = k * k;
   dim3 grid(ceil_div(p.N, kQueriesPerCta), p.L * (dual ? 2 : 1), p.B);
-  const size_t smem = (size_t)K2 * 33 * sizeof(float);
-  if (radius == 4)
-    lookup_kernel<4, kBwd><<<grid, kLookupThreads, smem, st>>>(p);
-  else
-    lookup_kernel<0, kBwd><<<grid, kLookupThreads, smem, st>>>(p);
+  const size_t smem = (size_t)(kLookupThreads / 32) * 64 * sizeof(float4) + ((size_t)K2 * 33 + kLookupThreads) * sizeof(float);
+  const bool recip = p.div_mode == PF_DIV_ATEN_CUDA;
+  if (radius == 4) {
+    if (recip)
+      lookup_kernel<4, kBwd, PF_DIV_ATEN_CUDA><<<grid, kLookupThreads, smem, st>>>(p);
+    else
+      lookup_kernel<4, kBwd, PF_DIV_IEEE><<<grid, kLookupThreads, smem, st>>>(p);
+  } else {
+    if (recip)
+      lookup_kernel<0, kBwd, PF_DIV_ATEN_CUDA><<<grid, kLookupThreads, smem, st>>>(p);
+    else
+      lookup_kernel<0, kBwd, PF_DIV_IEEE><<<grid, kLookupThreads, smem, st>>>(p);
+  }
   return check_launch(who);
 }
 
@@ -329,7 +407,7 @@ int rotate_forward(int batch, int h, int w, int num_levels, int radius, int div_
   rp.out = out;
   rp.draw = nullptr;
   dim3 grid(ceil_div(rp.N, kRotPixels), rp.L, rp.B);
-  rotate_kernel<false><<<grid, kRotThreads, (size_t)rp.K2 * 33 * sizeof(float), st>>>(rp);
+  rotate_kernel<false><<<grid, kRotThreads, rotate_smem_bytes(rp.K2), st>>>(rp);
   return check_launch("rotate_kernel");
 }
 
@@ -386,7 +464,7 @@ extern "C" int pf_lookup_dual_bwd(const pf_lookup_bwd_args *ba, void *stream) {
     rp.out = const_cast<float *>(ba->grad_other);
     rp.draw = a->scratch;
     dim3 grid(ceil_div(rp.N, kRotPixels), rp.L, rp.B);
-    rotate_kernel<true><<<grid, kRotThreads, (size_t)rp.K2 * 33 * sizeof(float), st>>>(rp);
+    rotate_kernel<true><<<grid, kRotThreads, rotate_smem_bytes(rp.K2), st>>>(rp);
     if (int e = check_launch("pf_lookup_dual_bwd(rotate)")) return e;
   }
   return launch_lookup<true>(p, a->radius, dual, st, "pf_lookup_dual_bwd");

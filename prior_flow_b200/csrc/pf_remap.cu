@@ -90,11 +90,11 @@ __global__ void __launch_bounds__(kRemapThreads) remap_kernel(const RemapParams 
   const Taps4 t = clamp_taps(make_taps(to_sample_coord(x, p.axW, p.div_mode), to_sample_coord(y, p.axH, p.div_mode)),
                              p.H, p.W);
   const long long plane = (long long)p.H * p.W;
-  const float *src = p.src + ((long long)b * p.C + c0) * plane;
-  float *out = p.out + ((long long)b * p.C + c0) * p.P + pix;
+  const float *src = opaque(p.src + ((long long)b * p.C + c0) * plane);
+  float *out = opaque(p.out + ((long long)b * p.C + c0) * p.P + pix);
   const int cn = min(kRemapChannelsPerThread, p.C - c0);
 #pragma unroll 8
-  for (int c = 0; c < cn; ++c) out[(long long)c * p.P] = blend4(src + c * plane, t);
+  for (int c = 0; c < cn; ++c, src += plane, out += p.P) *out = blend4(src, t);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -204,10 +204,10 @@ __global__ void __launch_bounds__(kWgcWarps * 32) warp_groupcorr_kernel(
     const float y = __ldg(coords + 2LL * b * HW + HW + pix);
     const Taps4 t = clamp_taps(make_taps(to_sample_coord(x, axW, div_mode), to_sample_coord(y, axH, div_mode)), H, W);
     const long long c0 = (long long)b * C + g * cpg + warp * cpw;
-    const float *p1 = f1 + c0 * HW + pix;
-    const float *p2 = f2 + c0 * HW;
+    const float *p1 = opaque(f1 + c0 * HW + pix);
+    const float *p2 = opaque(f2 + c0 * HW);
 #pragma unroll 8
-    for (int c = 0; c < cpw; ++c) acc = __fmaf_rn(__ldg(p1 + (long long)c * HW), blend4(p2 + (long long)c * HW, t), acc);
+    for (int c = 0; c < cpw; ++c, p1 += HW, p2 += HW) acc = __fmaf_rn(__ldg(p1), blend4(p2, t), acc);
   }
   part[warp][lane] = acc;
   __syncthreads();

@@ -55,7 +55,9 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     g = torch.Generator(device="cuda").manual_seed(0)
     fm = [torch.randn(B, C, h, w, device="cuda", generator=g) * 1.45 for _ in range(4)]
-    coords = TO.coords_grid(B, h, w, "cuda") + torch.randn(B, 2, h, w, device="cuda", generator=g) * 5
+    # a smooth flow field (low-resolution noise, bicubically upsampled, ~5 px): neighbouring pixels move together
+    low = torch.randn(B, 2, h // 8, w // 8, device="cuda", generator=g) * 5
+    coords = TO.coords_grid(B, h, w, "cuda") + torch.nn.functional.interpolate(low, size=(h, w), mode="bicubic", align_corners=True)
     Ra, Rb = TO.rotation_matrix([0., 0., -np.pi / 2], device="cuda"), TO.rotation_matrix([0., 0., np.pi / 2], device="cuda")
     gw = ops.samplegrid((1, 3, h, w), Ra.T.contiguous())
     gc = ops.samplegrid((1, 3, h, w), Rb)

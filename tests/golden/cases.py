@@ -69,7 +69,9 @@ def seeded_state_dict(template):
     """Deterministic parameters for the end-to-end golden: every tensor of `template` (a state_dict: name -> tensor
     with the reference's names/shapes) is filled from a numpy stream seeded by crc32(name), so the reference model
     (build container, CPU) and prior_flow_b200.model.PriOrRAFT (GPU box) get bit-identical weights without
-    shipping a 33 MB checkpoint.  Conv weights ~ N(0, 2/fan_in); biases ~ N(0, 0.01^2); norm weights ~ 1."""
+    shipping a 33 MB checkpoint.  Conv weights ~ N(0, 1/(3 fan_in)) — the variance of PyTorch's default conv init,
+    which keeps the recurrent update well conditioned (a 2/fan_in init makes the random network chaotic: a 1e-6
+    perturbation of the volume grows to 2 px after 12 iterations, measured); biases ~ N(0, 0.01^2); norm weights ~ 1."""
     import zlib
     import torch
     out = {}
@@ -85,7 +87,7 @@ def seeded_state_dict(template):
             out[name] = torch.from_numpy((1.0 + 0.1 * rs.rand(*shape)).astype(F))
         elif len(shape) >= 2:
             fan_in = int(np.prod(shape[1:]))
-            out[name] = torch.from_numpy((rs.randn(*shape) * np.sqrt(2.0 / fan_in)).astype(F))
+            out[name] = torch.from_numpy((rs.randn(*shape) * np.sqrt(1.0 / (3.0 * fan_in))).astype(F))
         elif name.endswith("weight"):
             out[name] = torch.from_numpy((1.0 + 0.05 * rs.randn(*shape)).astype(F))
         else:

@@ -108,12 +108,13 @@ def main():
     model.load_state_dict(cases.seeded_state_dict(model.state_dict()), strict=True)
     im1, im2 = (T(x) for x in cases.e2e_images())
     flow4 = model(im1, im2, iters=4, test_mode=True)
+    flow12 = model(im1, im2, iters=12, test_mode=True)
     init = T(cases.flow(seed=9, B=1, sigma=2.0))
     flow_init = model(im1, im2, iters=2, init_flow=init, test_mode=True)
     model.train()  # BatchNorm in cnet uses batch statistics; predictions for every iteration, both views
     model.freeze_bn()
     pa, pb = model(im1, im2, iters=2)
-    save("e2e.npz", flow4=N(flow4), flow_init=N(flow_init), train_A1=N(pa[1]), train_B1=N(pb[1]))
+    save("e2e.npz", flow4=N(flow4), flow12=N(flow12), flow_init=N(flow_init), train_A1=N(pa[1]), train_B1=N(pb[1]))
     print("golden files written to", HERE)
 
 

@@ -37,10 +37,12 @@ def test_flow_matches_reference_golden(models, volume_mode, tol):
     g = golden("e2e")
     with torch.no_grad():
         flow = ours(im1, im2, iters=4, test_mode=True)
+        flow12 = ours(im1, im2, iters=12, test_mode=True)
         flow_init = ours(im1, im2, iters=2, init_flow=torch.from_numpy(cases.flow(seed=9, B=1, sigma=2.0)).cuda(), test_mode=True)
     ours.volume_mode = None
     assert flow.shape == g["flow4"].shape
     assert mean_epe(flow.cpu().numpy(), g["flow4"]) < tol
+    assert mean_epe(flow12.cpu().numpy(), g["flow12"]) < tol
     assert mean_epe(flow_init.cpu().numpy(), g["flow_init"]) < tol
 
 
@@ -106,4 +108,4 @@ def test_training_step_backward_runs_and_matches_eager(models):
         m.eval()
     for ga, gb in zip(*grads):
         assert np.isfinite(ga).all()
-        assert np.abs(ga - gb).max() / np.abs(gb).max() < 1e-3
+        assert np.abs(ga - gb).max() / np.abs(gb).max() < 5e-3   # atomics + cuDNN sampler in the eager path (see test_gpu_torch_parity)
