@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 1
+#define PF_ABI_VERSION 2
 #define PF_MAX_LEVELS 4
 
 /* `tensor / python_scalar`: IEEE division on CPU, multiply by fp32 reciprocal in ATen's CUDA
@@ -43,7 +43,7 @@ enum pf_volume_mode {
 
 int pf_abi_version(void);
 const char *pf_last_error(void);
-/* Compile-time facts of the build: "sm_100a;tcgen05;tma;abi=1". */
+/* Compile-time facts of the build: "sm_100a;tcgen05;tma;abi=2". */
 const char *pf_build_info(void);
 
 /* ------------------------------------------------------------------------------------------------
@@ -94,6 +94,9 @@ typedef struct pf_lookup_args {
   float *scratch;                      /* [B, L*(2r+1)^2, h, w] pre-rotation map (caller-owned)   */
   float *dbg_own_xy;                   /* optional [B*h*w, L, (2r+1)^2, 2] unnormalised (ix, iy)  */
   float *dbg_other_xy;                 /* optional, same shape, orthogonal branch                 */
+  int out_channels_last;               /* 1: out_own / out_other are [B, h, w, L*(2r+1)^2]        */
+  int fuse_sum;                        /* 1: out_own = own + other (core/prior_raft.py:187-188),  */
+                                       /*    out_other is not written (may be NULL)               */
 } pf_lookup_args;
 int pf_lookup_dual(const pf_lookup_args *args, void *stream);
 

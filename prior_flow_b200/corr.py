@@ -101,6 +101,17 @@ class DCCL:
         return ops.lookup_autograd(coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x,
                                    self.radius, cyclic=True)
 
+    def summed(self, coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x,
+               channels_last: bool = False):
+        """`corr_own + corr_other` as `PriOr_RAFT.forward` forms it right after the call (core/prior_raft.py:185-188),
+        with the add fused into the rotate kernel; optionally in torch.channels_last memory format."""
+        coords = coords.float()
+        if isinstance(corr_pyramid_A, FeaturePyramid):
+            a, b = self(coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x)
+            return a + b
+        return ops.lookup_autograd(coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x,
+                                   self.radius, cyclic=True, channels_last=channels_last, fuse_sum=True)
+
 
 class CorrBlock:
     """Plain RAFT correlation block — core/corr.py:13-61 (dead code in PriOr_RAFT.forward, kept for the signature)."""

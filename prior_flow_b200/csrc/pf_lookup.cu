@@ -9,14 +9,17 @@
 //     a tap is then two 16-byte table reads, four adds and four multiplies away from its loads.
 //     Instruction issue — not memory — limited the earlier versions (ncu r01a: 76 % issue-slot
 //     utilisation at 13 % DRAM; r01b: 25 instructions per load, half of them integer address math).
-//   * Branch 0 (own view): taps are ordered y-major across lanes (x fastest), so a warp-wide load
-//     touches ~4 rows of <=10 contiguous floats of the query's private plane; L1 serves the
-//     four-corner overlap and every DRAM sector is fetched once.  Results are transposed through
-//     shared memory and written as full 128-byte rows of the [B, L*81, h, w] output.
-//   * Branch 1 (other view): the window is mapped through the LEVEL-0 rotation grid (8 L1-resident
-//     loads), then pyr_other[l][n] is sampled at the mapped point (scale mixing is the
-//     reference's).  The pre-rotation map goes to `scratch` CHANNELS-LAST
-//     ([B, N, L*81]) so that rotate_kernel reads whole 1296-byte vectors.
+//   * The (k+1)^2 footprint the window touches — of the query's private plane (own view) or of the
+//     two channels of the level-0 rotation grid (other view) — is staged in shared memory with
+//     cooperative loads (one warp-wide load = ~3 coalesced row segments) whenever consecutive
+//     window cells share a corner (always, except across the x seam); taps then blend from smem.
+//   * Branch 0 (own view): the blend is the result.  NCHW output goes through a shared-memory
+//     transpose and is written as full 128-byte rows; channels-last output is written directly.
+//   * Branch 1 (other view): the blend of the grid is the mapped point; pyr_other[l][n] is sampled
+//     there (scale mixing is the reference's) with an interior fast path
+//     (one base pointer, immediate offsets) and no loads at all for taps entirely outside the
+//     plane.  The pre-rotation map goes to `scratch` CHANNELS-LAST ([B, N, L*81]) so that
+//     rotate_kernel reads whole 1296-byte vectors.
 // rotate_kernel — img_rotate(., grid_c2w) of that map (core/corr.py:137-138): a cross-pixel
 //   gather, hence a second pass; 32 output pixels x one level per CTA, lanes across channels, four
 //   coalesced vector reads per pixel (the 10.6 MB intermediate stays in L2), shared-memory
@@ -33,7 +36,7 @@ constexpr int kQueriesPerWarp = kQueriesPerCta / (kLookupThreads / 32);
 
 struct LookupParams {
   int B, N, h, w;  // query grid, N = h*w
-  int radius, L, cyclic, div_mode, dual;
+  int radius, L, cyclic, div_mode, dual, channels_last, fuse_sum;
   const float *coords;
   const float *own[PF_MAX_LEVELS];
   const float *other[PF_MAX_LEVELS];
@@ -42,7 +45,7 @@ struct LookupParams {
   Axis ax_gw, ax_gh;  // axes of the rotation grid (query resolution)
   const float *grid_w2c;
   long long grid_bs;
-  float *out_own;                      // forward: [B, L*K2, N] output.  backward: incoming gradient (read only)
+  float *out_own;                      // forward: [B, L*K2, N] (or channels-last [B, N, L*K2]) output.  backward: incoming gradient
   float *raw;                          // forward: [B, N, L*K2] pre-rotation map.  backward: its gradient (read only)
   float *dbg_own, *dbg_other;
   float *d_own[PF_MAX_LEVELS];         // backward: gradient pyramids (+=)
@@ -90,21 +93,32 @@ __device__ __forceinline__ AxisEntry make_axis_entry(float s, int size, int stri
   return e;
 }
 
-template <int R, bool kBwd, int kDiv>
-__global__ void __launch_bounds__(kLookupThreads, 5) lookup_kernel(const LookupParams p) {
+// Per-warp shared-memory scratch of lookup_kernel (sizes for window edge k = 2r+1):
+//   T   [32] AxisEntry     one entry per window column (lanes 0..k-1) and row (lanes k..2k-1)
+//   pos [2][16] int        the k+1 distinct x (resp. y*stride) offsets of the footprint
+//   fp  [2][(k+1)(k+2)]    the staged (k+1)^2 footprint of the plane (own view) or of both grid channels (other view)
+//   dbg [32] float         sample coordinates for the debug dump
+__host__ __device__ constexpr int lookup_fp_floats(int k) { return (k + 1) * (k + 2); }
+__host__ __device__ constexpr int lookup_warp_floats(int k) { return 32 * 4 + 32 + 2 * lookup_fp_floats(k) + 32; }
+
+template <int R, bool kBwd, int kDiv, int BRANCH>
+__device__ __forceinline__ void lookup_body(const LookupParams &p, const int lvl) {
+  constexpr int branch = BRANCH;
   const int r = (R > 0) ? R : p.radius;
   const int k = 2 * r + 1;
   const int K2 = k * k;
-  constexpr int kRounds = (R > 0) ? ((2 * R + 1) * (2 * R + 1) + 31) / 32 : 8;  // radius <= 7 -> <= 225 taps
+  const int k1 = k + 1, pitch = k + 2, FP = k1 * k1;
+  constexpr int kRounds = (R > 0) ? ((2 * R + 1) * (2 * R + 1) + 31) / 32 : 8;     // radius <= 7 -> <= 225 taps
+  constexpr int kFpRounds = (R > 0) ? ((2 * R + 2) * (2 * R + 2) + 31) / 32 : 8;   // <= 256 footprint cells
   extern __shared__ float4 smem4[];
-  // [8 warps][2 buffers][32] axis entries, then the [K2][33] transpose tile (own-view branch only)
-  AxisEntry *tab = reinterpret_cast<AxisEntry *>(smem4) + (threadIdx.x >> 5) * 64;
-  float *tile = reinterpret_cast<float *>(smem4 + (kLookupThreads / 32) * 64);
-  float *dbg_tab = tile + K2 * 33 + (threadIdx.x >> 5) * 32;   // sample coordinates for the debug dump
-  const int lvl = blockIdx.y % p.L;
-  const int branch = blockIdx.y / p.L;
-  const int b = blockIdx.z;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
+  float *wbase = reinterpret_cast<float *>(smem4) + warp * lookup_warp_floats(k);
+  AxisEntry *T = reinterpret_cast<AxisEntry *>(wbase);
+  int *pos = reinterpret_cast<int *>(wbase + 128);
+  float *fp = wbase + 160;
+  float *dbg_tab = fp + 2 * lookup_fp_floats(k);
+  float *tile = reinterpret_cast<float *>(smem4) + (kLookupThreads / 32) * lookup_warp_floats(k);  // [K2][33], NCHW own view
+  const int b = blockIdx.z;
   const int n0 = blockIdx.x * kQueriesPerCta;
   const int Hl = p.Hl[lvl], Wl = p.Wl[lvl];
   const Axis axW = p.axW[lvl], axH = p.axH[lvl];
@@ -113,9 +127,10 @@ __global__ void __launch_bounds__(kLookupThreads, 5) lookup_kernel(const LookupP
   const float *gridx = opaque(p.grid_w2c + (long long)b * p.grid_bs);
   const float *gridy = opaque(gridx + p.N);
   float *dbg = branch ? p.dbg_other : p.dbg_own;
+  const bool use_tile = !branch && !p.channels_last;   // compile-time false for the other view
   float *io = p.out_own + ((long long)b * p.L + lvl) * K2 * (long long)p.N + n0;
-  if constexpr (kBwd) {  // own branch: stage the incoming gradient tile [K2][32 queries], coalesced rows
-    if (branch == 0) {
+  if constexpr (kBwd) {  // NCHW own branch: stage the incoming gradient tile [K2][32 queries], coalesced rows
+    if (use_tile) {
       if (n0 + lane < p.N)
         for (int ch = warp; ch < K2; ch += kLookupThreads / 32) tile[ch * 33 + lane] = io[(long long)ch * p.N + lane];
       __syncthreads();
@@ -128,8 +143,10 @@ __global__ void __launch_bounds__(kLookupThreads, 5) lookup_kernel(const LookupP
   const int size1 = branch ? (is_x ? p.w : p.h) : (is_x ? Wl : Hl);
   const int stride1 = is_x ? 1 : (branch ? p.w : Wl);
   const bool wrap1 = is_x && (branch || p.cyclic);
-  // tap -> (window column a, window row b, output channel), fixed per lane and round.
-  // own view: lanes walk x fastest (coalesced plane rows); other view: lanes walk the output channel.
+  const bool chain_lane = lane < 2 * k;
+  const bool has_next = chain_lane && lane != k - 1 && lane != 2 * k - 1;   // the next lane holds the next cell of my axis
+  // tap -> (window column a, window row b): fixed per lane and round.
+  // own view: lanes walk x fastest (coalesced rows); other view: lanes walk the output channel.
   int t_a[kRounds], t_b[kRounds];
 #pragma unroll
   for (int it = 0; it < kRounds; ++it) {
@@ -139,28 +156,73 @@ __global__ void __launch_bounds__(kLookupThreads, 5) lookup_kernel(const LookupP
     t_a[it] = branch ? hi : lo;
     t_b[it] = branch ? lo : hi;
   }
+  // footprint cell -> (row, column), fixed per lane and round
+  int f_rc[kFpRounds];
+#pragma unroll
+  for (int j = 0; j < kFpRounds; ++j) {
+    const int i = j * 32 + lane;
+    const int ii = i < FP ? i : 0;
+    const int rr = ii / k1;
+    f_rc[j] = (rr << 8) | (ii - rr * k1);
+  }
+
+  const int plane_sz = Hl * Wl;
+  const int q0 = warp * kQueriesPerWarp;
+  const long long nq0 = (long long)b * p.N + n0 + q0;   // first (batch, query) row of this warp
+  const float *coord_ptr = opaque(p.coords + ((long long)b * 2 + (is_x ? 0 : 1)) * p.N + n0 + q0);
+  const float *plane_it = kBwd ? nullptr : opaque(vol + nq0 * plane_sz);
+  float *dplane_it = kBwd ? opaque((branch ? p.d_other[lvl] : p.d_own[lvl]) + nq0 * plane_sz) : nullptr;
+  float *out_it = opaque((branch ? p.raw : p.out_own) + (nq0 * p.L + lvl) * K2);   // channels-last row of this query
+  const bool has_dbg = dbg != nullptr;
 
 #pragma unroll 1
   for (int qi = 0; qi < kQueriesPerWarp; ++qi) {
-    const int q = warp * kQueriesPerWarp + qi;
+    const int q = q0 + qi;
     const int n = n0 + q;
     if (n >= p.N) break;
-    AxisEntry *T = tab + (qi & 1) * 32;
+    // ---- (1) core/corr.py:123-126 + the sampler's coordinate chain, once per window row / column
+    bool fast;
     {
-      // core/corr.py:123-126 then the sampler's coordinate chain, once per window row / column
-      const float c = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + (is_x ? 0 : 1)) * p.N + n), inv_scale);
+      const float c = __fmul_rn(__ldg(coord_ptr + qi), inv_scale);
       float pc = __fadd_rn(c, off);
       if (wrap1) pc = remainder_pos(pc, ax1.size);
       const float sc = sample_coord<kDiv>(pc, ax1);
-      T[lane] = make_axis_entry(sc, size1, stride1);
-      if (dbg != nullptr) dbg_tab[lane] = sc;
+      const AxisEntry e = make_axis_entry(sc, size1, stride1);
+      T[lane] = e;
+      if (chain_lane) {
+        pos[(is_x ? 0 : 16) + (is_x ? lane : lane - k)] = e.o0;
+        if (!has_next) pos[(is_x ? 0 : 16) + k] = e.o1;
+      }
+      if (has_dbg) dbg_tab[lane] = sc;
+      // the footprint is a (k+1)^2 lattice iff consecutive cells share a corner (false across the seam)
+      const int next_o0 = __shfl_down_sync(0xffffffffu, e.o0, 1);
+      fast = !kBwd && __all_sync(0xffffffffu, !has_next || e.o1 == next_o0);
     }
     __syncwarp();
-    const long long plane_off = ((long long)b * p.N + n) * (long long)(Hl * Wl);
-    const float *plane = kBwd ? nullptr : opaque(vol + plane_off);
-    float *dplane = kBwd ? opaque((branch ? p.d_other[lvl] : p.d_own[lvl]) + plane_off) : nullptr;
-    float *rawq = opaque(p.raw + (((long long)b * p.N + n) * p.L + lvl) * K2);
-
+    const float *plane = plane_it;
+    float *dplane = dplane_it;
+    float *outq = out_it;
+    plane_it += plane_sz;
+    dplane_it += plane_sz;
+    out_it += p.L * K2;
+    // ---- (2) stage the footprint with cooperative loads (coalesced row segments of the plane / of the grid)
+    if (fast) {
+#pragma unroll
+      for (int j = 0; j < kFpRounds; ++j) {
+        if (j * 32 < FP && j * 32 + lane < FP) {
+          const int rr = f_rc[j] >> 8, cc = f_rc[j] & 255;
+          const int o = pos[16 + rr] + pos[cc];
+          if (branch) {
+            fp[rr * pitch + cc] = __ldg(gridx + o);
+            fp[lookup_fp_floats(k) + rr * pitch + cc] = __ldg(gridy + o);
+          } else {
+            fp[rr * pitch + cc] = __ldg(plane + o);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // ---- (3) taps
 #pragma unroll
     for (int it = 0; it < kRounds; ++it) {
       if (it * 32 >= K2) break;
@@ -168,47 +230,83 @@ __global__ void __launch_bounds__(kLookupThreads, 5) lookup_kernel(const LookupP
         const int aa = t_a[it], bb = t_b[it];
         const int ch = aa * k + bb;  // x-major channel order of the reference
         const AxisEntry ex = T[aa], ey = T[k + bb];
-        int o_nw = ey.o0 + ex.o0, o_ne = ey.o0 + ex.o1, o_sw = ey.o1 + ex.o0, o_se = ey.o1 + ex.o1;
         float w_nw = __fmul_rn(ex.w0, ey.w0), w_ne = __fmul_rn(ex.w1, ey.w0);
         float w_sw = __fmul_rn(ex.w0, ey.w1), w_se = __fmul_rn(ex.w1, ey.w1);
-        float ix = 0.f, iy = 0.f;
-        if (branch) {
+        float ix = 0.f, iy = 0.f, val = 0.f;
+        if constexpr (!branch) {
+          if constexpr (kBwd) {
+            const float g = use_tile ? tile[ch * 33 + q] : __ldg(outq + ch);
+            if (w_nw != 0.f) atomicAdd(dplane + ey.o0 + ex.o0, g * w_nw);
+            if (w_ne != 0.f) atomicAdd(dplane + ey.o0 + ex.o1, g * w_ne);
+            if (w_sw != 0.f) atomicAdd(dplane + ey.o1 + ex.o0, g * w_sw);
+            if (w_se != 0.f) atomicAdd(dplane + ey.o1 + ex.o1, g * w_se);
+          } else if (fast) {
+            const float *f = fp + bb * pitch + aa;
+            val = __fmul_rn(f[0], w_nw);
+            val = __fmaf_rn(f[1], w_ne, val);
+            val = __fmaf_rn(f[pitch], w_sw, val);
+            val = __fmaf_rn(f[pitch + 1], w_se, val);
+          } else {
+            val = __fmul_rn(__ldg(plane + ey.o0 + ex.o0), w_nw);
+            val = __fmaf_rn(__ldg(plane + ey.o0 + ex.o1), w_ne, val);
+            val = __fmaf_rn(__ldg(plane + ey.o1 + ex.o0), w_sw, val);
+            val = __fmaf_rn(__ldg(plane + ey.o1 + ex.o1), w_se, val);
+          }
+        } else {
           // core/corr.py:132-136 — map through the level-0 rotation grid, then index the level-l volume
-          float sx = __fmul_rn(__ldg(gridx + o_nw), w_nw), sy = __fmul_rn(__ldg(gridy + o_nw), w_nw);
-          sx = __fmaf_rn(__ldg(gridx + o_ne), w_ne, sx);
-          sy = __fmaf_rn(__ldg(gridy + o_ne), w_ne, sy);
-          sx = __fmaf_rn(__ldg(gridx + o_sw), w_sw, sx);
-          sy = __fmaf_rn(__ldg(gridy + o_sw), w_sw, sy);
-          sx = __fmaf_rn(__ldg(gridx + o_se), w_se, sx);
-          sy = __fmaf_rn(__ldg(gridy + o_se), w_se, sy);
+          float sx, sy;
+          if (fast) {
+            const float *f = fp + bb * pitch + aa, *g = f + lookup_fp_floats(k);
+            sx = __fmul_rn(f[0], w_nw), sy = __fmul_rn(g[0], w_nw);
+            sx = __fmaf_rn(f[1], w_ne, sx), sy = __fmaf_rn(g[1], w_ne, sy);
+            sx = __fmaf_rn(f[pitch], w_sw, sx), sy = __fmaf_rn(g[pitch], w_sw, sy);
+            sx = __fmaf_rn(f[pitch + 1], w_se, sx), sy = __fmaf_rn(g[pitch + 1], w_se, sy);
+          } else {
+            const int o_nw = ey.o0 + ex.o0, o_ne = ey.o0 + ex.o1, o_sw = ey.o1 + ex.o0, o_se = ey.o1 + ex.o1;
+            sx = __fmul_rn(__ldg(gridx + o_nw), w_nw), sy = __fmul_rn(__ldg(gridy + o_nw), w_nw);
+            sx = __fmaf_rn(__ldg(gridx + o_ne), w_ne, sx), sy = __fmaf_rn(__ldg(gridy + o_ne), w_ne, sy);
+            sx = __fmaf_rn(__ldg(gridx + o_sw), w_sw, sx), sy = __fmaf_rn(__ldg(gridy + o_sw), w_sw, sy);
+            sx = __fmaf_rn(__ldg(gridx + o_se), w_se, sx), sy = __fmaf_rn(__ldg(gridy + o_se), w_se, sy);
+          }
           ix = sample_coord<kDiv>(remainder_pos(sx, axW.size), axW);
           iy = sample_coord<kDiv>(sy, axH);
-          const AxisEntry fx = make_axis_entry(ix, Wl, 1), fy = make_axis_entry(iy, Hl, Wl);
-          o_nw = fy.o0 + fx.o0, o_ne = fy.o0 + fx.o1, o_sw = fy.o1 + fx.o0, o_se = fy.o1 + fx.o1;
-          w_nw = __fmul_rn(fx.w0, fy.w0), w_ne = __fmul_rn(fx.w1, fy.w0);
-          w_sw = __fmul_rn(fx.w0, fy.w1), w_se = __fmul_rn(fx.w1, fy.w1);
-        }
-        if constexpr (kBwd) {
-          const float g = branch ? __ldg(rawq + ch) : tile[ch * 33 + q];
-          if (w_nw != 0.f) atomicAdd(dplane + o_nw, g * w_nw);
-          if (w_ne != 0.f) atomicAdd(dplane + o_ne, g * w_ne);
-          if (w_sw != 0.f) atomicAdd(dplane + o_sw, g * w_sw);
-          if (w_se != 0.f) atomicAdd(dplane + o_se, g * w_se);
-        } else {
-          // a tap that falls entirely outside the plane (most of levels 2-3 of the orthogonal branch, whose
-          // level-0-unit coordinates index a 16x32 / 8x16 plane) contributes an exact 0: skip its DRAM round trip
-          float val = 0.f;
-          if (!branch || fmaxf(fmaxf(w_nw, w_ne), fmaxf(w_sw, w_se)) > 0.f) {
-            val = __fmul_rn(__ldg(plane + o_nw), w_nw);
-            val = __fmaf_rn(__ldg(plane + o_ne), w_ne, val);
-            val = __fmaf_rn(__ldg(plane + o_sw), w_sw, val);
-            val = __fmaf_rn(__ldg(plane + o_se), w_se, val);
+          const float fx = floorf(ix), fy = floorf(iy);
+          const int x0 = (int)fx, y0 = (int)fy;
+          if (!kBwd && (unsigned)x0 < (unsigned)(Wl - 1) && (unsigned)y0 < (unsigned)(Hl - 1)) {
+            // interior: all four taps valid, one base pointer, immediate offsets
+            const float dxw = __fsub_rn(ix, fx), dxe = __fsub_rn(__fadd_rn(fx, 1.f), ix);
+            const float dyn = __fsub_rn(iy, fy), dys = __fsub_rn(__fadd_rn(fy, 1.f), iy);
+            const float *s0 = plane + (y0 * Wl + x0), *s1 = s0 + Wl;
+            val = __fmul_rn(__ldg(s0), __fmul_rn(dxe, dys));
+            val = __fmaf_rn(__ldg(s0 + 1), __fmul_rn(dxw, dys), val);
+            val = __fmaf_rn(__ldg(s1), __fmul_rn(dxe, dyn), val);
+            val = __fmaf_rn(__ldg(s1 + 1), __fmul_rn(dxw, dyn), val);
+          } else if (x0 >= -1 && x0 < Wl && y0 >= -1 && y0 < Hl) {
+            // straddles the border (a tap entirely outside the plane is an exact 0 and needs no DRAM round trip:
+            // most of levels 2-3 here, whose level-0-unit coordinates index a 16x32 / 8x16 plane)
+            const AxisEntry gx = make_axis_entry(ix, Wl, 1), gy = make_axis_entry(iy, Hl, Wl);
+            const float v_nw = __fmul_rn(gx.w0, gy.w0), v_ne = __fmul_rn(gx.w1, gy.w0);
+            const float v_sw = __fmul_rn(gx.w0, gy.w1), v_se = __fmul_rn(gx.w1, gy.w1);
+            if constexpr (kBwd) {
+              const float g = __ldg(outq + ch);
+              if (v_nw != 0.f) atomicAdd(dplane + gy.o0 + gx.o0, g * v_nw);
+              if (v_ne != 0.f) atomicAdd(dplane + gy.o0 + gx.o1, g * v_ne);
+              if (v_sw != 0.f) atomicAdd(dplane + gy.o1 + gx.o0, g * v_sw);
+              if (v_se != 0.f) atomicAdd(dplane + gy.o1 + gx.o1, g * v_se);
+            } else {
+              val = __fmul_rn(__ldg(plane + gy.o0 + gx.o0), v_nw);
+              val = __fmaf_rn(__ldg(plane + gy.o0 + gx.o1), v_ne, val);
+              val = __fmaf_rn(__ldg(plane + gy.o1 + gx.o0), v_sw, val);
+              val = __fmaf_rn(__ldg(plane + gy.o1 + gx.o1), v_se, val);
+            }
           }
-          if (branch)
-            rawq[ch] = val;
-          else
+        }
+        if constexpr (!kBwd) {
+          if (use_tile)
             tile[ch * 33 + q] = val;
-          if (dbg != nullptr) {
+          else
+            outq[ch] = val;
+          if (has_dbg) {
             if (!branch) {
               ix = dbg_tab[aa];
               iy = dbg_tab[k + bb];
@@ -220,10 +318,10 @@ __global__ void __launch_bounds__(kLookupThreads, 5) lookup_kernel(const LookupP
         }
       }
     }
-    if (dbg != nullptr) __syncwarp();   // dbg_tab is single-buffered
+    __syncwarp();   // T / pos / fp are reused by the next query
   }
   if constexpr (!kBwd) {
-    if (branch == 0) {
+    if (use_tile) {
       __syncthreads();
       if (n0 + lane < p.N)
         for (int ch = warp; ch < K2; ch += kLookupThreads / 32) io[(long long)ch * p.N + lane] = tile[ch * 33 + lane];
@@ -231,30 +329,108 @@ __global__ void __launch_bounds__(kLookupThreads, 5) lookup_kernel(const LookupP
   }
 }
 
+template <int R, bool kBwd, int kDiv>
+__global__ void __launch_bounds__(kLookupThreads, 4) lookup_kernel(const LookupParams p) {
+  // one launch serves both views; each CTA runs the body specialised for its branch
+  if (blockIdx.y < p.L)
+    lookup_body<R, kBwd, kDiv, 0>(p, blockIdx.y);
+  else
+    lookup_body<R, kBwd, kDiv, 1>(p, blockIdx.y - p.L);
+}
+
 // ------------------------------------------------------------------------------------------------
 // img_rotate of the channels-last pre-rotation map: out[b, c, p] = sum_t w_t(p) raw[b, src_t(p), c].
 constexpr int kRotThreads = 256;
-constexpr int kRotPixels = 32;
+constexpr int kRotPixels = 32;     // backward / scalar kernel
+constexpr int kRotFwdPixels = 8;   // forward float4 kernel: one pixel per warp, 1024 CTAs at 64x128
 
 struct RotateParams {
-  int B, N, h, w, L, K2, div_mode;
+  int B, N, h, w, L, K2, div_mode, channels_last, fuse_sum;
   Axis axW, axH;
   const float *grid_c2w;
   long long grid_bs;
   const float *raw;   // fwd: [B, N, L*K2] in.   bwd: unused
-  float *out;         // fwd: [B, L*K2, N] out.  bwd: incoming gradient (read only)
+  float *out;         // fwd: out_other (or out_own when fuse_sum), [B, L*K2, N] or channels-last.  bwd: incoming gradient
   float *draw;        // bwd: [B, N, L*K2] (+=)
 };
 
+// Forward: one CTA = 32 output pixels x ALL channels.  The channels-last map makes a pixel's L*K2 floats one
+// contiguous, 16-byte aligned vector, so lanes walk float4s: 4 taps x one LDG.128 per 4 channels (ncu r01d: the
+// scalar per-level version spent 8.3 M instructions on 2.65 M outputs).  NCHW output goes through a shared
+// transpose tile [C][33]; channels-last output (and the fused `own + other` add) is written directly as float4.
+__global__ void __launch_bounds__(kRotThreads) rotate_fwd_kernel(const RotateParams p) {
+  extern __shared__ float tile[];  // [C][kRotFwdPixels + 1] (NCHW only), then one Taps4 per pixel
+  constexpr int kTP = kRotFwdPixels + 1;
+  const int C = p.L * p.K2, C4 = C >> 2;
+  Taps4 *taps = reinterpret_cast<Taps4 *>(tile + (p.channels_last ? 0 : C * kTP + (C & 1)));
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * kRotFwdPixels;
+  if (threadIdx.x < kRotFwdPixels && n0 + threadIdx.x < p.N) {
+    // module-local cyclic sampler of projection_prim_ortho.py:119-135 on the [.., h, w] map
+    const float *gx = p.grid_c2w + (long long)b * p.grid_bs;
+    const int n = n0 + threadIdx.x;
+    const float x = remainder_pos(__ldg(gx + n), p.axW.size);
+    const float y = __ldg(gx + p.N + n);
+    Taps4 t = clamp_taps(make_taps(to_sample_coord(x, p.axW, p.div_mode), to_sample_coord(y, p.axH, p.div_mode)), p.h, p.w);
+    t.o_nw *= C4, t.o_ne *= C4, t.o_sw *= C4, t.o_se *= C4;   // float4 offsets into the channels-last map
+    taps[threadIdx.x] = t;
+  }
+  __syncthreads();
+  const float4 *src = reinterpret_cast<const float4 *>(opaque(p.raw + (long long)b * p.N * C));
+  float4 *out_cl = reinterpret_cast<float4 *>(opaque(p.out + (long long)b * p.N * C));
+#pragma unroll 1
+  for (int qi = 0; qi < kRotFwdPixels / (kRotThreads / 32); ++qi) {
+    const int q = warp * (kRotFwdPixels / (kRotThreads / 32)) + qi;
+    if (n0 + q >= p.N) break;
+    const Taps4 t = taps[q];
+    const float4 *s_nw = src + t.o_nw, *s_ne = src + t.o_ne, *s_sw = src + t.o_sw, *s_se = src + t.o_se;
+    for (int c4 = lane; c4 < C4; c4 += 32) {
+      const float4 a = __ldg(s_nw + c4), bq = __ldg(s_ne + c4), c = __ldg(s_sw + c4), d = __ldg(s_se + c4);
+      float4 r;
+      r.x = __fmaf_rn(d.x, t.se, __fmaf_rn(c.x, t.sw, __fmaf_rn(bq.x, t.ne, __fmul_rn(a.x, t.nw))));
+      r.y = __fmaf_rn(d.y, t.se, __fmaf_rn(c.y, t.sw, __fmaf_rn(bq.y, t.ne, __fmul_rn(a.y, t.nw))));
+      r.z = __fmaf_rn(d.z, t.se, __fmaf_rn(c.z, t.sw, __fmaf_rn(bq.z, t.ne, __fmul_rn(a.z, t.nw))));
+      r.w = __fmaf_rn(d.w, t.se, __fmaf_rn(c.w, t.sw, __fmaf_rn(bq.w, t.ne, __fmul_rn(a.w, t.nw))));
+      if (p.channels_last) {
+        float4 *o = out_cl + (long long)(n0 + q) * C4 + c4;
+        if (p.fuse_sum) {   // corr_A + corr_B_A (core/prior_raft.py:187)
+          const float4 own = *o;
+          r.x = __fadd_rn(own.x, r.x), r.y = __fadd_rn(own.y, r.y), r.z = __fadd_rn(own.z, r.z), r.w = __fadd_rn(own.w, r.w);
+        }
+        *o = r;
+      } else {
+        float *tcol = tile + (c4 * 4) * kTP + q;
+        tcol[0] = r.x, tcol[kTP] = r.y, tcol[2 * kTP] = r.z, tcol[3 * kTP] = r.w;
+      }
+    }
+  }
+  if (!p.channels_last) {
+    __syncthreads();
+    // each channel row of the CTA is kRotFwdPixels consecutive floats (one 32-byte sector)
+    for (int i = threadIdx.x; i < C * kRotFwdPixels; i += kRotThreads) {
+      const int ch = i / kRotFwdPixels, qq = i - ch * kRotFwdPixels;
+      if (n0 + qq < p.N) {
+        float *o = p.out + ((long long)b * C + ch) * p.N + n0 + qq;
+        *o = p.fuse_sum ? __fadd_rn(*o, tile[ch * kTP + qq]) : tile[ch * kTP + qq];
+      }
+    }
+  }
+}
+
+static size_t rotate_fwd_smem_bytes(int C, int channels_last) {
+  return (channels_last ? 0 : ((size_t)C * (kRotFwdPixels + 1) + (C & 1)) * sizeof(float)) + kRotFwdPixels * sizeof(Taps4);
+}
+
 template <bool kBwd>
 __global__ void __launch_bounds__(kRotThreads) rotate_kernel(const RotateParams p) {
-  extern __shared__ float tile[];  // [K2][33] transpose tile, then one Taps4 per pixel
+  extern __shared__ float tile[];  // [K2][33] transpose tile (NCHW only), then one Taps4 per pixel
   Taps4 *taps = reinterpret_cast<Taps4 *>(tile + p.K2 * 33 + (p.K2 & 1));
   const int lvl = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * kRotPixels;
   const int C = p.L * p.K2;
-  float *io = p.out + ((long long)b * C + (long long)lvl * p.K2) * p.N + n0;
+  float *io = p.out + ((long long)b * C + (long long)lvl * p.K2) * p.N + n0;   // NCHW rows
   if (threadIdx.x < kRotPixels && n0 + threadIdx.x < p.N) {
     // module-local cyclic sampler of projection_prim_ortho.py:119-135 on the [.., h, w] map
     const float *gx = p.grid_c2w + (long long)b * p.grid_bs;
@@ -266,21 +442,23 @@ __global__ void __launch_bounds__(kRotThreads) rotate_kernel(const RotateParams 
     taps[threadIdx.x] = t;
   }
   if constexpr (kBwd) {
-    if (n0 + lane < p.N)
+    if (!p.channels_last && n0 + lane < p.N)
       for (int ch = warp; ch < p.K2; ch += kRotThreads / 32) tile[ch * 33 + lane] = io[(long long)ch * p.N + lane];
   }
   __syncthreads();
   const long long base = (long long)b * p.N * C + (long long)lvl * p.K2;
   const float *src = kBwd ? nullptr : opaque(p.raw + base);
   float *dst = kBwd ? opaque(p.draw + base) : nullptr;
+  float *out_cl = opaque(p.out + base);   // channels-last rows: + n * C + ch
 #pragma unroll 1
   for (int qi = 0; qi < kRotPixels / (kRotThreads / 32); ++qi) {
     const int q = warp * (kRotPixels / (kRotThreads / 32)) + qi;
     if (n0 + q >= p.N) break;
     const Taps4 t = taps[q];
+    float *oq = out_cl + (long long)(n0 + q) * C;
     if constexpr (kBwd) {
       for (int ch = lane; ch < p.K2; ch += 32) {
-        const float g = tile[ch * 33 + q];
+        const float g = p.channels_last ? __ldg(oq + ch) : tile[ch * 33 + q];
         if (t.nw != 0.f) atomicAdd(dst + t.o_nw + ch, g * t.nw);
         if (t.ne != 0.f) atomicAdd(dst + t.o_ne + ch, g * t.ne);
         if (t.sw != 0.f) atomicAdd(dst + t.o_sw + ch, g * t.sw);
@@ -293,14 +471,22 @@ __global__ void __launch_bounds__(kRotThreads) rotate_kernel(const RotateParams 
         acc = __fmaf_rn(__ldg(src + t.o_ne + ch), t.ne, acc);
         acc = __fmaf_rn(__ldg(src + t.o_sw + ch), t.sw, acc);
         acc = __fmaf_rn(__ldg(src + t.o_se + ch), t.se, acc);
-        tile[ch * 33 + q] = acc;
+        if (p.channels_last)
+          oq[ch] = p.fuse_sum ? __fadd_rn(oq[ch], acc) : acc;   // corr_A + corr_B_A (core/prior_raft.py:187)
+        else
+          tile[ch * 33 + q] = acc;
       }
     }
   }
   if constexpr (!kBwd) {
-    __syncthreads();
-    if (n0 + lane < p.N)
-      for (int ch = warp; ch < p.K2; ch += kRotThreads / 32) io[(long long)ch * p.N + lane] = tile[ch * 33 + lane];
+    if (!p.channels_last) {
+      __syncthreads();
+      if (n0 + lane < p.N)
+        for (int ch = warp; ch < p.K2; ch += kRotThreads / 32) {
+          float *o = io + (long long)ch * p.N + lane;
+          *o = p.fuse_sum ? __fadd_rn(*o, tile[ch * 33 + lane]) : tile[ch * 33 + lane];
+        }
+    }
   }
 }
 
@@ -324,6 +510,8 @@ static int fill_lookup_params(const pf_lookup_args *a, LookupParams &p, bool dua
   p.cyclic = a->cyclic;
   p.div_mode = a->div_mode;
   p.dual = dual;
+  p.channels_last = a->out_channels_last;
+  p.fuse_sum = a->fuse_sum;
   p.coords = a->coords;
   for (int l = 0; l < PF_MAX_LEVELS; ++l) {
     p.own[l] = l < p.L ? a->own[l] : nullptr;
@@ -358,12 +546,14 @@ static void fill_rotate_params(const pf_lookup_args *a, RotateParams &rp) {
   rp.L = a->num_levels;
   rp.K2 = k * k;
   rp.div_mode = a->div_mode;
+  rp.channels_last = a->out_channels_last;
+  rp.fuse_sum = a->fuse_sum;
   rp.axW = make_axis(a->w);
   rp.axH = make_axis(a->h);
   rp.grid_c2w = a->grid_c2w;
   rp.grid_bs = a->grid_batch_stride;
   rp.raw = a->scratch;
-  rp.out = a->out_other;
+  rp.out = a->fuse_sum ? a->out_own : a->out_other;
   rp.draw = nullptr;
 }
 
@@ -371,7 +561,7 @@ template <bool kBwd>
 static int launch_lookup(const LookupParams &p, int radius, bool dual, cudaStream_t st, const char *who) {
   const int k = 2 * radius + 1, K2 = k * k;
   dim3 grid(ceil_div(p.N, kQueriesPerCta), p.L * (dual ? 2 : 1), p.B);
-  const size_t smem = (size_t)(kLookupThreads / 32) * 64 * sizeof(float4) + ((size_t)K2 * 33 + kLookupThreads) * sizeof(float);
+  const size_t smem = ((size_t)(kLookupThreads / 32) * lookup_warp_floats(k) + (size_t)K2 * 33) * sizeof(float);
   const bool recip = p.div_mode == PF_DIV_ATEN_CUDA;
   if (radius == 4) {
     if (recip)
@@ -389,7 +579,7 @@ static int launch_lookup(const LookupParams &p, int radius, bool dual, cudaStrea
 
 // img_rotate of a channels-last pre-rotation map, shared with the on-the-fly path (pf_onthefly.cu).
 int rotate_forward(int batch, int h, int w, int num_levels, int radius, int div_mode, const float *grid_c2w,
-                   long long grid_bs, const float *raw, float *out, cudaStream_t st) {
+                   long long grid_bs, const float *raw, float *out, int channels_last, int fuse_sum, cudaStream_t st) {
   const int k = 2 * radius + 1;
   RotateParams rp;
   rp.B = batch;
@@ -399,6 +589,8 @@ int rotate_forward(int batch, int h, int w, int num_levels, int radius, int div_
   rp.L = num_levels;
   rp.K2 = k * k;
   rp.div_mode = div_mode;
+  rp.channels_last = channels_last;
+  rp.fuse_sum = fuse_sum;
   rp.axW = make_axis(w);
   rp.axH = make_axis(h);
   rp.grid_c2w = grid_c2w;
@@ -406,7 +598,14 @@ int rotate_forward(int batch, int h, int w, int num_levels, int radius, int div_
   rp.raw = raw;
   rp.out = out;
   rp.draw = nullptr;
-  dim3 grid(ceil_div(rp.N, kRotPixels), rp.L, rp.B);
+  const int C = rp.L * rp.K2;
+  if (C % 4 == 0 && (((uintptr_t)raw | (uintptr_t)out) & 15) == 0) {
+    const size_t smem = rotate_fwd_smem_bytes(C, channels_last);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(rotate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    rotate_fwd_kernel<<<dim3(ceil_div(rp.N, kRotFwdPixels), rp.B), kRotThreads, smem, st>>>(rp);
+    return check_launch("rotate_fwd_kernel");
+  }
+  dim3 grid(ceil_div(rp.N, kRotPixels), rp.L, rp.B);   // odd channel counts: scalar per-level kernel
   rotate_kernel<false><<<grid, kRotThreads, rotate_smem_bytes(rp.K2), st>>>(rp);
   return check_launch("rotate_kernel");
 }
@@ -420,7 +619,7 @@ extern "C" int pf_lookup_dual(const pf_lookup_args *a, void *stream) {
   LookupParams p;
   if (int e = fill_lookup_params(a, p, dual, "pf_lookup_dual")) return e;
   PF_REQUIRE(a->out_own != nullptr, "pf_lookup_dual: out_own is required");
-  PF_REQUIRE(!dual || a->out_other != nullptr, "pf_lookup_dual: out_other is required");
+  PF_REQUIRE(!dual || a->fuse_sum || a->out_other != nullptr, "pf_lookup_dual: out_other is required unless fuse_sum");
   for (int l = 0; l < p.L; ++l) {
     PF_REQUIRE(a->own[l] != nullptr, "pf_lookup_dual: own[%d] is null", l);
     PF_REQUIRE(!dual || a->other[l] != nullptr, "pf_lookup_dual: other[%d] is null", l);
@@ -430,7 +629,8 @@ extern "C" int pf_lookup_dual(const pf_lookup_args *a, void *stream) {
   if (dual) {
     // core/corr.py:137-138 — img_rotate of the [B, L*81, h, w] map with grid_c2w.
     return rotate_forward(a->batch, a->h, a->w, a->num_levels, a->radius, a->div_mode, a->grid_c2w,
-                          a->grid_batch_stride, a->scratch, a->out_other, st);
+                          a->grid_batch_stride, a->scratch, a->fuse_sum ? a->out_own : a->out_other, a->out_channels_last,
+                          a->fuse_sum, st);
   }
   return 0;
 }
@@ -446,6 +646,7 @@ extern "C" int pf_lookup_dual_bwd(const pf_lookup_bwd_args *ba, void *stream) {
   const bool dual = ba->grad_other != nullptr;
   LookupParams p;
   if (int e = fill_lookup_params(a, p, dual, "pf_lookup_dual_bwd")) return e;
+  p.fuse_sum = 0;
   PF_REQUIRE(ba->grad_own != nullptr, "pf_lookup_dual_bwd: grad_own is required");
   for (int l = 0; l < p.L; ++l) {
     PF_REQUIRE(ba->dgrad_own[l] != nullptr, "pf_lookup_dual_bwd: dgrad_own[%d] is null", l);
@@ -462,6 +663,7 @@ extern "C" int pf_lookup_dual_bwd(const pf_lookup_bwd_args *ba, void *stream) {
     const size_t bytes = (size_t)a->batch * rp.L * rp.K2 * rp.N * sizeof(float);
     if (cudaMemsetAsync(a->scratch, 0, bytes, st) != cudaSuccess) return check_launch("pf_lookup_dual_bwd(memset)");
     rp.out = const_cast<float *>(ba->grad_other);
+    rp.fuse_sum = 0;
     rp.draw = a->scratch;
     dim3 grid(ceil_div(rp.N, kRotPixels), rp.L, rp.B);
     rotate_kernel<true><<<grid, kRotThreads, rotate_smem_bytes(rp.K2), st>>>(rp);

@@ -210,11 +210,17 @@ class PriOrRAFT(nn.Module):
         self.args = SimpleNamespace(mixed_precision=mixed_precision, dropout=dropout, corr_levels=4, corr_radius=4)
         self.hidden_dim = self.context_dim = 128
         self.corr_mode, self.volume_mode = corr_mode, volume_mode
+        self.channels_last = False      # set by .to_channels_last(): lookups then emit torch.channels_last tensors
         cor_planes = 4 * 9 * 9
         self.fnet = Encoder(256, "instance", dropout)
         self.cnet = Encoder(256, "batch", dropout)
         self.ODDC = DualUpdateBlock(cor_planes, 128)
         self.update_block = UpdateBlock(cor_planes, 128)
+
+    def to_channels_last(self):
+        """NHWC weights + NHWC lookup outputs: cuDNN's tensor-core kernels run without NCHW<->NHWC conversions."""
+        self.channels_last = True
+        return self.to(memory_format=torch.channels_last)
 
     def freeze_bn(self):
         for m in self.modules():
@@ -277,12 +283,11 @@ class PriOrRAFT(nn.Module):
             flow_B_A = geo.flo_rotate(flow_B, sample_grid_W2C=g["B2A_W2C_8x"], sample_grid_C2W=g["B2A_8x"])
             flaw_B_A = ops.warp_groupcorr_autograd(f1A, f2A, coords0 + flow_B_A, 4)
             with amp():
-                corr_A, corr_B_A = lookup(coords1_A, pyr_A, pyr_B, g["A2B_W2C_8x"], g["B2A_8x"])
-                corr_B, corr_A_B = lookup(coords1_B, pyr_B, pyr_A, g["B2A_W2C_8x"], g["A2B_8x"])
-                net_A, mask_A, d_A = self.ODDC(net_A, inp_A, flow_A, corr_A + corr_B_A, flaw_A, flow_B_A, flaw_B_A,
-                                               want_mask=want_up)
-                net_B, mask_B, d_B = self.update_block(net_B, inp_B, corr_B + corr_A_B, flow_B,
-                                                       want_mask=want_up and not test_mode)
+                # corr_A + corr_B_A and corr_B + corr_A_B (prior_raft.py:185-188), the adds fused into the rotate kernel
+                corr_A = lookup.summed(coords1_A, pyr_A, pyr_B, g["A2B_W2C_8x"], g["B2A_8x"], self.channels_last)
+                corr_B = lookup.summed(coords1_B, pyr_B, pyr_A, g["B2A_W2C_8x"], g["A2B_8x"], self.channels_last)
+                net_A, mask_A, d_A = self.ODDC(net_A, inp_A, flow_A, corr_A, flaw_A, flow_B_A, flaw_B_A, want_mask=want_up)
+                net_B, mask_B, d_B = self.update_block(net_B, inp_B, corr_B, flow_B, want_mask=want_up and not test_mode)
             coords1_A = coords1_A + d_A
             coords1_B = coords1_B + d_B
             if want_up:

@@ -120,11 +120,19 @@ def avg_pool2x2(x: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------ (b)
+def _as_nchw_view(t_cl: torch.Tensor) -> torch.Tensor:
+    """[B,h,w,C] storage -> logical [B,C,h,w] tensor in torch.channels_last memory format (no copy)."""
+    return t_cl.permute(0, 3, 1, 2)
+
+
 def lookup(coords: torch.Tensor, pyr_own: Sequence[torch.Tensor], pyr_other: Optional[Sequence[torch.Tensor]] = None,
            grid_w2c: Optional[torch.Tensor] = None, grid_c2w: Optional[torch.Tensor] = None, radius: int = 4,
-           cyclic: bool = True, debug: bool = False):
+           cyclic: bool = True, debug: bool = False, channels_last: bool = False, fuse_sum: bool = False):
     """Pyramid lookup.  With `pyr_other` + grids: DCCL.__call__ (core/corr.py:113-144) -> (own, other);
     without: the single-view lookup of CorrBlock.__call__ (core/corr.py:30-51) -> own.
+    channels_last=True returns [B,324,h,w] tensors in torch.channels_last memory format (what cuDNN's tensor-core
+    convolutions consume without a layout conversion); fuse_sum=True returns the single tensor own + other
+    (`corr_A + corr_B_A`, core/prior_raft.py:187-188) with the add folded into the rotate kernel.
     debug=True additionally returns the unnormalised sample coordinates [B*h*w, L, k*k, 2] per branch."""
     lib = _lib.load()
     _chk(coords, "coords", 4)
@@ -139,13 +147,17 @@ def lookup(coords: torch.Tensor, pyr_own: Sequence[torch.Tensor], pyr_other: Opt
         if t.numel() != B * h * w * (h2 >> l) * (w2 >> l):
             raise ValueError(f"pyr_own[{l}] has {t.numel()} elements, expected [{B * h * w},1,{h2 >> l},{w2 >> l}]")
     dual = pyr_other is not None
+    if fuse_sum and not dual:
+        raise ValueError("fuse_sum needs the dual lookup")
     K2 = (2 * radius + 1) ** 2
     dev = coords.device
+    shape = (B, h, w, L * K2) if channels_last else (B, L * K2, h, w)
     with torch.cuda.device(dev):
-        out_own = torch.empty((B, L * K2, h, w), device=dev, dtype=torch.float32)
+        out_own = torch.empty(shape, device=dev, dtype=torch.float32)
         a = _lib.LookupArgs()
         a.batch, a.h, a.w, a.h2, a.w2 = B, h, w, h2, w2
         a.radius, a.num_levels, a.cyclic, a.div_mode = radius, L, int(cyclic), _state["div_mode"]
+        a.out_channels_last, a.fuse_sum = int(channels_last), int(fuse_sum)
         a.coords = coords.data_ptr()
         a.own = _lib.level_ptrs(own)
         a.out_own = out_own.data_ptr()
@@ -159,11 +171,13 @@ def lookup(coords: torch.Tensor, pyr_own: Sequence[torch.Tensor], pyr_other: Opt
             if bs_w != bs_c:
                 gw, gc = gw.expand(B, 2, h, w).contiguous(), gc.expand(B, 2, h, w).contiguous()
                 bs_w = gw.stride(0)
-            out_other = torch.empty_like(out_own)
             scratch = torch.empty_like(out_own)
             a.other = _lib.level_ptrs(other)
             a.grid_w2c, a.grid_c2w, a.grid_batch_stride = gw.data_ptr(), gc.data_ptr(), bs_w
-            a.out_other, a.scratch = out_other.data_ptr(), scratch.data_ptr()
+            a.scratch = scratch.data_ptr()
+            if not fuse_sum:
+                out_other = torch.empty_like(out_own)
+                a.out_other = out_other.data_ptr()
         dbg = None
         if debug:
             dbg = [torch.full((B * h * w, L, K2, 2), float("nan"), device=dev) for _ in range(2 if dual else 1)]
@@ -172,7 +186,10 @@ def lookup(coords: torch.Tensor, pyr_own: Sequence[torch.Tensor], pyr_other: Opt
                 a.dbg_other_xy = dbg[1].data_ptr()
         _lib.check(lib.pf_lookup_dual(C.byref(a), _stream()), "pf_lookup_dual")
         _count(2 if dual else 1)
-    res = (out_own, out_other) if dual else out_own
+    if channels_last:
+        out_own = _as_nchw_view(out_own)
+        out_other = _as_nchw_view(out_other) if out_other is not None else None
+    res = (out_own, out_other) if (dual and not fuse_sum) else out_own
     if debug:
         return res, dbg
     return res
@@ -323,8 +340,13 @@ def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence
 
 
 # ------------------------------------------------------------------------------------------ (e)
+def _grad_layout(g: torch.Tensor, channels_last: bool) -> torch.Tensor:
+    """Brings an incoming [B,C,h,w] gradient into the memory layout the backward kernels read."""
+    return g.permute(0, 2, 3, 1).contiguous() if channels_last else g.contiguous()
+
+
 def lookup_backward(coords, grad_own, grad_other, level_shapes, grid_w2c=None, grid_c2w=None, radius=4, cyclic=True,
-                    into_own=None, into_other=None):
+                    into_own=None, into_other=None, channels_last=False):
     """Adjoint of `lookup` w.r.t. the pyramids.  Returns (d_own levels, d_other levels); with `into_*` given the
     gradients are accumulated (+=) into those tensors instead of fresh zero tensors."""
     lib = _lib.load()
@@ -342,14 +364,15 @@ def lookup_backward(coords, grad_own, grad_other, level_shapes, grid_w2c=None, g
         a = ba.fwd
         a.batch, a.h, a.w, a.h2, a.w2 = B, h, w, h2, w2
         a.radius, a.num_levels, a.cyclic, a.div_mode = radius, L, int(cyclic), _state["div_mode"]
+        a.out_channels_last = int(channels_last)
         a.coords = coords.data_ptr()
-        grad_own = _chk(grad_own, "grad_own", 4).contiguous()
+        grad_own = _grad_layout(_chk(grad_own, "grad_own", 4), channels_last)
         ba.grad_own = grad_own.data_ptr()
         ba.dgrad_own = _lib.level_ptrs(d_own)
         if dual:
             d_other = into_other if into_other is not None else [torch.zeros(s, device=dev, dtype=torch.float32)
                                                                  for s in level_shapes]
-            grad_other = _chk(grad_other, "grad_other", 4).contiguous()
+            grad_other = _grad_layout(_chk(grad_other, "grad_other", 4), channels_last)
             gw, bs_w = _grid_arg(grid_w2c, "grid_w2c", B, h, w)
             gc, bs_c = _grid_arg(grid_c2w, "grid_c2w", B, h, w)
             if bs_w != bs_c:
@@ -449,23 +472,26 @@ class _DualLookupFn(torch.autograd.Function):
     """DCCL lookup with gradients to both pyramids (coords and grids carry none, prior_raft.py:171,176)."""
 
     @staticmethod
-    def forward(ctx, coords, grid_w2c, grid_c2w, radius, num_levels, *levels):
+    def forward(ctx, coords, grid_w2c, grid_c2w, radius, num_levels, channels_last, fuse_sum, *levels):
         own, other = levels[:num_levels], levels[num_levels:]
-        out_own, out_other = lookup(coords, own, other, grid_w2c, grid_c2w, radius)
+        out = lookup(coords, own, other, grid_w2c, grid_c2w, radius, channels_last=channels_last, fuse_sum=fuse_sum)
         ctx.save_for_backward(coords, grid_w2c, grid_c2w)
-        ctx.meta = (radius, num_levels, [tuple(t.shape) for t in own])
-        return out_own, out_other
+        ctx.meta = (radius, num_levels, [tuple(t.shape) for t in own], channels_last, fuse_sum)
+        return out
 
     @staticmethod
-    def backward(ctx, g_own, g_other):
+    def backward(ctx, *grads):
         coords, grid_w2c, grid_c2w = ctx.saved_tensors
-        radius, L, shapes = ctx.meta
+        radius, L, shapes, channels_last, fuse_sum = ctx.meta
+        g_own = grads[0]
+        g_other = g_own if fuse_sum else grads[1]      # d(own + other) flows to both branches unchanged
         if g_own is None:
             g_own = torch.zeros((coords.shape[0], L * (2 * radius + 1) ** 2) + tuple(coords.shape[2:]), device=coords.device)
         if g_other is None:
             g_other = torch.zeros_like(g_own)
-        d_own, d_other = lookup_backward(coords, g_own, g_other, shapes, grid_w2c, grid_c2w, radius)
-        return (None, None, None, None, None, *d_own, *d_other)
+        d_own, d_other = lookup_backward(coords, g_own, g_other, shapes, grid_w2c, grid_c2w, radius,
+                                         channels_last=channels_last)
+        return (None, None, None, None, None, None, None, *d_own, *d_other)
 
 
 class _SingleLookupFn(torch.autograd.Function):
@@ -484,14 +510,16 @@ class _SingleLookupFn(torch.autograd.Function):
         return (None, None, None, *d_own)
 
 
-def lookup_autograd(coords, pyr_own, pyr_other=None, grid_w2c=None, grid_c2w=None, radius=4, cyclic=True):
+def lookup_autograd(coords, pyr_own, pyr_other=None, grid_w2c=None, grid_c2w=None, radius=4, cyclic=True,
+                    channels_last=False, fuse_sum=False):
     needs = torch.is_grad_enabled() and any(t.requires_grad for t in list(pyr_own) + list(pyr_other or []))
     if not needs:
-        return lookup(coords, pyr_own, pyr_other, grid_w2c, grid_c2w, radius, cyclic)
+        return lookup(coords, pyr_own, pyr_other, grid_w2c, grid_c2w, radius, cyclic, channels_last=channels_last,
+                      fuse_sum=fuse_sum)
     if pyr_other is None:
         return _SingleLookupFn.apply(coords.detach(), radius, cyclic, *pyr_own)
-    return _DualLookupFn.apply(coords.detach(), grid_w2c.detach(), grid_c2w.detach(), radius, len(pyr_own), *pyr_own,
-                               *pyr_other)
+    return _DualLookupFn.apply(coords.detach(), grid_w2c.detach(), grid_c2w.detach(), radius, len(pyr_own), channels_last,
+                               fuse_sum, *pyr_own, *pyr_other)
 
 
 class _RemapFn(torch.autograd.Function):

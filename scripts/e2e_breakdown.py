@@ -16,7 +16,7 @@ TAG = os.environ.get("PF_TAG", "default")
 torch.manual_seed(0)
 model = PriOrRAFT().cuda().eval()
 if CL:
-    model = model.to(memory_format=torch.channels_last)
+    model = model.to_channels_last()
 g = torch.Generator().manual_seed(1234)
 im1 = (torch.rand(1, 3, 512, 1024, generator=g) * 255).cuda()
 im2 = (torch.rand(1, 3, 512, 1024, generator=g) * 255).cuda()

@@ -34,14 +34,27 @@ def test_library_exports_every_declared_symbol(lib):
     assert b"sm_100a" in lib.pf_build_info()
 
 
-def test_struct_layouts_match_header():
-    """ctypes mirrors are laid out like the C structs: sizes follow from the field lists in the header."""
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes mirrors have the size and field offsets gcc gives the C structs of include/priorcorr.h."""
     import ctypes as C
-    ptr, ll, i = C.sizeof(C.c_void_p), C.sizeof(C.c_longlong), C.sizeof(C.c_int)
-    assert C.sizeof(_lib.VolumeArgs) == 6 * i + 2 * ptr + 4 * ptr + ptr + ll
-    assert C.sizeof(_lib.LookupArgs) == 9 * i + 4 + ptr + 8 * ptr + 2 * ptr + ll + 5 * ptr
-    assert C.sizeof(_lib.RemapArgs) == 8 * i + 2 * ptr + 3 * ll + ptr
-    assert C.sizeof(_lib.LookupBwdArgs) == C.sizeof(_lib.LookupArgs) + 2 * ptr + 8 * ptr
+    import subprocess
+    structs = {"pf_volume_args": _lib.VolumeArgs, "pf_lookup_args": _lib.LookupArgs, "pf_onthefly_args": _lib.OnTheFlyArgs,
+               "pf_remap_args": _lib.RemapArgs, "pf_lookup_bwd_args": _lib.LookupBwdArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "priorcorr.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
 
 
 def test_argument_errors_are_reported_not_thrown(lib):

@@ -180,6 +180,25 @@ def test_lookup_coordinates_bit_exact(geo, gold_pyramids, edge):
             assert np.array_equal(np.floor(got[:, lvl, :, 0]), np.floor(ix.reshape(-1, 81)))
 
 
+@pytest.mark.parametrize("edge", [False, True])
+def test_lookup_channels_last_and_fused_sum(geo, gold_pyramids, edge):
+    """ABI v2 output modes: channels-last storage and `own + other` fused into the rotate kernel (prior_raft.py:187)."""
+    from prior_flow_b200 import ops
+    pa, pb = _gold_pyr_cuda(gold_pyramids)
+    c = cu(cases.edge_coords() if edge else cases.coords(seed=2))
+    gw, gc = cu(geo["a2b_w2c_8x"]), cu(geo["b2a_8x"])
+    own, other = ops.lookup(c, pa, pb, gw, gc, radius=4)
+    own_cl, other_cl = ops.lookup(c, pa, pb, gw, gc, radius=4, channels_last=True)
+    assert own_cl.shape == own.shape and own_cl.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(own_cl, own) and torch.equal(other_cl, other)
+    want = own + other
+    assert torch.equal(ops.lookup(c, pa, pb, gw, gc, radius=4, fuse_sum=True), want)
+    fused_cl = ops.lookup(c, pa, pb, gw, gc, radius=4, channels_last=True, fuse_sum=True)
+    assert fused_cl.is_contiguous(memory_format=torch.channels_last) and torch.equal(fused_cl, want)
+    single_cl = ops.lookup(c, pa, radius=4, cyclic=False, channels_last=True)
+    assert torch.equal(single_cl, ops.lookup(c, pa, radius=4, cyclic=False))
+
+
 def test_corrblock_lookup(gold_pyramids):
     from prior_flow_b200 import ops
     pa, _ = _gold_pyr_cuda(gold_pyramids)
@@ -250,19 +269,24 @@ def test_backward_kernels_match_autograd(geo):
     wb = torch.randn(1, 243, 8, 32, device="cuda")
     wf = torch.randn(1, 4, 8, 32, device="cuda")
 
-    def run(use_kernels):
+    def run(use_kernels, fused=False):
         leaves = [t.clone().requires_grad_(True) for t in (f1a, f2a, f1b, f2b)]
         a1, a2, b1, b2 = leaves
         if use_kernels:
             pa = ops.volume_pyramid_autograd(a1, a2, 3, "fp32_simt")
             pb = ops.volume_pyramid_autograd(b1, b2, 3, "fp32_simt")
-            own, other = ops.lookup_autograd(c, pa, pb, gw, gc, 4)
+            if fused:   # channels-last + fused sum: one output, gradient flows to both branches
+                both = ops.lookup_autograd(c, pa, pb, gw, gc, 4, channels_last=True, fuse_sum=True)
+                own, other = both, torch.zeros_like(both)
+            else:
+                own, other = ops.lookup_autograd(c, pa, pb, gw, gc, 4)
             flaw = ops.warp_groupcorr_autograd(a1, a2, c, 4)
         else:
             pa, pb = TO.build_pyramid(TO.corr_volume(a1, a2), 3), TO.build_pyramid(TO.corr_volume(b1, b2), 3)
             own, other = TO.dccl_lookup(c, pa, pb, gw, gc, 4)
             flaw = TO.warp_groupcorr(a1, a2, c, 4)
-        loss = (own * wa).sum() + (other * wb).sum() + (flaw * wf).sum()
+        wb_ = wa if fused else wb
+        loss = (own * wa).sum() + (other * wb_).sum() + (flaw * wf).sum()
         loss.backward()
         return [t.grad.detach().cpu().numpy() for t in leaves]
 
@@ -270,9 +294,10 @@ def test_backward_kernels_match_autograd(geo):
     ops.set_div_mode("aten_cuda")
     try:
         got, want = run(True), run(False)
+        got_fused, want_fused = run(True, fused=True), run(False, fused=True)
     finally:
         ops.set_div_mode(prev)
-    for g, w_ in zip(got, want):
+    for g, w_ in list(zip(got, want)) + list(zip(got_fused, want_fused)):
         assert rel_to_max(g, w_) < 2e-5      # atomics + different summation order
 
 
