@@ -170,6 +170,8 @@ def main_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     ops.set_volume_mode(a.volume_mode)
     torch.backends.cudnn.benchmark = True     # let cuDNN pick its conv algorithms (the default picks a CUDA-core SGEMM for the 1x1)

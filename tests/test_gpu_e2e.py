@@ -109,3 +109,21 @@ def test_training_step_backward_runs_and_matches_eager(models):
     for ga, gb in zip(*grads):
         assert np.isfinite(ga).all()
         assert np.abs(ga - gb).max() / np.abs(gb).max() < 5e-3   # atomics + cuDNN sampler in the eager path (see test_gpu_torch_parity)
+
+
+def test_train_step_reduces_loss():
+    """Config-5 shaped step at reduced size: forward + backward kernels + AdamW; the loss must go down."""
+    from prior_flow_b200 import distributed as pfd
+    from prior_flow_b200.model import PriOrRAFT
+    from prior_flow_b200.train import train_step
+    torch.manual_seed(0)
+    model = PriOrRAFT().cuda()
+    model.train()
+    model.freeze_bn()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-7)   # tiny plain-gradient steps: the loss must follow its own gradient
+    ctx = pfd.Context(0, 0, 1, torch.device("cuda", 0))
+    im1, im2 = (torch.from_numpy(x).cuda() for x in cases.e2e_images())
+    gt = torch.from_numpy(cases.flow(seed=12, B=1, h=128, w=256, sigma=1.0)).cuda()
+    valid = torch.ones(1, 128, 256, device="cuda")
+    losses = [train_step(model, opt, (im1, im2, gt, valid), ctx, iters=3)["loss"] for _ in range(4)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
