@@ -287,6 +287,9 @@ def main_ours(a):
                 ts.append(s.elapsed_time(e))
             return sum(ts) / len(ts)
 
+        fill_buf = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        fill_gbs = (1 << 30) / kernel_ms(lambda: fill_buf.fill_(1), reps=10) / 1e6     # what a write-only stream sustains here
+        del fill_buf
         look_ms = kernel_ms(lambda: ops.lookup(coords, pa, pb, grids["A2B_W2C_8x"], grids["B2A_8x"], 4))
         vol_ms = kernel_ms(lambda: ops.volume_pyramid(fm[0], fm[1], 4))
         look_bytes = B * (N * 2 * 4 * 100 * 4 + 2 * N * 324 * 4 + 3 * 2 * N * 4)          # 47.45 MB at B=1
@@ -298,6 +301,7 @@ def main_ours(a):
                     "algorithmic_bytes_per_launch": look_bytes,
                     "other_kernels": {"volume_pyramid(tcgen05, fp32 split) per view": {
                         "ms": round(vol_ms, 4), "GB/s": round(vol_bytes / vol_ms / 1e6, 1), "frac_hbm": round(vol_bytes / vol_ms / 1e6 / hbm, 4),
+                        "frac_of_write_only_stream": round(vol_bytes / vol_ms / 1e6 / fill_gbs, 4), "write_only_stream_GB/s": round(fill_gbs, 1),
                         "TFLOP/s_algorithmic": round(2.0 * B * N * N * 256 / vol_ms / 1e9, 1)}}}
         del pa, pb, flush, fm
         torch.cuda.empty_cache()

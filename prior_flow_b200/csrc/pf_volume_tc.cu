@@ -10,14 +10,14 @@
 // fp16 carries the same 11 significant bits as TF32, so this is the "3xTF32" scheme at twice the
 // tensor rate and half the operand bytes.  PF_VOL_F16 issues the first product only.
 //
-// Structure (persistent, one CTA per SM, 6 warps):
+// Structure (persistent, one CTA per SM, 10 warps):
 //   prep kernels : absmax -> power-of-two scale ; transpose [C, N] fp32 -> K-major [N, C] fp16 hi/lo
 //   warp 0       : TMA producer.  A tile = 128 query rows x 64 k (2-D map); B tile = 8x32 *patch*
 //                  of target pixels x 64 k (4-D map over [B, h, w, C]) — the N-tile is a spatial
 //                  patch so that the 2x2 / 4x4 / 8x8 pools are tile-local.  SWIZZLE_128B, 96 KB/stage.
 //   warp 1       : TMEM alloc (512 cols = 2 accumulator stages of 128 x 256 fp32) and the single
 //                  thread issuing tcgen05.mma (M128 N256 K16), tcgen05.commit -> mbarriers.
-//   warps 2..5   : epilogue.  tcgen05.ld (thread = query row, registers = one patch row of 32
+//   warps 2..9   : epilogue, two groups of 4 warps alternating tiles (one per TMEM accumulator stage).  tcgen05.ld (thread = query row, registers = one patch row of 32
 //                  targets), scale by 1/(sqrt(C) s_a s_b), level 0 staged in swizzled smem and
 //                  written with TMA (3-D map over [B*N, h, w]); levels 1..3 pooled in registers
 //                  in avg_pool2d's order ((a+b)+c+d)/4 from the rounded finer level and stored
@@ -26,6 +26,7 @@
 // 4 x 4 MiB per view at 512x1024) stay in L2.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "pf_common.cuh"
 
@@ -40,7 +41,7 @@ constexpr int A_PLANE = BM * BK * 2;    // 16 KiB
 constexpr int B_PLANE = BN * BK * 2;    // 32 KiB
 constexpr int OUT_STAGE = BM * 32 * 4;  // 16 KiB: 128 rows x one 32-float patch row
 constexpr int kOutStages = 2;
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;         // TMA warp, MMA warp, 2 x 4 epilogue warps
 constexpr int kAccCols = BN;            // fp32 accumulator columns per stage
 constexpr uint32_t kTmemCols = 512;
 
@@ -91,6 +92,29 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// Multicast variant: the box lands at the same smem offset in every CTA of `mask`, and each destination CTA's mbarrier
+// (same offset) receives the complete_tx.
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2,
+                                               int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
                "r"(c0), "r"(c1), "r"(c2)
@@ -102,7 +126,7 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -219,7 +243,11 @@ struct TcParams {
   float *lvl1, *lvl2, *lvl3;
 };
 
-template <bool kSplit>
+// kCluster = 2: CTA pairs (thread-block cluster 2x1x1) work on two M-tiles of the SAME target patch in lockstep; each
+// CTA fetches half of the B (patch) tile and TMA-multicasts it to both, so the L2 -> SM operand traffic per tile drops
+// from A + B to A + B/2 (ncu r01a: that traffic, not the tensor pipe or HBM, bounded the 1-CTA kernel).  A stage is
+// recycled only when BOTH CTAs' MMAs have retired it (commit multicast to both empty barriers, count 2).
+template <bool kSplit, int kCluster>
 __global__ void __launch_bounds__(kTcThreads, 1)
 volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -241,7 +269,7 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, kCluster);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
@@ -256,21 +284,30 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCluster > 1)
+    cluster_sync_all();   // the peer's barriers must be initialised before anything is multicast at them
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0;
+  // work items: kCluster consecutive M-tiles of one patch per cluster, so the peers share the B tile
+  const long long first_item = blockIdx.x / kCluster, item_stride = gridDim.x / kCluster;
+  const long long total_items = p.total_tiles / kCluster;
+  const int tiles_m_items = p.tiles_m / kCluster;
+  constexpr uint16_t kMask = (1u << kCluster) - 1;
 
   if (warp == 0) {
     // ================================================================= TMA producer (one thread)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int per_b = p.tiles_m * p.patches_x * p.patches_y;
-        const int b = (int)(tile / per_b);
-        int r = (int)(tile - (long long)b * per_b);
-        const int mt = r / (p.patches_x * p.patches_y);
-        r -= mt * p.patches_x * p.patches_y;
+      for (long long item = first_item; item < total_items; item += item_stride) {
+        const int per_b = tiles_m_items * p.patches_x * p.patches_y;
+        const int b = (int)(item / per_b);
+        int r = (int)(item - (long long)b * per_b);
+        const int mt = (r / (p.patches_x * p.patches_y)) * kCluster + (int)cta_rank;
+        r %= p.patches_x * p.patches_y;
         const int py = r / p.patches_x, px = r - py * p.patches_x;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -279,10 +316,18 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           const uint32_t sbase = smem_u32(smem + stage * C_::kStageBytes);
           const int row = b * p.N + mt * BM;
           tma_load_2d(sbase, &map_a_hi, full, kb * BK, row);
-          tma_load_4d(sbase + A_PLANE, &map_b_hi, full, kb * BK, px * PATCH_W, py * PATCH_H, b);
-          if (kSplit) {
-            tma_load_2d(sbase + A_PLANE + B_PLANE, &map_a_lo, full, kb * BK, row);
-            tma_load_4d(sbase + 2 * A_PLANE + B_PLANE, &map_b_lo, full, kb * BK, px * PATCH_W, py * PATCH_H, b);
+          if (kSplit) tma_load_2d(sbase + A_PLANE + B_PLANE, &map_a_lo, full, kb * BK, row);
+          if (kCluster == 1) {
+            tma_load_4d(sbase + A_PLANE, &map_b_hi, full, kb * BK, px * PATCH_W, py * PATCH_H, b);
+            if (kSplit) tma_load_4d(sbase + 2 * A_PLANE + B_PLANE, &map_b_lo, full, kb * BK, px * PATCH_W, py * PATCH_H, b);
+          } else {
+            // my half of the patch rows (box height PATCH_H / kCluster), delivered to both CTAs
+            constexpr int kHalfRows = PATCH_H / kCluster, kHalfBytes = B_PLANE / kCluster;
+            const int y = py * PATCH_H + (int)cta_rank * kHalfRows;
+            tma_load_4d_mc(sbase + A_PLANE + cta_rank * kHalfBytes, &map_b_hi, full, kb * BK, px * PATCH_W, y, b, kMask);
+            if (kSplit)
+              tma_load_4d_mc(sbase + 2 * A_PLANE + B_PLANE + cta_rank * kHalfBytes, &map_b_lo, full, kb * BK, px * PATCH_W, y, b,
+                             kMask);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -296,7 +341,7 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (long long item = first_item; item < total_items; item += item_stride) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccCols;
@@ -321,7 +366,11 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             for (int k = 0; k < BK / UMMA_K; ++k)
               umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
           }
-          umma_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
+          // frees the smem stage when these MMAs retire — in both CTAs, since the peer multicasts into my smem too
+          if (kCluster > 1)
+            umma_commit_mc(bar_empty + 8 * stage, kMask);
+          else
+            umma_commit(bar_empty + 8 * stage);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -332,112 +381,121 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       }
     }
   } else {
-    // ================================================================= epilogue (4 warps)
+    // ================================================================= epilogue (2 groups x 4 warps)
+    // Group g drains TMEM accumulator stage g, i.e. every other tile of this CTA, so two tiles' epilogues overlap
+    // (ncu r01a stall sampling: a single 4-warp epilogue was the critical path, ~12k cycles per tile in both the
+    // fp32-split and the f16 mode).  Each group owns one 16 KiB staging buffer and walks the 8 patch rows one at a
+    // time; the TMEM load of the next row is in flight while the current one is staged, stored and pooled.
+    const int group = (warp - 2) >> 2;     // 0: warps 2-5, 1: warps 6-9
     const int quarter = warp & 3;          // TMEM lane quarter this warp may read
     const int row = quarter * 32 + lane;   // query row inside the tile
-    const bool leader = threadIdx.x == 64;
+    const bool leader = (threadIdx.x & 127) == 64;   // thread 64 (group 0) / 192 (group 1): first lane of a group's first warp
     const float scale = p.inv_sqrt_c / (split_scale(p.amax_bits[0]) * split_scale(p.amax_bits[1]));
-    uint32_t acc = 0, acc_phase = 0;
+    const uint32_t acc = (uint32_t)group;
+    uint32_t acc_phase = 0;
+    uint8_t *stage_buf = out_stage + group * OUT_STAGE;
     const int w1 = p.w >> 1, h1 = p.h >> 1, w2 = p.w >> 2, h2 = p.h >> 2, w3 = p.w >> 3, h3 = p.h >> 3;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int per_b = p.tiles_m * p.patches_x * p.patches_y;
-      const int b = (int)(tile / per_b);
-      int r = (int)(tile - (long long)b * per_b);
-      const int mt = r / (p.patches_x * p.patches_y);
-      r -= mt * p.patches_x * p.patches_y;
+    for (long long item = first_item + group * item_stride; item < total_items; item += 2 * item_stride) {
+      const int per_b = tiles_m_items * p.patches_x * p.patches_y;
+      const int b = (int)(item / per_b);
+      int r = (int)(item - (long long)b * per_b);
+      const int mt = (r / (p.patches_x * p.patches_y)) * kCluster + (int)cta_rank;
+      r %= p.patches_x * p.patches_y;
       const int py = r / p.patches_x, px = r - py * p.patches_x;
       const long long qrow = (long long)b * p.N + mt * BM + row;  // global query index (plane index)
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      acc_phase ^= 1;
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * kAccCols + ((uint32_t)(quarter * 32) << 16);
-      float l1_prev[16], l2_prev[8];
+      uint32_t un[32];
+      tmem_ld32(taddr, un);
+      float vp[32], l1_prev[16], l2_prev[8];
 #pragma unroll
-      for (int cp = 0; cp < PATCH_H / 2; ++cp) {
-        uint32_t ua[32], ub[32];
-        tmem_ld32(taddr + (2 * cp) * 32, ua);
-        tmem_ld32(taddr + (2 * cp + 1) * 32, ub);
+      for (int c = 0; c < PATCH_H; ++c) {
         tmem_ld_wait();
-        if (cp == PATCH_H / 2 - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+        float vc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) vc[j] = __uint_as_float(un[j]) * scale;
+        if (c + 1 < PATCH_H) {
+          tmem_ld32(taddr + (c + 1) * 32, un);   // prefetch the next patch row
+        } else {                                  // accumulator fully read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         }
-        float va[32], vb[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          va[j] = __uint_as_float(ua[j]) * scale;
-          vb[j] = __uint_as_float(ub[j]) * scale;
-        }
-        // ---- level 0: two patch rows through swizzled staging + TMA store
+        // ---- level 0: one patch row through swizzled staging + TMA store
         if (leader) tma_store_wait_read0();
-        epi_bar_sync();
+        epi_bar_sync(group);
         {
-          uint8_t *r0 = out_stage + row * 128, *r1 = r0 + OUT_STAGE;
+          uint8_t *r0 = stage_buf + row * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int off = ((j ^ (row & 7)) << 4);
-            *reinterpret_cast<float4 *>(r0 + off) = make_float4(va[4 * j], va[4 * j + 1], va[4 * j + 2], va[4 * j + 3]);
-            *reinterpret_cast<float4 *>(r1 + off) = make_float4(vb[4 * j], vb[4 * j + 1], vb[4 * j + 2], vb[4 * j + 3]);
-          }
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4 *>(r0 + ((j ^ (row & 7)) << 4)) = make_float4(vc[4 * j], vc[4 * j + 1], vc[4 * j + 2], vc[4 * j + 3]);
         }
         fence_async_smem();
-        epi_bar_sync();
+        epi_bar_sync(group);
         if (leader) {
-          const int y = py * PATCH_H + 2 * cp, rowg = b * p.N + mt * BM;
-          tma_store_3d(&map_out, smem_u32(out_stage), px * PATCH_W, y, rowg);
-          tma_store_3d(&map_out, smem_u32(out_stage + OUT_STAGE), px * PATCH_W, y + 1, rowg);
+          tma_store_3d(&map_out, smem_u32(stage_buf), px * PATCH_W, py * PATCH_H + c, b * p.N + mt * BM);
           tma_store_commit();
         }
-        // ---- level 1: ((a + b) + c + d) / 4 over the 2x2 window, row-major order (avg_pool2d)
-        if (p.num_levels > 1) {
-          float l1[16];
+        if (c & 1) {
+          const int cp = c >> 1;
+          // ---- level 1: ((a + b) + c + d) / 4 over the 2x2 window, row-major order (avg_pool2d)
+          if (p.num_levels > 1) {
+            float l1[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            l1[j] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(va[2 * j], va[2 * j + 1]), vb[2 * j]), vb[2 * j + 1]), 0.25f);
-          float *d1 = p.lvl1 + (qrow * h1 + (py * (PATCH_H / 2) + cp)) * w1 + px * (PATCH_W / 2);
+            for (int j = 0; j < 16; ++j)
+              l1[j] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(vp[2 * j], vp[2 * j + 1]), vc[2 * j]), vc[2 * j + 1]), 0.25f);
+            float *d1 = p.lvl1 + (qrow * h1 + (py * (PATCH_H / 2) + cp)) * w1 + px * (PATCH_W / 2);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4 *>(d1 + 4 * j) = make_float4(l1[4 * j], l1[4 * j + 1], l1[4 * j + 2], l1[4 * j + 3]);
-          if (p.num_levels > 2) {
-            if (cp & 1) {
-              float l2[8];
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4 *>(d1 + 4 * j) = make_float4(l1[4 * j], l1[4 * j + 1], l1[4 * j + 2], l1[4 * j + 3]);
+            if (p.num_levels > 2) {
+              if (cp & 1) {
+                float l2[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                l2[j] = __fmul_rn(
-                    __fadd_rn(__fadd_rn(__fadd_rn(l1_prev[2 * j], l1_prev[2 * j + 1]), l1[2 * j]), l1[2 * j + 1]), 0.25f);
-              float *d2 = p.lvl2 + (qrow * h2 + (py * (PATCH_H / 4) + (cp >> 1))) * w2 + px * (PATCH_W / 4);
-              *reinterpret_cast<float4 *>(d2) = make_float4(l2[0], l2[1], l2[2], l2[3]);
-              *reinterpret_cast<float4 *>(d2 + 4) = make_float4(l2[4], l2[5], l2[6], l2[7]);
-              if (p.num_levels > 3) {
-                if (cp == 3) {
-                  float l3[4];
+                for (int j = 0; j < 8; ++j)
+                  l2[j] = __fmul_rn(
+                      __fadd_rn(__fadd_rn(__fadd_rn(l1_prev[2 * j], l1_prev[2 * j + 1]), l1[2 * j]), l1[2 * j + 1]), 0.25f);
+                float *d2 = p.lvl2 + (qrow * h2 + (py * (PATCH_H / 4) + (cp >> 1))) * w2 + px * (PATCH_W / 4);
+                *reinterpret_cast<float4 *>(d2) = make_float4(l2[0], l2[1], l2[2], l2[3]);
+                *reinterpret_cast<float4 *>(d2 + 4) = make_float4(l2[4], l2[5], l2[6], l2[7]);
+                if (p.num_levels > 3) {
+                  if (cp == 3) {
+                    float l3[4];
 #pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    l3[j] = __fmul_rn(
-                        __fadd_rn(__fadd_rn(__fadd_rn(l2_prev[2 * j], l2_prev[2 * j + 1]), l2[2 * j]), l2[2 * j + 1]),
-                        0.25f);
-                  float *d3 = p.lvl3 + (qrow * h3 + py) * w3 + px * (PATCH_W / 8);
-                  *reinterpret_cast<float4 *>(d3) = make_float4(l3[0], l3[1], l3[2], l3[3]);
-                } else {
+                    for (int j = 0; j < 4; ++j)
+                      l3[j] = __fmul_rn(
+                          __fadd_rn(__fadd_rn(__fadd_rn(l2_prev[2 * j], l2_prev[2 * j + 1]), l2[2 * j]), l2[2 * j + 1]),
+                          0.25f);
+                    float *d3 = p.lvl3 + (qrow * h3 + py) * w3 + px * (PATCH_W / 8);
+                    *reinterpret_cast<float4 *>(d3) = make_float4(l3[0], l3[1], l3[2], l3[3]);
+                  } else {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) l2_prev[j] = l2[j];
+                    for (int j = 0; j < 8; ++j) l2_prev[j] = l2[j];
+                  }
                 }
-              }
-            } else {
+              } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) l1_prev[j] = l1[j];
+                for (int j = 0; j < 16; ++j) l1_prev[j] = l1[j];
+              }
             }
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vp[j] = vc[j];
         }
       }
-      if ((acc ^= 1) == 0) acc_phase ^= 1;
     }
     if (leader) tma_store_wait_all();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kCluster > 1)
+    cluster_sync_all();   // no CTA may exit while its peer can still multicast into it or signal its barriers
+  else
+    __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -514,6 +572,10 @@ int volume_build_tc(const pf_volume_args *a, cudaStream_t st) {
   if (int e = check_launch("pf_volume_build(prep)")) return e;
 
   // ---- tensor maps
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int cluster = ((N / BM) % 2 == 0 && sms % 2 == 0 && getenv("PF_VOLUME_NO_CLUSTER") == nullptr) ? 2 : 1;
   CUtensorMap m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out;
   {
     cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)B * N};
@@ -525,7 +587,7 @@ int volume_build_tc(const pf_volume_args *a, cudaStream_t st) {
   {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)w * C * 2, (cuuint64_t)h * w * C * 2};
-    cuuint32_t box[4] = {BK, PATCH_W, PATCH_H, 1};
+    cuuint32_t box[4] = {BK, PATCH_W, (cuuint32_t)(PATCH_H / cluster), 1};
     if (int e = encode(&m_b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, b_hi, dims, strides, box, "B.hi")) return e;
     if (int e = encode(&m_b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, b_lo, dims, strides, box, "B.lo")) return e;
   }
@@ -553,18 +615,33 @@ int volume_build_tc(const pf_volume_args *a, cudaStream_t st) {
   p.lvl2 = a->num_levels > 2 ? a->level[2] : nullptr;
   p.lvl3 = a->num_levels > 3 ? a->level[3] : nullptr;
 
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const unsigned grid = (unsigned)(p.total_tiles < sms ? p.total_tiles : sms);
-  if (split) {
-    auto kern = volume_tc_kernel<true>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::kSmemBytes);
-    kern<<<grid, kTcThreads, Cfg<true>::kSmemBytes, st>>>(m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, p);
-  } else {
-    auto kern = volume_tc_kernel<false>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::kSmemBytes);
-    kern<<<grid, kTcThreads, Cfg<false>::kSmemBytes, st>>>(m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, p);
+  unsigned grid = (unsigned)(p.total_tiles < sms ? p.total_tiles : sms);
+  grid -= grid % cluster;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  auto launch = [&](auto kern, int smem) -> cudaError_t {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cfg.dynamicSmemBytes = smem;
+    return cudaLaunchKernelEx(&cfg, kern, m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, p);
+  };
+  cudaError_t err;
+  if (split)
+    err = cluster == 2 ? launch(volume_tc_kernel<true, 2>, Cfg<true>::kSmemBytes) : launch(volume_tc_kernel<true, 1>, Cfg<true>::kSmemBytes);
+  else
+    err = cluster == 2 ? launch(volume_tc_kernel<false, 2>, Cfg<false>::kSmemBytes)
+                       : launch(volume_tc_kernel<false, 1>, Cfg<false>::kSmemBytes);
+  if (err != cudaSuccess) {
+    set_error("pf_volume_build(tcgen05): launch failed: %s", cudaGetErrorString(err));
+    return 2;
   }
   return check_launch("pf_volume_build(tcgen05)");
 }

@@ -80,6 +80,12 @@ def main():
         rows.append(r)
         print(json.dumps(r), flush=True)
 
+    # what this GPU sustains for a pure-write and a copy stream (the volume build is write-only)
+    big = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+    big2 = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+    rec("hbm_fill_1GiB (write-only stream)", lambda: big.fill_(1), float(1 << 30))
+    rec("hbm_copy_1GiB (read+write stream)", lambda: big2.copy_(big), float(2 << 30))
+    del big, big2
     pyr_bytes = sum(B * N * (h >> l) * (w >> l) * 4 for l in range(4))
     vol_bytes = pyr_bytes + 2 * B * C * N * 4
     vol_flops = 2.0 * B * N * N * C
