@@ -99,7 +99,7 @@ __device__ __forceinline__ AxisEntry make_axis_entry(float s, int size, int stri
 //   fp  [2][(k+1)(k+2)]    the staged (k+1)^2 footprint of the plane (own view) or of both grid channels (other view)
 //   dbg [32] float         sample coordinates for the debug dump
 __host__ __device__ constexpr int lookup_fp_floats(int k) { return (k + 1) * (k + 2); }
-__host__ __device__ constexpr int lookup_warp_floats(int k) { return 32 * 4 + 32 + 2 * lookup_fp_floats(k) + 32; }
+__host__ __device__ constexpr int lookup_warp_floats(int k) { return 2 * (32 * 4 + 32 + 2 * lookup_fp_floats(k) + 32); }  // two sets
 
 template <int R, bool kBwd, int kDiv, int BRANCH>
 __device__ __forceinline__ void lookup_body(const LookupParams &p, const int lvl) {
@@ -113,10 +113,10 @@ __device__ __forceinline__ void lookup_body(const LookupParams &p, const int lvl
   extern __shared__ float4 smem4[];
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
   float *wbase = reinterpret_cast<float *>(smem4) + warp * lookup_warp_floats(k);
-  AxisEntry *T = reinterpret_cast<AxisEntry *>(wbase);
-  int *pos = reinterpret_cast<int *>(wbase + 128);
-  float *fp = wbase + 160;
-  float *dbg_tab = fp + 2 * lookup_fp_floats(k);
+  AxisEntry *T = reinterpret_cast<AxisEntry *>(wbase);              // [2][32]
+  int *pos = reinterpret_cast<int *>(wbase + 256);                   // [2][32]
+  float *fp = wbase + 320;                                           // [2][2][fp_floats]
+  float *dbg_tab = fp + 4 * lookup_fp_floats(k);                     // [2][32]
   float *tile = reinterpret_cast<float *>(smem4) + (kLookupThreads / 32) * lookup_warp_floats(k);  // [K2][33], NCHW own view
   const int b = blockIdx.z;
   const int n0 = blockIdx.x * kQueriesPerCta;
@@ -175,53 +175,84 @@ __device__ __forceinline__ void lookup_body(const LookupParams &p, const int lvl
   float *out_it = opaque((branch ? p.raw : p.out_own) + (nq0 * p.L + lvl) * K2);   // channels-last row of this query
   const bool has_dbg = dbg != nullptr;
 
+  // Software pipeline over the warp's queries: while the taps of query qi run, the coordinate chain of qi+1 has
+  // already been resolved into the other table set and its footprint loads are in flight (held in registers, parked
+  // in shared memory at the top of the next iteration) — a warp always has DRAM requests outstanding.
+  float pf0[kFpRounds], pf1[kFpRounds];   // prefetched footprint cells (second array: grid y channel, other view)
+  // (1) core/corr.py:123-126 + the sampler's coordinate chain, once per window row / column, into table set `set`
+  auto resolve = [&](int qi, int set) -> bool {
+    const float c = __fmul_rn(__ldg(coord_ptr + qi), inv_scale);
+    float pc = __fadd_rn(c, off);
+    if (wrap1) pc = remainder_pos(pc, ax1.size);
+    const float sc = sample_coord<kDiv>(pc, ax1);
+    const AxisEntry e = make_axis_entry(sc, size1, stride1);
+    T[set * 32 + lane] = e;
+    if (chain_lane) {
+      pos[set * 32 + (is_x ? 0 : 16) + (is_x ? lane : lane - k)] = e.o0;
+      if (!has_next) pos[set * 32 + (is_x ? 0 : 16) + k] = e.o1;
+    }
+    if (has_dbg) dbg_tab[set * 32 + lane] = sc;
+    // the footprint is a (k+1)^2 lattice iff consecutive cells share a corner (false across the seam)
+    const int next_o0 = __shfl_down_sync(0xffffffffu, e.o0, 1);
+    const bool lattice = !kBwd && __all_sync(0xffffffffu, !has_next || e.o1 == next_o0);
+    __syncwarp();
+    return lattice;
+  };
+  // (2a) issue the cooperative footprint loads (coalesced row segments of the plane / of the grid) into registers
+  auto prefetch = [&](const float *plane, int set) {
+#pragma unroll
+    for (int j = 0; j < kFpRounds; ++j) {
+      if (j * 32 < FP && j * 32 + lane < FP) {
+        const int o = pos[set * 32 + 16 + (f_rc[j] >> 8)] + pos[set * 32 + (f_rc[j] & 255)];
+        if (branch) {
+          pf0[j] = __ldg(gridx + o);
+          pf1[j] = __ldg(gridy + o);
+        } else {
+          pf0[j] = __ldg(plane + o);
+        }
+      }
+    }
+  };
+  // (2b) park them in shared memory
+  auto park = [&](int set) {
+    float *f = fp + set * 2 * lookup_fp_floats(k);
+#pragma unroll
+    for (int j = 0; j < kFpRounds; ++j) {
+      if (j * 32 < FP && j * 32 + lane < FP) {
+        const int cell = (f_rc[j] >> 8) * pitch + (f_rc[j] & 255);
+        f[cell] = pf0[j];
+        if (branch) f[lookup_fp_floats(k) + cell] = pf1[j];
+      }
+    }
+  };
+  const int nq_w = min(kQueriesPerWarp, p.N - n0 - q0);   // live queries of this warp (may be <= 0)
+  bool fast_next = false;
+  if (nq_w > 0) {
+    fast_next = resolve(0, 0);
+    if (fast_next) prefetch(plane_it, 0);
+  }
+
 #pragma unroll 1
-  for (int qi = 0; qi < kQueriesPerWarp; ++qi) {
+  for (int qi = 0; qi < nq_w; ++qi) {
     const int q = q0 + qi;
     const int n = n0 + q;
-    if (n >= p.N) break;
-    // ---- (1) core/corr.py:123-126 + the sampler's coordinate chain, once per window row / column
-    bool fast;
-    {
-      const float c = __fmul_rn(__ldg(coord_ptr + qi), inv_scale);
-      float pc = __fadd_rn(c, off);
-      if (wrap1) pc = remainder_pos(pc, ax1.size);
-      const float sc = sample_coord<kDiv>(pc, ax1);
-      const AxisEntry e = make_axis_entry(sc, size1, stride1);
-      T[lane] = e;
-      if (chain_lane) {
-        pos[(is_x ? 0 : 16) + (is_x ? lane : lane - k)] = e.o0;
-        if (!has_next) pos[(is_x ? 0 : 16) + k] = e.o1;
-      }
-      if (has_dbg) dbg_tab[lane] = sc;
-      // the footprint is a (k+1)^2 lattice iff consecutive cells share a corner (false across the seam)
-      const int next_o0 = __shfl_down_sync(0xffffffffu, e.o0, 1);
-      fast = !kBwd && __all_sync(0xffffffffu, !has_next || e.o1 == next_o0);
-    }
-    __syncwarp();
+    const int set = qi & 1;
+    const bool fast = fast_next;
     const float *plane = plane_it;
     float *dplane = dplane_it;
     float *outq = out_it;
     plane_it += plane_sz;
     dplane_it += plane_sz;
     out_it += p.L * K2;
-    // ---- (2) stage the footprint with cooperative loads (coalesced row segments of the plane / of the grid)
-    if (fast) {
-#pragma unroll
-      for (int j = 0; j < kFpRounds; ++j) {
-        if (j * 32 < FP && j * 32 + lane < FP) {
-          const int rr = f_rc[j] >> 8, cc = f_rc[j] & 255;
-          const int o = pos[16 + rr] + pos[cc];
-          if (branch) {
-            fp[rr * pitch + cc] = __ldg(gridx + o);
-            fp[lookup_fp_floats(k) + rr * pitch + cc] = __ldg(gridy + o);
-          } else {
-            fp[rr * pitch + cc] = __ldg(plane + o);
-          }
-        }
-      }
-      __syncwarp();
+    if (fast) park(set);
+    __syncwarp();                       // footprint of qi visible; taps of qi-1 (other set) finished in every lane
+    if (qi + 1 < nq_w) {
+      fast_next = resolve(qi + 1, set ^ 1);
+      if (fast_next) prefetch(plane_it, set ^ 1);
     }
+    const AxisEntry *Tq = T + set * 32;
+    const float *fpq = fp + set * 2 * lookup_fp_floats(k);
+    const float *dbgq = dbg_tab + set * 32;
     // ---- (3) taps
 #pragma unroll
     for (int it = 0; it < kRounds; ++it) {
@@ -229,7 +260,7 @@ __device__ __forceinline__ void lookup_body(const LookupParams &p, const int lvl
       if (it * 32 + lane < K2) {
         const int aa = t_a[it], bb = t_b[it];
         const int ch = aa * k + bb;  // x-major channel order of the reference
-        const AxisEntry ex = T[aa], ey = T[k + bb];
+        const AxisEntry ex = Tq[aa], ey = Tq[k + bb];
         float w_nw = __fmul_rn(ex.w0, ey.w0), w_ne = __fmul_rn(ex.w1, ey.w0);
         float w_sw = __fmul_rn(ex.w0, ey.w1), w_se = __fmul_rn(ex.w1, ey.w1);
         float ix = 0.f, iy = 0.f, val = 0.f;
@@ -241,7 +272,7 @@ __device__ __forceinline__ void lookup_body(const LookupParams &p, const int lvl
             if (w_sw != 0.f) atomicAdd(dplane + ey.o1 + ex.o0, g * w_sw);
             if (w_se != 0.f) atomicAdd(dplane + ey.o1 + ex.o1, g * w_se);
           } else if (fast) {
-            const float *f = fp + bb * pitch + aa;
+            const float *f = fpq + bb * pitch + aa;
             val = __fmul_rn(f[0], w_nw);
             val = __fmaf_rn(f[1], w_ne, val);
             val = __fmaf_rn(f[pitch], w_sw, val);
@@ -256,7 +287,7 @@ __device__ __forceinline__ void lookup_body(const LookupParams &p, const int lvl
           // core/corr.py:132-136 — map through the level-0 rotation grid, then index the level-l volume
           float sx, sy;
           if (fast) {
-            const float *f = fp + bb * pitch + aa, *g = f + lookup_fp_floats(k);
+            const float *f = fpq + bb * pitch + aa, *g = f + lookup_fp_floats(k);
             sx = __fmul_rn(f[0], w_nw), sy = __fmul_rn(g[0], w_nw);
             sx = __fmaf_rn(f[1], w_ne, sx), sy = __fmaf_rn(g[1], w_ne, sy);
             sx = __fmaf_rn(f[pitch], w_sw, sx), sy = __fmaf_rn(g[pitch], w_sw, sy);
@@ -308,8 +339,8 @@ __device__ __forceinline__ void lookup_body(const LookupParams &p, const int lvl
             outq[ch] = val;
           if (has_dbg) {
             if (!branch) {
-              ix = dbg_tab[aa];
-              iy = dbg_tab[k + bb];
+              ix = dbgq[aa];
+              iy = dbgq[k + bb];
             }
             float *d = dbg + ((((long long)b * p.N + n) * p.L + lvl) * K2 + ch) * 2;
             d[0] = ix;
@@ -318,7 +349,6 @@ __device__ __forceinline__ void lookup_body(const LookupParams &p, const int lvl
         }
       }
     }
-    __syncwarp();   // T / pos / fp are reused by the next query
   }
   if constexpr (!kBwd) {
     if (use_tile) {
