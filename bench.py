@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--iters", type=int, default=12)
     ap.add_argument("--volume-mode", default="fp32", choices=["fp32", "f16", "fp32_simt"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
-    ap.add_argument("--memory-format", default="channels_last", choices=["nchw", "channels_last"],
+    ap.add_argument("--memory-format", default="nchw", choices=["nchw", "channels_last"],
                     help="memory format of the cuDNN side; channels_last also makes the lookups emit NHWC directly")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()

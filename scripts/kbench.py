@@ -48,6 +48,7 @@ def main():
     ap.add_argument("--w", type=int, default=128)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--skip-torch", action="store_true")
+    ap.add_argument("--cpu", action="store_true", help="also time the ATen restatement of each op on the host cores (reference's CPU path)")
     a = ap.parse_args()
     B, h, w, C = a.batch, a.h, a.w, 256
     N = h * w
@@ -65,9 +66,27 @@ def main():
     gfull = ops.samplegrid((1, 3, 8 * h, 8 * w), Ra)
     rows = []
 
-    def rec(name, fn, bytes_=None, flops=None, torch_fn=None):
+    import time as _time
+    cpu_threads = os.cpu_count() or 1
+    torch.set_num_threads(cpu_threads)
+
+    def cpu_time(make_fn):
+        """best of 3 wall-clock runs of the same op restated with ATen ops on CPU tensors"""
+        f = make_fn()
+        f()
+        ts = []
+        for _ in range(3):
+            t0 = _time.perf_counter()
+            f()
+            ts.append(_time.perf_counter() - t0)
+        return min(ts) * 1e3
+
+    def rec(name, fn, bytes_=None, flops=None, torch_fn=None, cpu_fn=None):
         med, best = timeit(fn, a.iters, flush)
         r = {"kernel": name, "ms_median": round(med, 4), "ms_best": round(best, 4)}
+        if cpu_fn is not None and a.cpu:
+            r["cpu_reference_ms"] = round(cpu_time(cpu_fn), 2)
+            r["cpu_threads"] = cpu_threads
         if bytes_:
             r["GBps"] = round(bytes_ / med / 1e6, 1)
             r["frac_hbm"] = round(bytes_ / med / 1e6 / hbm, 3)
@@ -91,22 +110,31 @@ def main():
     vol_flops = 2.0 * B * N * N * C
     for mode in ("fp32", "f16", "fp32_simt"):
         rec(f"volume_pyramid[{mode}]", lambda m=mode: ops.volume_pyramid(fm[0], fm[1], 4, m), vol_bytes, vol_flops,
-            (lambda: TO.build_pyramid(TO.corr_volume(fm[0], fm[1]))) if mode == "fp32" else None)
+            (lambda: TO.build_pyramid(TO.corr_volume(fm[0], fm[1]))) if mode == "fp32" else None,
+            (lambda: (lambda a_=fm[0].cpu(), b_=fm[1].cpu(): TO.build_pyramid(TO.corr_volume(a_, b_)))) if mode == "fp32" else None)
     pa, pb = ops.volume_pyramid(fm[0], fm[1], 4), ops.volume_pyramid(fm[2], fm[3], 4)
     K2 = 81
     look_bytes = B * N * 2 * 4 * 100 * 4 + 2 * B * N * 4 * K2 * 4 + 3 * B * 2 * N * 4
+    def cpu_lookup():
+        c_, pa_, pb_ = coords.cpu(), [t.cpu() for t in pa], [t.cpu() for t in pb]
+        gw_, gc_ = gw.expand(B, -1, -1, -1).cpu(), gc.expand(B, -1, -1, -1).cpu()
+        return lambda: TO.dccl_lookup(c_, pa_, pb_, gw_, gc_, 4)
     rec("lookup_dual", lambda: ops.lookup(coords, pa, pb, gw, gc, 4), look_bytes, None,
-        lambda: TO.dccl_lookup(coords, pa, pb, gw.expand(B, -1, -1, -1), gc.expand(B, -1, -1, -1), 4))
+        lambda: TO.dccl_lookup(coords, pa, pb, gw.expand(B, -1, -1, -1), gc.expand(B, -1, -1, -1), 4), cpu_lookup)
     rec("lookup_single", lambda: ops.lookup(coords, pa, radius=4, cyclic=True), look_bytes // 2)
     flow = coords - TO.coords_grid(B, h, w, "cuda")
     rec("flo_rotate", lambda: ops.flo_rotate(flow, gw, gc), 4 * B * 2 * N * 4, None,
-        lambda: TO.flo_rotate(flow, gw.expand(B, -1, -1, -1), gc.expand(B, -1, -1, -1)))
+        lambda: TO.flo_rotate(flow, gw.expand(B, -1, -1, -1), gc.expand(B, -1, -1, -1)),
+        lambda: (lambda f_=flow.cpu(), a_=gw.expand(B, -1, -1, -1).cpu(), b_=gc.expand(B, -1, -1, -1).cpu(): TO.flo_rotate(f_, a_, b_)))
     rec("warp_groupcorr", lambda: ops.warp_groupcorr(fm[0], fm[1], coords, 4), 2 * B * C * N * 4 + B * 6 * N * 4, None,
-        lambda: TO.warp_groupcorr(fm[0], fm[1], coords, 4))
+        lambda: TO.warp_groupcorr(fm[0], fm[1], coords, 4),
+        lambda: (lambda a_=fm[0].cpu(), b_=fm[1].cpu(), c_=coords.cpu(): TO.warp_groupcorr(a_, b_, c_, 4)))
     rec("img_rotate_fullres", lambda: ops.remap(img, gfull, "B2HW", True), (2 * 6 + 2) * B * 64 * N * 4, None,
-        lambda: TO.img_rotate(img, gfull.expand(B, -1, -1, -1)))
+        lambda: TO.img_rotate(img, gfull.expand(B, -1, -1, -1)),
+        lambda: (lambda i_=img.cpu(), g_=gfull.expand(B, -1, -1, -1).cpu(): TO.img_rotate(i_, g_)))
     rec("samplegrid_fullres", lambda: ops.samplegrid((1, 3, 8 * h, 8 * w), Ra), 2 * 64 * N * 4, None,
-        lambda: TO.generate_samplegrid((1, 3, 8 * h, 8 * w), Ra))
+        lambda: TO.generate_samplegrid((1, 3, 8 * h, 8 * w), Ra),
+        lambda: (lambda r_=Ra.cpu(): TO.generate_samplegrid((1, 3, 8 * h, 8 * w), r_)))
     cl = lambda t: t.permute(0, 2, 3, 1).contiguous()
     f1a, f2a, f1b, f2b = cl(fm[0]), ops.channels_last_pyramid(fm[1], 4), cl(fm[2]), ops.channels_last_pyramid(fm[3], 4)
     rec("lookup_onthefly", lambda: ops.lookup_onthefly(coords, f1a, f2a, f1b, f2b, gw, gc, 4))
