@@ -222,17 +222,24 @@ __global__ void __launch_bounds__(kWgcWarps * 32) warp_groupcorr_kernel(
 // ------------------------------------------------------------------------------------------------
 // 2x2 average pool (F.avg_pool2d(x, 2, stride=2)): ((a + b) + c + d) / 4 in window row-major order.
 __global__ void avg_pool2x2_kernel(const float *__restrict__ in, float *__restrict__ out, long long planes, int H, int W) {
-  const int Ho = H / 2, Wo = W / 2;
+  const int Ho = H / 2, Wo = W / 2;   // odd tails are dropped, like avg_pool2d
   const long long total = planes * Ho * Wo;
+  const bool vec = (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 7) == 0);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int xo = (int)(i % Wo);
     const long long r = i / Wo;
     const int yo = (int)(r % Ho);
     const long long pl = r / Ho;
     const float *s = in + (pl * H + 2 * yo) * W + 2 * xo;
-    const float2 top = *reinterpret_cast<const float2 *>(s);
-    const float2 bot = *reinterpret_cast<const float2 *>(s + W);
-    out[i] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(top.x, top.y), bot.x), bot.y), 0.25f);
+    float a, b, c, d;
+    if (vec) {
+      const float2 top = *reinterpret_cast<const float2 *>(s);
+      const float2 bot = *reinterpret_cast<const float2 *>(s + W);
+      a = top.x, b = top.y, c = bot.x, d = bot.y;
+    } else {
+      a = s[0], b = s[1], c = s[W], d = s[W + 1];
+    }
+    out[i] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a, b), c), d), 0.25f);
   }
 }
 
@@ -300,7 +307,6 @@ int pf_warp_groupcorr(const float *fmap1, const float *fmap2, const float *coord
 int pf_avg_pool2x2(const float *in, float *out, long long planes, int H, int W, void *stream) {
   using namespace pf;
   PF_REQUIRE(in && out && planes > 0 && H >= 2 && W >= 2, "pf_avg_pool2x2: bad arguments");
-  PF_REQUIRE(W % 2 == 0, "pf_avg_pool2x2: W must be even (float2 loads)");
   const long long total = planes * (H / 2) * (W / 2);
   unsigned blocks = (unsigned)((total + 255) / 256 < 148LL * 32 ? (total + 255) / 256 : 148LL * 32);
   avg_pool2x2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, planes, H, W);

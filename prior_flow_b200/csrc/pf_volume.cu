@@ -12,6 +12,7 @@ long long volume_tc_workspace_bytes(int batch, int channels, int h, int w, int m
 // natural layout for a register-blocked outer product: 128x128 tile, BK = 8, 8x8 per thread.
 constexpr int kSimtTile = 128, kSimtBK = 8;
 
+template <bool kVec>   // kVec: N % 4 == 0, float4 global accesses; otherwise element-wise with bounds checks
 __global__ void __launch_bounds__(256) volume_simt_kernel(const float *__restrict__ A, const float *__restrict__ Bm,
                                                           float *__restrict__ V, int C, int N, float scale) {
   __shared__ __align__(16) float As[kSimtBK][kSimtTile];
@@ -32,8 +33,20 @@ __global__ void __launch_bounds__(256) volume_simt_kernel(const float *__restric
   for (int k0 = 0; k0 < C; k0 += kSimtBK) {
     float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
     if (k0 + lr < C) {
-      if (n0 + lc < N) va = *reinterpret_cast<const float4 *>(Ab + (long long)(k0 + lr) * N + n0 + lc);
-      if (m0 + lc < N) vb = *reinterpret_cast<const float4 *>(Bb + (long long)(k0 + lr) * N + m0 + lc);
+      const float *pa = Ab + (long long)(k0 + lr) * N + n0 + lc, *pb = Bb + (long long)(k0 + lr) * N + m0 + lc;
+      if (kVec) {
+        if (n0 + lc < N) va = *reinterpret_cast<const float4 *>(pa);
+        if (m0 + lc < N) vb = *reinterpret_cast<const float4 *>(pb);
+      } else {
+        float ta[4] = {0.f, 0.f, 0.f, 0.f}, tb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (n0 + lc + j < N) ta[j] = pa[j];
+          if (m0 + lc + j < N) tb[j] = pb[j];
+        }
+        va = make_float4(ta[0], ta[1], ta[2], ta[3]);
+        vb = make_float4(tb[0], tb[1], tb[2], tb[3]);
+      }
     }
     *reinterpret_cast<float4 *>(&As[lr][lc]) = va;
     *reinterpret_cast<float4 *>(&Bs[lr][lc]) = vb;
@@ -60,10 +73,16 @@ __global__ void __launch_bounds__(256) volume_simt_kernel(const float *__restric
 #pragma unroll
     for (int jh = 0; jh < 2; ++jh) {
       const int m = m0 + jh * 64 + tx * 4;
-      if (m < N) {
-        float4 o = make_float4(acc[i][jh * 4 + 0] * scale, acc[i][jh * 4 + 1] * scale, acc[i][jh * 4 + 2] * scale,
-                               acc[i][jh * 4 + 3] * scale);
-        *reinterpret_cast<float4 *>(Vb + (long long)n * N + m) = o;
+      if (kVec) {
+        if (m < N) {
+          float4 o = make_float4(acc[i][jh * 4 + 0] * scale, acc[i][jh * 4 + 1] * scale, acc[i][jh * 4 + 2] * scale,
+                                 acc[i][jh * 4 + 3] * scale);
+          *reinterpret_cast<float4 *>(Vb + (long long)n * N + m) = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (m + j < N) Vb[(long long)n * N + m + j] = acc[i][jh * 4 + j] * scale;
       }
     }
   }
@@ -71,10 +90,13 @@ __global__ void __launch_bounds__(256) volume_simt_kernel(const float *__restric
 
 static int volume_build_simt(const pf_volume_args *a, cudaStream_t st) {
   const int N = a->h * a->w;
-  PF_REQUIRE(N % 4 == 0, "pf_volume_build(simt): h*w must be a multiple of 4");
   dim3 grid(ceil_div(N, kSimtTile), ceil_div(N, kSimtTile), a->batch);
   const float scale = 1.0f / sqrtf((float)a->channels);
-  volume_simt_kernel<<<grid, 256, 0, st>>>(a->fmap1, a->fmap2, a->level[0], a->channels, N, scale);
+  const bool vec = N % 4 == 0 && (((uintptr_t)a->fmap1 | (uintptr_t)a->fmap2 | (uintptr_t)a->level[0]) & 15) == 0;
+  if (vec)
+    volume_simt_kernel<true><<<grid, 256, 0, st>>>(a->fmap1, a->fmap2, a->level[0], a->channels, N, scale);
+  else
+    volume_simt_kernel<false><<<grid, 256, 0, st>>>(a->fmap1, a->fmap2, a->level[0], a->channels, N, scale);
   if (int e = check_launch("pf_volume_build(simt)")) return e;
   for (int l = 1; l < a->num_levels; ++l) {
     if (int e = pf_avg_pool2x2(a->level[l - 1], a->level[l], (long long)a->batch * N, a->h >> (l - 1), a->w >> (l - 1),
@@ -102,8 +124,6 @@ int pf_volume_build(const pf_volume_args *a, void *stream) {
   for (int l = 0; l < a->num_levels; ++l) {
     PF_REQUIRE(a->level[l] != nullptr, "pf_volume_build: level[%d] is null", l);
     PF_REQUIRE((a->h >> l) >= 1 && (a->w >> l) >= 1, "pf_volume_build: level %d is empty", l);
-    PF_REQUIRE(l == 0 || (((a->h >> (l - 1)) % 2 == 0) && ((a->w >> (l - 1)) % 2 == 0)),
-               "pf_volume_build: h, w must be divisible by 2^(levels-1)");
   }
   cudaStream_t st = (cudaStream_t)stream;
   switch (a->mode) {

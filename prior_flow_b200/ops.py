@@ -80,6 +80,12 @@ def _grid_arg(g: torch.Tensor, name: str, B: int, H: int, W: int) -> Tuple[torch
 
 
 # ------------------------------------------------------------------------------------------ (a)
+def tcgen05_shape_ok(channels: int, h: int, w: int, num_levels: int = 4) -> bool:
+    """Shapes the tensor-core volume kernel tiles exactly (pf_volume_build): other shapes (e.g. h = 55 after
+    InputPadder) run the CUDA-core variant."""
+    return w % 32 == 0 and h % 8 == 0 and (h * w) % 128 == 0 and channels % 64 == 0 and num_levels <= 4
+
+
 def volume_pyramid(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int = 4,
                    mode: Optional[str] = None) -> List[torch.Tensor]:
     """Fused corr volume + avg-pool pyramid (core/prior_raft.py:69-75 + core/corr.py:99-111).
@@ -91,6 +97,8 @@ def volume_pyramid(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int = 4
     fmap1, fmap2 = fmap1.contiguous(), fmap2.contiguous()
     B, Cn, h, w = fmap1.shape
     mode_id = _lib.VOLUME_MODES[mode or _state["volume_mode"]]
+    if mode_id != _lib.VOL_FP32_SIMT and not tcgen05_shape_ok(Cn, h, w, num_levels):
+        mode_id = _lib.VOL_FP32_SIMT    # still on the GPU, exact fp32: the tcgen05 tiling needs 8x32 patches of the map
     with torch.cuda.device(fmap1.device):
         levels = [torch.empty((B * h * w, 1, h >> l, w >> l), device=fmap1.device, dtype=torch.float32)
                   for l in range(num_levels)]

@@ -312,3 +312,40 @@ def test_remap_backward_matches_autograd(geo):
     b = src.clone().requires_grad_(True)
     (TO.img_rotate(b, grid) * w_).sum().backward()
     assert rel_to_max(host(a.grad), host(b.grad)) < 1e-5
+
+
+# ------------------------------------------------------------------ shapes the tensor-core tiling does not cover
+@pytest.mark.parametrize("B,C,h,w,L", [(2, 64, 5, 9, 2), (1, 96, 11, 24, 3), (1, 128, 8, 32, 4)])
+def test_odd_shapes_volume_pyramid_lookup(B, C, h, w, L):
+    """Arbitrary (odd, non-multiple-of-8) feature-map sizes: the host layer falls back to the CUDA-core volume kernel,
+    pooling floors like avg_pool2d, lookups handle ragged query counts.  Checked against the numpy oracle."""
+    from prior_flow_b200 import ops
+    rs = np.random.RandomState(77)
+    f1 = (rs.randn(B, C, h, w) * 1.45).astype(np.float32)
+    f2 = (rs.randn(B, C, h, w) * 1.45).astype(np.float32)
+    want = O.build_pyramid(O.corr_volume(f1, f2), L)
+    got = ops.volume_pyramid(cu(f1), cu(f2), L)            # default mode "fp32": tcgen05 when tileable, else CUDA cores
+    for l in range(L):
+        assert got[l].shape == want[l].shape
+        assert rel_to_max(host(got[l]), want[l]) < 1e-5
+    c = cases.coords(seed=5, B=B, h=h, w=w, sigma=1.5)
+    out = host(ops.lookup(cu(c), [cu(x) for x in want], radius=2, cyclic=True))
+    ref_outs = []
+    for lvl in range(L):
+        Hl, Wl = want[lvl].shape[-2:]
+        px, py = O.window_points(c, lvl, 2)
+        ix, iy = O.pixel_to_sample_coords(px, py, Hl, Wl, True)
+        ref_outs.append(O.bilinear_zeros(want[lvl], ix, iy).reshape(B, h, w, 25))
+    assert np.array_equal(out, np.concatenate(ref_outs, -1).transpose(0, 3, 1, 2))
+
+
+def test_bad_arguments_raise_with_library_message():
+    from prior_flow_b200 import _lib, ops
+    with pytest.raises(_lib.PriorCorrError, match="pyramid too deep"):
+        ops.lookup(torch.zeros(1, 2, 4, 4, device="cuda"), [torch.zeros(16, 1, 4 >> l, 4 >> l, device="cuda") for l in range(4)],
+                   radius=4, cyclic=False)
+    with pytest.raises(ValueError):
+        ops.volume_pyramid(torch.zeros(1, 64, 8, 32, device="cuda"), torch.zeros(1, 64, 8, 16, device="cuda"))
+    with pytest.raises(TypeError):
+        ops.flo_rotate(torch.zeros(1, 2, 8, 16, device="cuda", dtype=torch.float16), torch.zeros(1, 2, 8, 16, device="cuda"),
+                       torch.zeros(1, 2, 8, 16, device="cuda"))
