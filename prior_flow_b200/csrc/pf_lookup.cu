@@ -28,6 +28,8 @@
 // Coordinates are bit-exact restatements (pf_common.cuh); values are ATen's FMA chain.
 #include "pf_common.cuh"
 
+#include <stdlib.h>
+
 namespace pf {
 
 constexpr int kQueriesPerCta = 32;
@@ -37,6 +39,7 @@ constexpr int kQueriesPerWarp = kQueriesPerCta / (kLookupThreads / 32);
 struct LookupParams {
   int B, N, h, w;  // query grid, N = h*w
   int radius, L, cyclic, div_mode, dual, channels_last, fuse_sum;
+  int w_pow2, w2_pow2;                 // the rotation grid's width / the pyramid's level-0 width is a power of two
   const float *coords;
   const float *own[PF_MAX_LEVELS];
   const float *other[PF_MAX_LEVELS];
@@ -369,6 +372,334 @@ __global__ void __launch_bounds__(kLookupThreads, 4) lookup_kernel(const LookupP
 }
 
 // ------------------------------------------------------------------------------------------------
+// lookup_rows_kernel — the radius-4 forward kernel (r02).  ncu r01e showed the tap-per-lane kernel above issue-bound
+// (30 M warp instructions per call at 65 % issue-slot utilisation, L1 79 % busy, DRAM 17 %): per (query, level) it
+// paid a coordinate-table build, a staged footprint copy and 3 rounds of 81/96-efficient taps that each re-read the
+// tables.  Here a lane owns one COLUMN of one query's window and walks its rows:
+//   * lane = 10 * qq + a: three queries per warp, a = 0..9 the 10 columns of the (k+1)^2 footprint.  The lane runs
+//     the x coordinate chain of its own column (weights stay in registers for all 9 rows) and the y chain of window
+//     row a, which it publishes to a 400-byte per-warp table (offsets as int4 rows, weights as float2).
+//   * own view: one LDG per footprint row (three coalesced 40-byte segments per warp instruction), the right
+//     neighbour by SHFL, 4 weight products + 4 FMAs per output: ~60 instructions per (query, level) instead of ~270.
+//   * other view: the same walk over the two channels of the rotation grid gives the mapped point of every tap;
+//     the second sampler then runs in groups of three rows so that 12 plane loads per lane are in flight at once,
+//     with a warp vote that skips rows mapped entirely outside the (smaller, scale-mixed) level-l plane — most of
+//     levels 1-3 — and an all-interior shortcut (one base pointer, no clamps).
+//   * the lattice assumption (corner sharing between neighbouring cells) is verified per triple with one vote;
+//     the rare exceptions (a coordinate within an ulp of an integer) take a direct four-load path.
+//   * outputs go through one [81][97] shared tile per CTA (96 queries x one level x one branch) and leave as
+//     128-byte rows (NCHW) or 324-byte channel runs (channels-last scratch).
+// Coordinate arithmetic is shortened with exact identities only (see sample_coord_x): results are bit-identical
+// to the long chain, which the debug dump (kDbg) still proves tap by tap.
+constexpr int kRowsThreads = 256;
+constexpr int kRowsWarps = kRowsThreads / 32;
+constexpr int kRowsQ = 96;                 // queries per CTA = 32 triples
+constexpr int kRowsPitch = kRowsQ + 1;     // tile pitch (odd -> conflict-free both ways)
+constexpr int kRowsK = 9, kRowsK2 = 81;
+constexpr int kRowsWarpWords = 3 * 12 * 2 + 3 * 10 * 2 + 32;   // o0 rows, o1 rows (int, pitch 12), weights (float2, pitch 10), dbg y
+
+// to_sample_coord with the exact scalings folded: 2p*inv == 2*(p*inv) (power-of-two scaling), fl(2q - 1) is one FMA,
+// and ((g+1) * 0.5) * (W-1) == (g+1) * ((W-1)/2) because the halving is exact.  4 instructions instead of 6.
+template <int kDiv>
+__device__ __forceinline__ float sample_coord_x(float p, const Axis ax, const float half_m1) {
+  const float q = (kDiv == PF_DIV_ATEN_CUDA) ? __fmul_rn(p, ax.inv_m1) : __fdiv_rn(p, ax.size_m1);
+  const float g = __fmaf_rn(q, 2.f, -1.f);
+  float v = __fmul_rn(__fadd_rn(g, 1.f), half_m1);
+  if (!(fabsf(v) <= 2147483648.f)) v = -100.f;
+  return v;
+}
+
+// torch.remainder(x, m), m > 0.  For a power-of-two m the quotient, its truncation, the product and the
+// difference are all exact, so three instructions reproduce fmodf; otherwise the general routine.
+__device__ __forceinline__ float remainder_sel(float x, const Axis ax, const bool pow2) {
+  if (pow2) {
+    const float t = truncf(__fmul_rn(x, 1.0f / ax.size));
+    float r = __fmaf_rn(-t, ax.size, x);
+    if (r < 0.f) r = __fadd_rn(r, ax.size);
+    return r;
+  }
+  return remainder_pos(x, ax.size);
+}
+
+template <int kDiv, bool kDbg, int BRANCH>
+__device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const int lvl) {
+  extern __shared__ float4 smem4[];
+  float *tile = reinterpret_cast<float *>(smem4);                                  // [81][97]
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  float *wbase = tile + ((kRowsK2 * kRowsPitch + 3) & ~3) + warp * kRowsWarpWords;
+  int *tyo0 = reinterpret_cast<int *>(wbase);            // [3][12] row offsets of tap y0 (entry 9 = o1 of row 8)
+  int *tyo1 = tyo0 + 36;                                 // [3][12] row offsets of tap y1 (direct path only)
+  float2 *tyw = reinterpret_cast<float2 *>(tyo1 + 36);   // [3][10] (w0, w1) per window row
+  float *tdbg = reinterpret_cast<float *>(tyw + 30);     // [27] y sample coordinate (debug dump)
+  const int b = blockIdx.z, n0 = blockIdx.x * kRowsQ;
+  const int Hl = p.Hl[lvl], Wl = p.Wl[lvl];
+  const Axis axW = p.axW[lvl], axH = p.axH[lvl];
+  const float hW = __fmul_rn(0.5f, axW.size_m1), hH = __fmul_rn(0.5f, axH.size_m1);
+  const float inv_scale = 1.0f / (float)(1 << lvl);
+  const int l10 = lane / 10;
+  const int qq = l10 < 2 ? l10 : 2;             // lanes 30, 31 shadow lanes 20, 21 (valid addresses, no stores)
+  const int a = lane - 10 * l10;
+  const bool act = lane < 30 && a < kRowsK;     // this lane produces outputs (column a of query qq)
+  const float off = (float)(a - 4);
+  const Axis ax1x = BRANCH ? p.ax_gw : axW, ax1y = BRANCH ? p.ax_gh : axH;   // first sampler's axes
+  const float h1x = __fmul_rn(0.5f, ax1x.size_m1), h1y = __fmul_rn(0.5f, ax1y.size_m1);
+  const int size1x = BRANCH ? p.w : Wl, size1y = BRANCH ? p.h : Hl;
+  const bool wrap1 = BRANCH || p.cyclic;
+  const bool pow2_1 = BRANCH ? p.w_pow2 : p.w2_pow2;
+  const float *vol = opaque(BRANCH ? p.other[lvl] : p.own[lvl]);
+  const int plane_sz = Hl * Wl;
+  const float *gridx = opaque(p.grid_w2c + (long long)b * p.grid_bs);
+  const float *cxp = opaque(p.coords + (long long)b * 2 * p.N);
+  float *dbg = BRANCH ? p.dbg_other : p.dbg_own;
+  float *tcol = tile + a * kRowsK * kRowsPitch;   // + b * pitch + query
+
+#pragma unroll 1
+  for (int t = warp; t < kRowsQ / 3; t += kRowsWarps) {
+    if (n0 + 3 * t >= p.N) break;                                  // warp-uniform
+    __syncwarp();                                                  // the previous triple's table reads are done
+    const int ql = 3 * t + qq;
+    const int n = min(n0 + ql, p.N - 1);
+    // ---- coordinate chains: column a (x) and window row a (y) of query qq   (core/corr.py:123-126 + utils.py:85-86)
+    const float cx = __fmul_rn(__ldg(cxp + n), inv_scale), cy = __fmul_rn(__ldg(cxp + p.N + n), inv_scale);
+    float px = __fadd_rn(cx, off);
+    if (wrap1) px = remainder_sel(px, ax1x, pow2_1);
+    const float scx = sample_coord_x<kDiv>(px, ax1x, h1x);
+    const float scy = sample_coord_x<kDiv>(__fadd_rn(cy, off), ax1y, h1y);
+    const AxisEntry ex = make_axis_entry(scx, size1x, 1);
+    const AxisEntry ey = make_axis_entry(scy, size1y, size1x);
+    if (act) {
+      tyo0[qq * 12 + a] = ey.o0;
+      tyo1[qq * 12 + a] = ey.o1;
+      if (a == kRowsK - 1) tyo0[qq * 12 + kRowsK] = ey.o1;
+      tyw[qq * 10 + a] = make_float2(ey.w0, ey.w1);
+      if (kDbg) tdbg[qq * 9 + a] = scy;
+    }
+    const int o1_left = __shfl_up_sync(0xffffffffu, ex.o1, 1);
+    const int col = (a == kRowsK) ? o1_left : ex.o0;               // the footprint column this lane loads
+    const int col_right = __shfl_down_sync(0xffffffffu, col, 1);
+    const int yo0_next = __shfl_down_sync(0xffffffffu, ey.o0, 1);
+    const bool okx = !act || ex.w1 == 0.f || ex.o1 == col_right;
+    const bool oky = !act || a == kRowsK - 1 || ey.w1 == 0.f || ey.o1 == yo0_next;
+    const bool lattice = __all_sync(0xffffffffu, okx && oky);
+    __syncwarp();
+    const long long row = (long long)b * p.N + n;
+    const float2 *wy = tyw + qq * 10;
+
+    if constexpr (!BRANCH) {
+      // ================= own view =================
+      const float *pl = opaque(vol + row * plane_sz);
+      if (lattice) {
+        const float *plc = opaque(pl + col);
+        const int4 ya = *reinterpret_cast<const int4 *>(tyo0 + qq * 12), yb = *reinterpret_cast<const int4 *>(tyo0 + qq * 12 + 4);
+        const int2 yc = *reinterpret_cast<const int2 *>(tyo0 + qq * 12 + 8);
+        const int yo[10] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w, yc.x, yc.y};
+        float v[10], vr[10];
+#pragma unroll
+        for (int r = 0; r < 10; ++r) v[r] = __ldg(plc + yo[r]);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) vr[r] = __shfl_down_sync(0xffffffffu, v[r], 1);
+#pragma unroll
+        for (int bb = 0; bb < kRowsK; ++bb) {
+          const float2 w = wy[bb];
+          float val = __fmul_rn(v[bb], __fmul_rn(ex.w0, w.x));
+          val = __fmaf_rn(vr[bb], __fmul_rn(ex.w1, w.x), val);
+          val = __fmaf_rn(v[bb + 1], __fmul_rn(ex.w0, w.y), val);
+          val = __fmaf_rn(vr[bb + 1], __fmul_rn(ex.w1, w.y), val);
+          if (act) tcol[bb * kRowsPitch + ql] = val;
+        }
+      } else {
+#pragma unroll 1
+        for (int bb = 0; bb < kRowsK; ++bb) {
+          const float2 w = wy[bb];
+          const float *r0 = pl + tyo0[qq * 12 + bb], *r1 = pl + tyo1[qq * 12 + bb];
+          float val = __fmul_rn(__ldg(r0 + ex.o0), __fmul_rn(ex.w0, w.x));
+          val = __fmaf_rn(__ldg(r0 + ex.o1), __fmul_rn(ex.w1, w.x), val);
+          val = __fmaf_rn(__ldg(r1 + ex.o0), __fmul_rn(ex.w0, w.y), val);
+          val = __fmaf_rn(__ldg(r1 + ex.o1), __fmul_rn(ex.w1, w.y), val);
+          if (act) tcol[bb * kRowsPitch + ql] = val;
+        }
+      }
+      if (kDbg && dbg != nullptr && act && n0 + ql < p.N) {
+        for (int bb = 0; bb < kRowsK; ++bb) {
+          float *d = dbg + (((row * p.L + lvl) * kRowsK2) + a * kRowsK + bb) * 2;
+          d[0] = scx;
+          d[1] = tdbg[qq * 9 + bb];
+        }
+      }
+    } else {
+      // ================= other view =================  core/corr.py:132-136
+      const float *pl = opaque(vol + row * plane_sz);
+      float sx[kRowsK], sy[kRowsK];
+      if (lattice) {
+        const float *gxc = opaque(gridx + col), *gyc = opaque(gxc + p.N);
+        const int4 ya = *reinterpret_cast<const int4 *>(tyo0 + qq * 12), yb = *reinterpret_cast<const int4 *>(tyo0 + qq * 12 + 4);
+        const int2 yc = *reinterpret_cast<const int2 *>(tyo0 + qq * 12 + 8);
+        const int yo[10] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w, yc.x, yc.y};
+        float gx[10], gy[10];
+#pragma unroll
+        for (int r = 0; r < 10; ++r) gx[r] = __ldg(gxc + yo[r]), gy[r] = __ldg(gyc + yo[r]);
+        float gxr = __shfl_down_sync(0xffffffffu, gx[0], 1), gyr = __shfl_down_sync(0xffffffffu, gy[0], 1);
+#pragma unroll
+        for (int bb = 0; bb < kRowsK; ++bb) {
+          const float2 w = wy[bb];
+          const float w_nw = __fmul_rn(ex.w0, w.x), w_ne = __fmul_rn(ex.w1, w.x);
+          const float w_sw = __fmul_rn(ex.w0, w.y), w_se = __fmul_rn(ex.w1, w.y);
+          const float gxr1 = __shfl_down_sync(0xffffffffu, gx[bb + 1], 1), gyr1 = __shfl_down_sync(0xffffffffu, gy[bb + 1], 1);
+          float x = __fmul_rn(gx[bb], w_nw), y = __fmul_rn(gy[bb], w_nw);
+          x = __fmaf_rn(gxr, w_ne, x), y = __fmaf_rn(gyr, w_ne, y);
+          x = __fmaf_rn(gx[bb + 1], w_sw, x), y = __fmaf_rn(gy[bb + 1], w_sw, y);
+          x = __fmaf_rn(gxr1, w_se, x), y = __fmaf_rn(gyr1, w_se, y);
+          sx[bb] = x, sy[bb] = y;
+          gxr = gxr1, gyr = gyr1;
+        }
+      } else {
+        const float *gy0 = gridx + p.N;
+#pragma unroll
+        for (int bb = 0; bb < kRowsK; ++bb) {
+          const float2 w = wy[bb];
+          const int r0 = tyo0[qq * 12 + bb], r1 = tyo1[qq * 12 + bb];
+          const float w_nw = __fmul_rn(ex.w0, w.x), w_ne = __fmul_rn(ex.w1, w.x);
+          const float w_sw = __fmul_rn(ex.w0, w.y), w_se = __fmul_rn(ex.w1, w.y);
+          float x = __fmul_rn(__ldg(gridx + r0 + ex.o0), w_nw), y = __fmul_rn(__ldg(gy0 + r0 + ex.o0), w_nw);
+          x = __fmaf_rn(__ldg(gridx + r0 + ex.o1), w_ne, x), y = __fmaf_rn(__ldg(gy0 + r0 + ex.o1), w_ne, y);
+          x = __fmaf_rn(__ldg(gridx + r1 + ex.o0), w_sw, x), y = __fmaf_rn(__ldg(gy0 + r1 + ex.o0), w_sw, y);
+          x = __fmaf_rn(__ldg(gridx + r1 + ex.o1), w_se, x), y = __fmaf_rn(__ldg(gy0 + r1 + ex.o1), w_se, y);
+          sx[bb] = x, sy[bb] = y;
+        }
+      }
+      // second sampler into pyr_other[lvl][n], three rows at a time (12 loads per lane in flight)
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        float iy[3], fy[3];
+        int y0[3];
+        bool in_y = false;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          iy[j] = sample_coord_x<kDiv>(sy[3 * g + j], axH, hH);
+          fy[j] = floorf(iy[j]);
+          y0[j] = (int)fy[j];
+          in_y |= (unsigned)(y0[j] + 1) <= (unsigned)Hl;           // y0 in [-1, Hl-1]: at least one tap row inside
+        }
+        float val[3] = {0.f, 0.f, 0.f};
+        float ix[3] = {0.f, 0.f, 0.f};
+        if (kDbg || __any_sync(0xffffffffu, act && in_y)) {
+          float fx[3];
+          int x0[3];
+          bool interior = true;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            ix[j] = sample_coord_x<kDiv>(remainder_sel(sx[3 * g + j], axW, p.w2_pow2), axW, hW);
+            fx[j] = floorf(ix[j]);
+            x0[j] = (int)fx[j];
+            interior &= (unsigned)x0[j] < (unsigned)(Wl - 1) && (unsigned)y0[j] < (unsigned)(Hl - 1);
+          }
+          if (__all_sync(0xffffffffu, !act || interior)) {
+            float t00[3], t01[3], t10[3], t11[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const float *s0 = pl + (y0[j] * Wl + x0[j]);
+              if (!act) s0 = pl;
+              t00[j] = __ldg(s0), t01[j] = __ldg(s0 + 1), t10[j] = __ldg(s0 + Wl), t11[j] = __ldg(s0 + Wl + 1);
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const float dxw = __fsub_rn(ix[j], fx[j]), dxe = __fsub_rn(__fadd_rn(fx[j], 1.f), ix[j]);
+              const float dyn = __fsub_rn(iy[j], fy[j]), dys = __fsub_rn(__fadd_rn(fy[j], 1.f), iy[j]);
+              float v = __fmul_rn(t00[j], __fmul_rn(dxe, dys));
+              v = __fmaf_rn(t01[j], __fmul_rn(dxw, dys), v);
+              v = __fmaf_rn(t10[j], __fmul_rn(dxe, dyn), v);
+              val[j] = __fmaf_rn(t11[j], __fmul_rn(dxw, dyn), v);
+            }
+          } else {
+            AxisEntry gxe[3], gye[3];
+            float t00[3], t01[3], t10[3], t11[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              gxe[j] = make_axis_entry(ix[j], Wl, 1), gye[j] = make_axis_entry(iy[j], Hl, Wl);
+              t00[j] = __ldg(pl + gye[j].o0 + gxe[j].o0), t01[j] = __ldg(pl + gye[j].o0 + gxe[j].o1);
+              t10[j] = __ldg(pl + gye[j].o1 + gxe[j].o0), t11[j] = __ldg(pl + gye[j].o1 + gxe[j].o1);
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              float v = __fmul_rn(t00[j], __fmul_rn(gxe[j].w0, gye[j].w0));
+              v = __fmaf_rn(t01[j], __fmul_rn(gxe[j].w1, gye[j].w0), v);
+              v = __fmaf_rn(t10[j], __fmul_rn(gxe[j].w0, gye[j].w1), v);
+              val[j] = __fmaf_rn(t11[j], __fmul_rn(gxe[j].w1, gye[j].w1), v);
+            }
+          }
+        }
+        if (act) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) tcol[(3 * g + j) * kRowsPitch + ql] = val[j];
+          if (kDbg && dbg != nullptr && n0 + ql < p.N) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              float *d = dbg + (((row * p.L + lvl) * kRowsK2) + a * kRowsK + 3 * g + j) * 2;
+              d[0] = ix[j];
+              d[1] = iy[j];
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- CTA write-out of the [81][96] tile
+  const int nq = min(kRowsQ, p.N - n0);
+  if (!BRANCH && !p.channels_last) {
+    float *o = p.out_own + ((long long)b * p.L + lvl) * kRowsK2 * (long long)p.N + n0;       // NCHW rows
+    for (int ch = warp; ch < kRowsK2; ch += kRowsWarps) {
+      const float *trow = tile + ch * kRowsPitch;
+      float *orow = o + (long long)ch * p.N;
+#pragma unroll
+      for (int j = 0; j < kRowsQ / 32; ++j)
+        if (j * 32 + lane < nq) orow[j * 32 + lane] = trow[j * 32 + lane];
+    }
+  } else {
+    float *o = (BRANCH ? p.raw : p.out_own) + (((long long)b * p.N + n0) * p.L + lvl) * kRowsK2;   // channels-last rows
+    for (int q = warp; q < nq; q += kRowsWarps) {
+      float *orow = o + (long long)q * p.L * kRowsK2;
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (j * 32 + lane < kRowsK2) orow[j * 32 + lane] = tile[(j * 32 + lane) * kRowsPitch + q];
+    }
+  }
+}
+
+template <int kDiv, bool kDbg>
+__global__ void __launch_bounds__(kRowsThreads, 3) lookup_rows_kernel(const LookupParams p) {
+  // heaviest CTAs first: other view level 0..L-1, then own view
+  const int y = blockIdx.y;
+  if (p.dual) {
+    if (y < p.L)
+      lookup_rows_body<kDiv, kDbg, 1>(p, y);
+    else
+      lookup_rows_body<kDiv, kDbg, 0>(p, y - p.L);
+  } else {
+    lookup_rows_body<kDiv, kDbg, 0>(p, y);
+  }
+}
+
+static size_t lookup_rows_smem_bytes() {
+  return (size_t)(((kRowsK2 * kRowsPitch + 3) & ~3) + kRowsWarps * kRowsWarpWords) * sizeof(float);
+}
+
+static int launch_lookup_rows(const LookupParams &p, bool dual, cudaStream_t st, const char *who) {
+  dim3 grid(ceil_div(p.N, kRowsQ), p.L * (dual ? 2 : 1), p.B);
+  const size_t smem = lookup_rows_smem_bytes();
+  const bool recip = p.div_mode == PF_DIV_ATEN_CUDA;
+  const bool dbg = p.dbg_own != nullptr || p.dbg_other != nullptr;
+#define PF_ROWS_LAUNCH(DIV, DBG) lookup_rows_kernel<DIV, DBG><<<grid, kRowsThreads, smem, st>>>(p)
+  if (recip) {
+    if (dbg) PF_ROWS_LAUNCH(PF_DIV_ATEN_CUDA, true); else PF_ROWS_LAUNCH(PF_DIV_ATEN_CUDA, false);
+  } else {
+    if (dbg) PF_ROWS_LAUNCH(PF_DIV_IEEE, true); else PF_ROWS_LAUNCH(PF_DIV_IEEE, false);
+  }
+#undef PF_ROWS_LAUNCH
+  return check_launch(who);
+}
+
+// ------------------------------------------------------------------------------------------------
 // img_rotate of the channels-last pre-rotation map: out[b, c, p] = sum_t w_t(p) raw[b, src_t(p), c].
 constexpr int kRotThreads = 256;
 constexpr int kRotPixels = 32;     // backward / scalar kernel
@@ -540,6 +871,8 @@ static int fill_lookup_params(const pf_lookup_args *a, LookupParams &p, bool dua
   p.cyclic = a->cyclic;
   p.div_mode = a->div_mode;
   p.dual = dual;
+  p.w_pow2 = (a->w & (a->w - 1)) == 0;
+  p.w2_pow2 = (a->w2 & (a->w2 - 1)) == 0 && (a->w2 >> (a->num_levels - 1)) >= 1;
   p.channels_last = a->out_channels_last;
   p.fuse_sum = a->fuse_sum;
   p.coords = a->coords;
@@ -655,7 +988,14 @@ extern "C" int pf_lookup_dual(const pf_lookup_args *a, void *stream) {
     PF_REQUIRE(!dual || a->other[l] != nullptr, "pf_lookup_dual: other[%d] is null", l);
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (int e = launch_lookup<false>(p, a->radius, dual, st, "pf_lookup_dual")) return e;
+  // radius 4 (the model's) runs the column-walk kernel; other radii the generic tap-per-lane kernel
+  // (PF_LOOKUP_LEGACY=1 forces the latter, for A/B timing only)
+  static const bool legacy = getenv("PF_LOOKUP_LEGACY") != nullptr && getenv("PF_LOOKUP_LEGACY")[0] == '1';
+  if (a->radius == 4 && !legacy) {
+    if (int e = launch_lookup_rows(p, dual, st, "pf_lookup_dual")) return e;
+  } else {
+    if (int e = launch_lookup<false>(p, a->radius, dual, st, "pf_lookup_dual")) return e;
+  }
   if (dual) {
     // core/corr.py:137-138 — img_rotate of the [B, L*81, h, w] map with grid_c2w.
     return rotate_forward(a->batch, a->h, a->w, a->num_levels, a->radius, a->div_mode, a->grid_c2w,
