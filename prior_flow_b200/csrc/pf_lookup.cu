@@ -396,6 +396,10 @@ constexpr int kRowsWarps = kRowsThreads / 32;
 constexpr int kRowsQ = 96;                 // queries per CTA = 32 triples
 constexpr int kRowsPitch = kRowsQ + 1;     // tile pitch (odd -> conflict-free both ways)
 constexpr int kRowsK = 9, kRowsK2 = 81;
+#ifndef PF_OWN_STREAM
+#define PF_OWN_STREAM 1
+#endif
+constexpr bool kOwnStream = PF_OWN_STREAM;   // own-view footprint rows are read exactly once: evict-first loads keep L1 for the grid
 constexpr int kRowsWarpWords = 3 * 12 * 2 + 3 * 10 * 2 + 32;   // o0 rows, o1 rows (int, pitch 12), weights (float2, pitch 10), dbg y
 
 // to_sample_coord with the exact scalings folded: 2p*inv == 2*(p*inv) (power-of-two scaling), fl(2q - 1) is one FMA,
@@ -453,6 +457,12 @@ __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const in
   float *dbg = BRANCH ? p.dbg_other : p.dbg_own;
   float *tcol = tile + a * kRowsK * kRowsPitch;   // + b * pitch + query
 
+  // the coordinates of the warp's next triple are fetched one iteration ahead (the chain below starts with them)
+  float ncx, ncy;
+  {
+    const int n_first = min(n0 + 3 * warp + qq, p.N - 1);
+    ncx = __ldg(cxp + n_first), ncy = __ldg(cxp + p.N + n_first);
+  }
 #pragma unroll 1
   for (int t = warp; t < kRowsQ / 3; t += kRowsWarps) {
     if (n0 + 3 * t >= p.N) break;                                  // warp-uniform
@@ -460,7 +470,11 @@ __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const in
     const int ql = 3 * t + qq;
     const int n = min(n0 + ql, p.N - 1);
     // ---- coordinate chains: column a (x) and window row a (y) of query qq   (core/corr.py:123-126 + utils.py:85-86)
-    const float cx = __fmul_rn(__ldg(cxp + n), inv_scale), cy = __fmul_rn(__ldg(cxp + p.N + n), inv_scale);
+    const float cx = __fmul_rn(ncx, inv_scale), cy = __fmul_rn(ncy, inv_scale);
+    {
+      const int n_next = min(n0 + ql + 3 * kRowsWarps, p.N - 1);
+      ncx = __ldg(cxp + n_next), ncy = __ldg(cxp + p.N + n_next);
+    }
     float px = __fadd_rn(cx, off);
     if (wrap1) px = remainder_sel(px, ax1x, pow2_1);
     const float scx = sample_coord_x<kDiv>(px, ax1x, h1x);
@@ -495,7 +509,7 @@ __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const in
         const int yo[10] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w, yc.x, yc.y};
         float v[10], vr[10];
 #pragma unroll
-        for (int r = 0; r < 10; ++r) v[r] = __ldg(plc + yo[r]);
+        for (int r = 0; r < 10; ++r) v[r] = kOwnStream ? __ldcs(plc + yo[r]) : __ldg(plc + yo[r]);
 #pragma unroll
         for (int r = 0; r < 10; ++r) vr[r] = __shfl_down_sync(0xffffffffu, v[r], 1);
 #pragma unroll
