@@ -393,9 +393,10 @@ __global__ void __launch_bounds__(kLookupThreads, 4) lookup_kernel(const LookupP
 // to the long chain, which the debug dump (kDbg) still proves tap by tap.
 constexpr int kRowsThreads = 256;
 constexpr int kRowsWarps = kRowsThreads / 32;
-constexpr int kRowsQ = 96;                 // queries per CTA = 32 triples
-constexpr int kRowsPitch = kRowsQ + 1;     // tile pitch (odd -> conflict-free both ways)
 constexpr int kRowsK = 9, kRowsK2 = 81;
+#ifndef PF_ROWS_MIN_CTAS
+#define PF_ROWS_MIN_CTAS 6   // sweep r02d (profiles/): Q = 48 x 6 CTAs per SM is the fastest shape; L1 (what the carve-out leaves) matters as much as warps
+#endif
 #ifndef PF_OWN_STREAM
 #define PF_OWN_STREAM 1
 #endif
@@ -415,6 +416,7 @@ __device__ __forceinline__ float sample_coord_x(float p, const Axis ax, const fl
 
 // torch.remainder(x, m), m > 0.  For a power-of-two m the quotient, its truncation, the product and the
 // difference are all exact, so three instructions reproduce fmodf; otherwise the general routine.
+__device__ __noinline__ float remainder_general(float x, float m) { return remainder_pos(x, m); }   // one copy of fmodf's slow path
 __device__ __forceinline__ float remainder_sel(float x, const Axis ax, const bool pow2) {
   if (pow2) {
     const float t = truncf(__fmul_rn(x, 1.0f / ax.size));
@@ -422,11 +424,12 @@ __device__ __forceinline__ float remainder_sel(float x, const Axis ax, const boo
     if (r < 0.f) r = __fadd_rn(r, ax.size);
     return r;
   }
-  return remainder_pos(x, ax.size);
+  return remainder_general(x, ax.size);
 }
 
-template <int kDiv, bool kDbg, int BRANCH>
+template <int kDiv, bool kDbg, int kRowsQ, int BRANCH>
 __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const int lvl) {
+  constexpr int kRowsPitch = kRowsQ | 1;   // tile pitch (odd -> conflict-free both ways)
   extern __shared__ float4 smem4[];
   float *tile = reinterpret_cast<float *>(smem4);                                  // [81][97]
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
@@ -543,32 +546,11 @@ __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const in
     } else {
       // ================= other view =================  core/corr.py:132-136
       const float *pl = opaque(vol + row * plane_sz);
-      float sx[kRowsK], sy[kRowsK];
-      if (lattice) {
-        const float *gxc = opaque(gridx + col), *gyc = opaque(gxc + p.N);
-        const int4 ya = *reinterpret_cast<const int4 *>(tyo0 + qq * 12), yb = *reinterpret_cast<const int4 *>(tyo0 + qq * 12 + 4);
-        const int2 yc = *reinterpret_cast<const int2 *>(tyo0 + qq * 12 + 8);
-        const int yo[10] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w, yc.x, yc.y};
-        float gx[10], gy[10];
-#pragma unroll
-        for (int r = 0; r < 10; ++r) gx[r] = __ldg(gxc + yo[r]), gy[r] = __ldg(gyc + yo[r]);
-        float gxr = __shfl_down_sync(0xffffffffu, gx[0], 1), gyr = __shfl_down_sync(0xffffffffu, gy[0], 1);
-#pragma unroll
-        for (int bb = 0; bb < kRowsK; ++bb) {
-          const float2 w = wy[bb];
-          const float w_nw = __fmul_rn(ex.w0, w.x), w_ne = __fmul_rn(ex.w1, w.x);
-          const float w_sw = __fmul_rn(ex.w0, w.y), w_se = __fmul_rn(ex.w1, w.y);
-          const float gxr1 = __shfl_down_sync(0xffffffffu, gx[bb + 1], 1), gyr1 = __shfl_down_sync(0xffffffffu, gy[bb + 1], 1);
-          float x = __fmul_rn(gx[bb], w_nw), y = __fmul_rn(gy[bb], w_nw);
-          x = __fmaf_rn(gxr, w_ne, x), y = __fmaf_rn(gyr, w_ne, y);
-          x = __fmaf_rn(gx[bb + 1], w_sw, x), y = __fmaf_rn(gy[bb + 1], w_sw, y);
-          x = __fmaf_rn(gxr1, w_se, x), y = __fmaf_rn(gyr1, w_se, y);
-          sx[bb] = x, sy[bb] = y;
-          gxr = gxr1, gyr = gyr1;
-        }
-      } else {
+      float *dq = (kDbg && dbg != nullptr && act && n0 + ql < p.N) ? dbg + ((row * p.L + lvl) * kRowsK2 + a * kRowsK) * 2 : nullptr;
+      if (!lattice) {
+        // rare: a window coordinate within an ulp of an integer broke the corner sharing — four direct loads per tap
         const float *gy0 = gridx + p.N;
-#pragma unroll
+#pragma unroll 1
         for (int bb = 0; bb < kRowsK; ++bb) {
           const float2 w = wy[bb];
           const int r0 = tyo0[qq * 12 + bb], r1 = tyo1[qq * 12 + bb];
@@ -578,79 +560,102 @@ __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const in
           x = __fmaf_rn(__ldg(gridx + r0 + ex.o1), w_ne, x), y = __fmaf_rn(__ldg(gy0 + r0 + ex.o1), w_ne, y);
           x = __fmaf_rn(__ldg(gridx + r1 + ex.o0), w_sw, x), y = __fmaf_rn(__ldg(gy0 + r1 + ex.o0), w_sw, y);
           x = __fmaf_rn(__ldg(gridx + r1 + ex.o1), w_se, x), y = __fmaf_rn(__ldg(gy0 + r1 + ex.o1), w_se, y);
-          sx[bb] = x, sy[bb] = y;
+          const float ix = sample_coord_x<kDiv>(remainder_sel(x, axW, p.w2_pow2), axW, hW);
+          const float iy = sample_coord_x<kDiv>(y, axH, hH);
+          const AxisEntry gxe = make_axis_entry(ix, Wl, 1), gye = make_axis_entry(iy, Hl, Wl);
+          float v = __fmul_rn(__ldg(pl + gye.o0 + gxe.o0), __fmul_rn(gxe.w0, gye.w0));
+          v = __fmaf_rn(__ldg(pl + gye.o0 + gxe.o1), __fmul_rn(gxe.w1, gye.w0), v);
+          v = __fmaf_rn(__ldg(pl + gye.o1 + gxe.o0), __fmul_rn(gxe.w0, gye.w1), v);
+          v = __fmaf_rn(__ldg(pl + gye.o1 + gxe.o1), __fmul_rn(gxe.w1, gye.w1), v);
+          if (act) tcol[bb * kRowsPitch + ql] = v;
+          if (kDbg && dq != nullptr) dq[2 * bb] = ix, dq[2 * bb + 1] = iy;
         }
-      }
-      // second sampler into pyr_other[lvl][n], three rows at a time (12 loads per lane in flight)
+      } else {
+        const float *gxc = opaque(gridx + col), *gyc = opaque(gxc + p.N);
+        // three window rows at a time: four rows of both grid channels (L1-resident; reloading the shared row per group
+        // costs two loads and keeps the kernel at 64 registers = 4 CTAs per SM), first sampler, then the second sampler
+        // with 12 plane loads per lane in flight
 #pragma unroll
-      for (int g = 0; g < 3; ++g) {
-        float iy[3], fy[3];
-        int y0[3];
-        bool in_y = false;
+        for (int g = 0; g < 3; ++g) {
+          const int *yrow = tyo0 + qq * 12 + 3 * g;   // rows 3g .. 3g+3 (entry 9 = o1 of row 8)
+          const int yo[4] = {yrow[0], yrow[1], yrow[2], yrow[3]};
+          float gx[4], gy[4], gxr[4], gyr[4];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          iy[j] = sample_coord_x<kDiv>(sy[3 * g + j], axH, hH);
-          fy[j] = floorf(iy[j]);
-          y0[j] = (int)fy[j];
-          in_y |= (unsigned)(y0[j] + 1) <= (unsigned)Hl;           // y0 in [-1, Hl-1]: at least one tap row inside
-        }
-        float val[3] = {0.f, 0.f, 0.f};
-        float ix[3] = {0.f, 0.f, 0.f};
-        if (kDbg || __any_sync(0xffffffffu, act && in_y)) {
-          float fx[3];
-          int x0[3];
-          bool interior = true;
+          for (int r = 0; r < 4; ++r) gx[r] = __ldg(gxc + yo[r]), gy[r] = __ldg(gyc + yo[r]);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) gxr[r] = __shfl_down_sync(0xffffffffu, gx[r], 1), gyr[r] = __shfl_down_sync(0xffffffffu, gy[r], 1);
+          float sx[3], iy[3], fy[3];
+          int y0[3];
+          bool in_y = false;
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
-            ix[j] = sample_coord_x<kDiv>(remainder_sel(sx[3 * g + j], axW, p.w2_pow2), axW, hW);
-            fx[j] = floorf(ix[j]);
-            x0[j] = (int)fx[j];
-            interior &= (unsigned)x0[j] < (unsigned)(Wl - 1) && (unsigned)y0[j] < (unsigned)(Hl - 1);
+            const float2 w = wy[3 * g + j];
+            const float w_nw = __fmul_rn(ex.w0, w.x), w_ne = __fmul_rn(ex.w1, w.x);
+            const float w_sw = __fmul_rn(ex.w0, w.y), w_se = __fmul_rn(ex.w1, w.y);
+            float x = __fmul_rn(gx[j], w_nw), y = __fmul_rn(gy[j], w_nw);
+            x = __fmaf_rn(gxr[j], w_ne, x), y = __fmaf_rn(gyr[j], w_ne, y);
+            x = __fmaf_rn(gx[j + 1], w_sw, x), y = __fmaf_rn(gy[j + 1], w_sw, y);
+            x = __fmaf_rn(gxr[j + 1], w_se, x), y = __fmaf_rn(gyr[j + 1], w_se, y);
+            sx[j] = x;
+            iy[j] = sample_coord_x<kDiv>(y, axH, hH);
+            fy[j] = floorf(iy[j]);
+            y0[j] = (int)fy[j];
+            in_y |= (unsigned)(y0[j] + 1) <= (unsigned)Hl;           // y0 in [-1, Hl-1]: at least one tap row inside
           }
-          if (__all_sync(0xffffffffu, !act || interior)) {
+          float val[3] = {0.f, 0.f, 0.f};
+          float ix[3] = {0.f, 0.f, 0.f};
+          // rows mapped entirely outside the (scale-mixed, smaller) level-l plane are exact zeros: most of levels 1-3
+          if (kDbg || __any_sync(0xffffffffu, act && in_y)) {
+            float fx[3];
+            int x0[3];
+            bool interior = true;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              ix[j] = sample_coord_x<kDiv>(remainder_sel(sx[j], axW, p.w2_pow2), axW, hW);
+              fx[j] = floorf(ix[j]);
+              x0[j] = (int)fx[j];
+              interior &= (unsigned)x0[j] < (unsigned)(Wl - 1) && (unsigned)y0[j] < (unsigned)(Hl - 1);
+            }
             float t00[3], t01[3], t10[3], t11[3];
+            if (__all_sync(0xffffffffu, !act || interior)) {
+              // all four taps of every lane in range: one base pointer, immediate offsets, no clamps
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const float *s0 = pl + (y0[j] * Wl + x0[j]);
-              if (!act) s0 = pl;
-              t00[j] = __ldg(s0), t01[j] = __ldg(s0 + 1), t10[j] = __ldg(s0 + Wl), t11[j] = __ldg(s0 + Wl + 1);
-            }
+              for (int j = 0; j < 3; ++j) {
+                const float *s0 = pl + (act ? y0[j] * Wl + x0[j] : 0);
+                t00[j] = __ldg(s0), t01[j] = __ldg(s0 + 1), t10[j] = __ldg(s0 + Wl), t11[j] = __ldg(s0 + Wl + 1);
+              }
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const float dxw = __fsub_rn(ix[j], fx[j]), dxe = __fsub_rn(__fadd_rn(fx[j], 1.f), ix[j]);
-              const float dyn = __fsub_rn(iy[j], fy[j]), dys = __fsub_rn(__fadd_rn(fy[j], 1.f), iy[j]);
-              float v = __fmul_rn(t00[j], __fmul_rn(dxe, dys));
-              v = __fmaf_rn(t01[j], __fmul_rn(dxw, dys), v);
-              v = __fmaf_rn(t10[j], __fmul_rn(dxe, dyn), v);
-              val[j] = __fmaf_rn(t11[j], __fmul_rn(dxw, dyn), v);
-            }
-          } else {
-            AxisEntry gxe[3], gye[3];
-            float t00[3], t01[3], t10[3], t11[3];
+              for (int j = 0; j < 3; ++j) {
+                const float dxw = __fsub_rn(ix[j], fx[j]), dxe = __fsub_rn(__fadd_rn(fx[j], 1.f), ix[j]);
+                const float dyn = __fsub_rn(iy[j], fy[j]), dys = __fsub_rn(__fadd_rn(fy[j], 1.f), iy[j]);
+                float v = __fmul_rn(t00[j], __fmul_rn(dxe, dys));
+                v = __fmaf_rn(t01[j], __fmul_rn(dxw, dys), v);
+                v = __fmaf_rn(t10[j], __fmul_rn(dxe, dyn), v);
+                val[j] = __fmaf_rn(t11[j], __fmul_rn(dxw, dyn), v);
+              }
+            } else {
+              AxisEntry gxe[3], gye[3];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              gxe[j] = make_axis_entry(ix[j], Wl, 1), gye[j] = make_axis_entry(iy[j], Hl, Wl);
-              t00[j] = __ldg(pl + gye[j].o0 + gxe[j].o0), t01[j] = __ldg(pl + gye[j].o0 + gxe[j].o1);
-              t10[j] = __ldg(pl + gye[j].o1 + gxe[j].o0), t11[j] = __ldg(pl + gye[j].o1 + gxe[j].o1);
-            }
+              for (int j = 0; j < 3; ++j) {
+                gxe[j] = make_axis_entry(ix[j], Wl, 1), gye[j] = make_axis_entry(iy[j], Hl, Wl);
+                t00[j] = __ldg(pl + gye[j].o0 + gxe[j].o0), t01[j] = __ldg(pl + gye[j].o0 + gxe[j].o1);
+                t10[j] = __ldg(pl + gye[j].o1 + gxe[j].o0), t11[j] = __ldg(pl + gye[j].o1 + gxe[j].o1);
+              }
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              float v = __fmul_rn(t00[j], __fmul_rn(gxe[j].w0, gye[j].w0));
-              v = __fmaf_rn(t01[j], __fmul_rn(gxe[j].w1, gye[j].w0), v);
-              v = __fmaf_rn(t10[j], __fmul_rn(gxe[j].w0, gye[j].w1), v);
-              val[j] = __fmaf_rn(t11[j], __fmul_rn(gxe[j].w1, gye[j].w1), v);
+              for (int j = 0; j < 3; ++j) {
+                float v = __fmul_rn(t00[j], __fmul_rn(gxe[j].w0, gye[j].w0));
+                v = __fmaf_rn(t01[j], __fmul_rn(gxe[j].w1, gye[j].w0), v);
+                v = __fmaf_rn(t10[j], __fmul_rn(gxe[j].w0, gye[j].w1), v);
+                val[j] = __fmaf_rn(t11[j], __fmul_rn(gxe[j].w1, gye[j].w1), v);
+              }
             }
           }
-        }
-        if (act) {
+          if (act) {
 #pragma unroll
-          for (int j = 0; j < 3; ++j) tcol[(3 * g + j) * kRowsPitch + ql] = val[j];
-          if (kDbg && dbg != nullptr && n0 + ql < p.N) {
+            for (int j = 0; j < 3; ++j) tcol[(3 * g + j) * kRowsPitch + ql] = val[j];
+            if (kDbg && dq != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              float *d = dbg + (((row * p.L + lvl) * kRowsK2) + a * kRowsK + 3 * g + j) * 2;
-              d[0] = ix[j];
-              d[1] = iy[j];
+              for (int j = 0; j < 3; ++j) dq[2 * (3 * g + j)] = ix[j], dq[2 * (3 * g + j) + 1] = iy[j];
             }
           }
         }
@@ -666,7 +671,7 @@ __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const in
       const float *trow = tile + ch * kRowsPitch;
       float *orow = o + (long long)ch * p.N;
 #pragma unroll
-      for (int j = 0; j < kRowsQ / 32; ++j)
+      for (int j = 0; j < (kRowsQ + 31) / 32; ++j)
         if (j * 32 + lane < nq) orow[j * 32 + lane] = trow[j * 32 + lane];
     }
   } else {
@@ -680,36 +685,52 @@ __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const in
   }
 }
 
-template <int kDiv, bool kDbg>
-__global__ void __launch_bounds__(kRowsThreads, 3) lookup_rows_kernel(const LookupParams p) {
+template <int kDiv, bool kDbg, int kRowsQ, int kMinCtas>
+__global__ void __launch_bounds__(kRowsThreads, kMinCtas) lookup_rows_kernel(const LookupParams p) {
   // heaviest CTAs first: other view level 0..L-1, then own view
   const int y = blockIdx.y;
-  if (p.dual) {
-    if (y < p.L)
-      lookup_rows_body<kDiv, kDbg, 1>(p, y);
-    else
-      lookup_rows_body<kDiv, kDbg, 0>(p, y - p.L);
-  } else {
-    lookup_rows_body<kDiv, kDbg, 0>(p, y);
-  }
+  if (p.dual && y < p.L)
+    lookup_rows_body<kDiv, kDbg, kRowsQ, 1>(p, y);
+  else
+    lookup_rows_body<kDiv, kDbg, kRowsQ, 0>(p, p.dual ? y - p.L : y);
 }
 
-static size_t lookup_rows_smem_bytes() {
-  return (size_t)(((kRowsK2 * kRowsPitch + 3) & ~3) + kRowsWarps * kRowsWarpWords) * sizeof(float);
+static size_t lookup_rows_smem_bytes(int Q) {
+  return (size_t)(((kRowsK2 * (Q | 1) + 3) & ~3) + kRowsWarps * kRowsWarpWords) * sizeof(float);
+}
+
+// Default shape of the kernel; PF_LOOKUP_Q / PF_LOOKUP_OCC select the other compiled shapes for A/B timing.
+#ifndef PF_ROWS_Q
+#define PF_ROWS_Q 48
+#endif
+
+template <int kDiv, bool kDbg>
+static void launch_rows_shape(const LookupParams &p, bool dual, int q, int occ, cudaStream_t st) {
+#define PF_ROWS_SHAPE(Q, OCC)                                                                       \
+  if (q == Q && occ == OCC) {                                                                       \
+    dim3 grid(ceil_div(p.N, Q), p.L * (dual ? 2 : 1), p.B);                                         \
+    lookup_rows_kernel<kDiv, kDbg, Q, OCC><<<grid, kRowsThreads, lookup_rows_smem_bytes(Q), st>>>(p); \
+    return;                                                                                         \
+  }
+  if constexpr (kDiv == PF_DIV_ATEN_CUDA && !kDbg) {   // the tuning shapes exist for the production flavour only
+    PF_ROWS_SHAPE(96, 3) PF_ROWS_SHAPE(96, 4) PF_ROWS_SHAPE(48, 3) PF_ROWS_SHAPE(48, 4) PF_ROWS_SHAPE(48, 6)
+    PF_ROWS_SHAPE(24, 4) PF_ROWS_SHAPE(24, 6) PF_ROWS_SHAPE(24, 8)
+  }
+  q = PF_ROWS_Q, occ = PF_ROWS_MIN_CTAS;
+  PF_ROWS_SHAPE(PF_ROWS_Q, PF_ROWS_MIN_CTAS)
+#undef PF_ROWS_SHAPE
 }
 
 static int launch_lookup_rows(const LookupParams &p, bool dual, cudaStream_t st, const char *who) {
-  dim3 grid(ceil_div(p.N, kRowsQ), p.L * (dual ? 2 : 1), p.B);
-  const size_t smem = lookup_rows_smem_bytes();
+  static const int q = getenv("PF_LOOKUP_Q") ? atoi(getenv("PF_LOOKUP_Q")) : PF_ROWS_Q;
+  static const int occ = getenv("PF_LOOKUP_OCC") ? atoi(getenv("PF_LOOKUP_OCC")) : PF_ROWS_MIN_CTAS;
   const bool recip = p.div_mode == PF_DIV_ATEN_CUDA;
   const bool dbg = p.dbg_own != nullptr || p.dbg_other != nullptr;
-#define PF_ROWS_LAUNCH(DIV, DBG) lookup_rows_kernel<DIV, DBG><<<grid, kRowsThreads, smem, st>>>(p)
   if (recip) {
-    if (dbg) PF_ROWS_LAUNCH(PF_DIV_ATEN_CUDA, true); else PF_ROWS_LAUNCH(PF_DIV_ATEN_CUDA, false);
+    if (dbg) launch_rows_shape<PF_DIV_ATEN_CUDA, true>(p, dual, q, occ, st); else launch_rows_shape<PF_DIV_ATEN_CUDA, false>(p, dual, q, occ, st);
   } else {
-    if (dbg) PF_ROWS_LAUNCH(PF_DIV_IEEE, true); else PF_ROWS_LAUNCH(PF_DIV_IEEE, false);
+    if (dbg) launch_rows_shape<PF_DIV_IEEE, true>(p, dual, q, occ, st); else launch_rows_shape<PF_DIV_IEEE, false>(p, dual, q, occ, st);
   }
-#undef PF_ROWS_LAUNCH
   return check_launch(who);
 }
 
@@ -717,7 +738,7 @@ static int launch_lookup_rows(const LookupParams &p, bool dual, cudaStream_t st,
 // img_rotate of the channels-last pre-rotation map: out[b, c, p] = sum_t w_t(p) raw[b, src_t(p), c].
 constexpr int kRotThreads = 256;
 constexpr int kRotPixels = 32;     // backward / scalar kernel
-constexpr int kRotFwdPixels = 8;   // forward float4 kernel: one pixel per warp, 1024 CTAs at 64x128
+constexpr int kRotFwdPixels = 16;  // forward float4 kernel: two pixels per warp, 512 CTAs at 64x128
 
 struct RotateParams {
   int B, N, h, w, L, K2, div_mode, channels_last, fuse_sum;
@@ -729,22 +750,23 @@ struct RotateParams {
   float *draw;        // bwd: [B, N, L*K2] (+=)
 };
 
-// Forward: one CTA = 32 output pixels x ALL channels.  The channels-last map makes a pixel's L*K2 floats one
-// contiguous, 16-byte aligned vector, so lanes walk float4s: 4 taps x one LDG.128 per 4 channels (ncu r01d: the
-// scalar per-level version spent 8.3 M instructions on 2.65 M outputs).  NCHW output goes through a shared
-// transpose tile [C][33]; channels-last output (and the fused `own + other` add) is written directly as float4.
+// Forward: one CTA = 16 output pixels x ALL channels, a warp = 2 pixels.  The channels-last map makes a pixel's L*K2
+// floats one contiguous, 16-byte aligned vector, so lanes walk float4s: 4 taps x 2 pixels = 8 LDG.128 in flight per
+// lane and round.  Channels-last output (and the fused `own + other` add) is written directly as float4.  NCHW output
+// goes through a pixel-major shared tile [16][C + 8] — conflict-free STS.128 in, 64-byte channel rows out, two rows
+// per warp instruction — instead of the r01 version's channel-major [C][9] tile (4-way conflicts on the way in, 32-byte
+// rows and a division per element on the way out: ncu r01e, 3.7 M instructions for 2.65 M outputs).
 __global__ void __launch_bounds__(kRotThreads) rotate_fwd_kernel(const RotateParams p) {
-  extern __shared__ float tile[];  // [C][kRotFwdPixels + 1] (NCHW only), then one Taps4 per pixel
-  constexpr int kTP = kRotFwdPixels + 1;
-  const int C = p.L * p.K2, C4 = C >> 2;
-  Taps4 *taps = reinterpret_cast<Taps4 *>(tile + (p.channels_last ? 0 : C * kTP + (C & 1)));
+  extern __shared__ __align__(16) float tile[];  // [kRotFwdPixels][Cp] (NCHW only), then one Taps4 per pixel
+  const int C = p.L * p.K2, C4 = C >> 2, Cp = C + 8;
+  Taps4 *taps = reinterpret_cast<Taps4 *>(tile + (p.channels_last ? 0 : kRotFwdPixels * Cp));
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * kRotFwdPixels;
-  if (threadIdx.x < kRotFwdPixels && n0 + threadIdx.x < p.N) {
+  if (threadIdx.x < kRotFwdPixels) {
     // module-local cyclic sampler of projection_prim_ortho.py:119-135 on the [.., h, w] map
     const float *gx = p.grid_c2w + (long long)b * p.grid_bs;
-    const int n = n0 + threadIdx.x;
+    const int n = min(n0 + (int)threadIdx.x, p.N - 1);
     const float x = remainder_pos(__ldg(gx + n), p.axW.size);
     const float y = __ldg(gx + p.N + n);
     Taps4 t = clamp_taps(make_taps(to_sample_coord(x, p.axW, p.div_mode), to_sample_coord(y, p.axH, p.div_mode)), p.h, p.w);
@@ -754,47 +776,57 @@ __global__ void __launch_bounds__(kRotThreads) rotate_fwd_kernel(const RotatePar
   __syncthreads();
   const float4 *src = reinterpret_cast<const float4 *>(opaque(p.raw + (long long)b * p.N * C));
   float4 *out_cl = reinterpret_cast<float4 *>(opaque(p.out + (long long)b * p.N * C));
-#pragma unroll 1
-  for (int qi = 0; qi < kRotFwdPixels / (kRotThreads / 32); ++qi) {
-    const int q = warp * (kRotFwdPixels / (kRotThreads / 32)) + qi;
-    if (n0 + q >= p.N) break;
-    const Taps4 t = taps[q];
-    const float4 *s_nw = src + t.o_nw, *s_ne = src + t.o_ne, *s_sw = src + t.o_sw, *s_se = src + t.o_se;
-    for (int c4 = lane; c4 < C4; c4 += 32) {
-      const float4 a = __ldg(s_nw + c4), bq = __ldg(s_ne + c4), c = __ldg(s_sw + c4), d = __ldg(s_se + c4);
-      float4 r;
-      r.x = __fmaf_rn(d.x, t.se, __fmaf_rn(c.x, t.sw, __fmaf_rn(bq.x, t.ne, __fmul_rn(a.x, t.nw))));
-      r.y = __fmaf_rn(d.y, t.se, __fmaf_rn(c.y, t.sw, __fmaf_rn(bq.y, t.ne, __fmul_rn(a.y, t.nw))));
-      r.z = __fmaf_rn(d.z, t.se, __fmaf_rn(c.z, t.sw, __fmaf_rn(bq.z, t.ne, __fmul_rn(a.z, t.nw))));
-      r.w = __fmaf_rn(d.w, t.se, __fmaf_rn(c.w, t.sw, __fmaf_rn(bq.w, t.ne, __fmul_rn(a.w, t.nw))));
+  constexpr int kPerWarp = kRotFwdPixels / (kRotThreads / 32);   // 2
+  const int q0 = warp * kPerWarp;
+  Taps4 t[kPerWarp];
+#pragma unroll
+  for (int i = 0; i < kPerWarp; ++i) t[i] = taps[q0 + i];
+  for (int c4 = lane; c4 < C4; c4 += 32) {
+    float4 r[kPerWarp];
+#pragma unroll
+    for (int i = 0; i < kPerWarp; ++i) {
+      const float4 a = __ldg(src + t[i].o_nw + c4), bq = __ldg(src + t[i].o_ne + c4);
+      const float4 c = __ldg(src + t[i].o_sw + c4), d = __ldg(src + t[i].o_se + c4);
+      r[i].x = __fmaf_rn(d.x, t[i].se, __fmaf_rn(c.x, t[i].sw, __fmaf_rn(bq.x, t[i].ne, __fmul_rn(a.x, t[i].nw))));
+      r[i].y = __fmaf_rn(d.y, t[i].se, __fmaf_rn(c.y, t[i].sw, __fmaf_rn(bq.y, t[i].ne, __fmul_rn(a.y, t[i].nw))));
+      r[i].z = __fmaf_rn(d.z, t[i].se, __fmaf_rn(c.z, t[i].sw, __fmaf_rn(bq.z, t[i].ne, __fmul_rn(a.z, t[i].nw))));
+      r[i].w = __fmaf_rn(d.w, t[i].se, __fmaf_rn(c.w, t[i].sw, __fmaf_rn(bq.w, t[i].ne, __fmul_rn(a.w, t[i].nw))));
+    }
+#pragma unroll
+    for (int i = 0; i < kPerWarp; ++i) {
       if (p.channels_last) {
-        float4 *o = out_cl + (long long)(n0 + q) * C4 + c4;
-        if (p.fuse_sum) {   // corr_A + corr_B_A (core/prior_raft.py:187)
-          const float4 own = *o;
-          r.x = __fadd_rn(own.x, r.x), r.y = __fadd_rn(own.y, r.y), r.z = __fadd_rn(own.z, r.z), r.w = __fadd_rn(own.w, r.w);
+        if (n0 + q0 + i < p.N) {
+          float4 *o = out_cl + (long long)(n0 + q0 + i) * C4 + c4;
+          if (p.fuse_sum) {   // corr_A + corr_B_A (core/prior_raft.py:187)
+            const float4 own = *o;
+            r[i].x = __fadd_rn(own.x, r[i].x), r[i].y = __fadd_rn(own.y, r[i].y);
+            r[i].z = __fadd_rn(own.z, r[i].z), r[i].w = __fadd_rn(own.w, r[i].w);
+          }
+          *o = r[i];
         }
-        *o = r;
       } else {
-        float *tcol = tile + (c4 * 4) * kTP + q;
-        tcol[0] = r.x, tcol[kTP] = r.y, tcol[2 * kTP] = r.z, tcol[3 * kTP] = r.w;
+        *reinterpret_cast<float4 *>(tile + (q0 + i) * Cp + 4 * c4) = r[i];
       }
     }
   }
   if (!p.channels_last) {
     __syncthreads();
-    // each channel row of the CTA is kRotFwdPixels consecutive floats (one 32-byte sector)
-    for (int i = threadIdx.x; i < C * kRotFwdPixels; i += kRotThreads) {
-      const int ch = i / kRotFwdPixels, qq = i - ch * kRotFwdPixels;
-      if (n0 + qq < p.N) {
-        float *o = p.out + ((long long)b * C + ch) * p.N + n0 + qq;
-        *o = p.fuse_sum ? __fadd_rn(*o, tile[ch * kTP + qq]) : tile[ch * kTP + qq];
+    // 64-byte channel rows: lanes 0-15 write row c, lanes 16-31 row c + 1
+    const int px = lane & (kRotFwdPixels - 1), par = lane >> 4;
+    if (n0 + px < p.N) {
+      float *o = opaque(p.out + (long long)b * C * p.N + n0 + px);
+      const float *tp = tile + px * Cp;
+#pragma unroll 4
+      for (int c = 2 * warp + par; c < C; c += 2 * (kRotThreads / 32)) {
+        float *oc = o + (long long)c * p.N;
+        *oc = p.fuse_sum ? __fadd_rn(*oc, tp[c]) : tp[c];
       }
     }
   }
 }
 
 static size_t rotate_fwd_smem_bytes(int C, int channels_last) {
-  return (channels_last ? 0 : ((size_t)C * (kRotFwdPixels + 1) + (C & 1)) * sizeof(float)) + kRotFwdPixels * sizeof(Taps4);
+  return (channels_last ? 0 : (size_t)kRotFwdPixels * (C + 8) * sizeof(float)) + kRotFwdPixels * sizeof(Taps4);
 }
 
 template <bool kBwd>
