@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 2
+#define PF_ABI_VERSION 3
 #define PF_MAX_LEVELS 4
 
 /* `tensor / python_scalar`: IEEE division on CPU, multiply by fp32 reciprocal in ATen's CUDA
@@ -43,7 +43,7 @@ enum pf_volume_mode {
 
 int pf_abi_version(void);
 const char *pf_last_error(void);
-/* Compile-time facts of the build: "sm_100a;tcgen05;tma;abi=2". */
+/* Compile-time facts of the build: "sm_100a;tcgen05;tma;abi=3". */
 const char *pf_build_info(void);
 
 /* ------------------------------------------------------------------------------------------------
@@ -97,6 +97,10 @@ typedef struct pf_lookup_args {
   int out_channels_last;               /* 1: out_own / out_other are [B, h, w, L*(2r+1)^2]        */
   int fuse_sum;                        /* 1: out_own = own + other (core/prior_raft.py:187-188),  */
                                        /*    out_other is not written (may be NULL)               */
+  float *scratch_own;                  /* optional [B, h, w, L*(2r+1)^2] (caller-owned).  With    */
+                                       /* fuse_sum and NCHW output the own view is staged here    */
+                                       /* channels-last and added in the rotate kernel's single   */
+                                       /* write pass instead of a read-modify-write of out_own    */
 } pf_lookup_args;
 int pf_lookup_dual(const pf_lookup_args *args, void *stream);
 

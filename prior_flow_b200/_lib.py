@@ -11,7 +11,7 @@ import threading
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libpriorcorr.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LEVELS = 4
 
 DIV_IEEE, DIV_ATEN_CUDA = 0, 1
@@ -36,7 +36,7 @@ class LookupArgs(C.Structure):
                 ("grid_w2c", _fp), ("grid_c2w", _fp), ("grid_batch_stride", C.c_longlong),
                 ("out_own", _fp), ("out_other", _fp), ("scratch", _fp),
                 ("dbg_own_xy", _fp), ("dbg_other_xy", _fp),
-                ("out_channels_last", C.c_int), ("fuse_sum", C.c_int)]
+                ("out_channels_last", C.c_int), ("fuse_sum", C.c_int), ("scratch_own", _fp)]
 
 
 class OnTheFlyArgs(C.Structure):

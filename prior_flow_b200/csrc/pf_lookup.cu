@@ -748,6 +748,7 @@ struct RotateParams {
   const float *raw;   // fwd: [B, N, L*K2] in.   bwd: unused
   float *out;         // fwd: out_other (or out_own when fuse_sum), [B, L*K2, N] or channels-last.  bwd: incoming gradient
   float *draw;        // bwd: [B, N, L*K2] (+=)
+  const float *own_cl;  // fwd, NCHW + fuse_sum: the own view staged channels-last [B, N, L*K2]; added before the single write pass
 };
 
 // Forward: one CTA = 16 output pixels x ALL channels, a warp = 2 pixels.  The channels-last map makes a pixel's L*K2
@@ -805,6 +806,11 @@ __global__ void __launch_bounds__(kRotThreads) rotate_fwd_kernel(const RotatePar
           *o = r[i];
         }
       } else {
+        if (p.own_cl != nullptr) {   // corr_A + corr_B_A with the own view read as one coalesced float4
+          const float4 own = __ldg(reinterpret_cast<const float4 *>(p.own_cl + (long long)b * p.N * C) + (long long)min(n0 + q0 + i, p.N - 1) * C4 + c4);
+          r[i].x = __fadd_rn(own.x, r[i].x), r[i].y = __fadd_rn(own.y, r[i].y);
+          r[i].z = __fadd_rn(own.z, r[i].z), r[i].w = __fadd_rn(own.w, r[i].w);
+        }
         *reinterpret_cast<float4 *>(tile + (q0 + i) * Cp + 4 * c4) = r[i];
       }
     }
@@ -819,7 +825,7 @@ __global__ void __launch_bounds__(kRotThreads) rotate_fwd_kernel(const RotatePar
 #pragma unroll 4
       for (int c = 2 * warp + par; c < C; c += 2 * (kRotThreads / 32)) {
         float *oc = o + (long long)c * p.N;
-        *oc = p.fuse_sum ? __fadd_rn(*oc, tp[c]) : tp[c];
+        *oc = (p.fuse_sum && p.own_cl == nullptr) ? __fadd_rn(*oc, tp[c]) : tp[c];
       }
     }
   }
@@ -964,6 +970,7 @@ static void fill_rotate_params(const pf_lookup_args *a, RotateParams &rp) {
   rp.raw = a->scratch;
   rp.out = a->fuse_sum ? a->out_own : a->out_other;
   rp.draw = nullptr;
+  rp.own_cl = nullptr;
 }
 
 template <bool kBwd>
@@ -988,7 +995,8 @@ static int launch_lookup(const LookupParams &p, int radius, bool dual, cudaStrea
 
 // img_rotate of a channels-last pre-rotation map, shared with the on-the-fly path (pf_onthefly.cu).
 int rotate_forward(int batch, int h, int w, int num_levels, int radius, int div_mode, const float *grid_c2w,
-                   long long grid_bs, const float *raw, float *out, int channels_last, int fuse_sum, cudaStream_t st) {
+                   long long grid_bs, const float *raw, float *out, int channels_last, int fuse_sum, cudaStream_t st,
+                   const float *own_cl) {
   const int k = 2 * radius + 1;
   RotateParams rp;
   rp.B = batch;
@@ -1007,6 +1015,7 @@ int rotate_forward(int batch, int h, int w, int num_levels, int radius, int div_
   rp.raw = raw;
   rp.out = out;
   rp.draw = nullptr;
+  rp.own_cl = (fuse_sum && !channels_last) ? own_cl : nullptr;
   const int C = rp.L * rp.K2;
   if (C % 4 == 0 && (((uintptr_t)raw | (uintptr_t)out) & 15) == 0) {
     const size_t smem = rotate_fwd_smem_bytes(C, channels_last);
@@ -1034,6 +1043,15 @@ extern "C" int pf_lookup_dual(const pf_lookup_args *a, void *stream) {
     PF_REQUIRE(!dual || a->other[l] != nullptr, "pf_lookup_dual: other[%d] is null", l);
   }
   cudaStream_t st = (cudaStream_t)stream;
+  // fused sum into an NCHW tensor: stage the own view channels-last (coalesced 324-byte runs, no transpose tile) and
+  // let the rotate kernel add it while it transposes — one write pass over out_own instead of write + read-modify-write
+  const int C_all = p.L * (2 * a->radius + 1) * (2 * a->radius + 1);
+  const bool stage_own = dual && a->fuse_sum && !a->out_channels_last && a->scratch_own != nullptr && C_all % 4 == 0 &&
+                         (((uintptr_t)a->scratch_own | (uintptr_t)a->scratch | (uintptr_t)a->out_own) & 15) == 0;
+  if (stage_own) {
+    p.channels_last = 1;
+    p.out_own = a->scratch_own;
+  }
   // radius 4 (the model's) runs the column-walk kernel; other radii the generic tap-per-lane kernel
   // (PF_LOOKUP_LEGACY=1 forces the latter, for A/B timing only)
   static const bool legacy = getenv("PF_LOOKUP_LEGACY") != nullptr && getenv("PF_LOOKUP_LEGACY")[0] == '1';
@@ -1046,7 +1064,7 @@ extern "C" int pf_lookup_dual(const pf_lookup_args *a, void *stream) {
     // core/corr.py:137-138 — img_rotate of the [B, L*81, h, w] map with grid_c2w.
     return rotate_forward(a->batch, a->h, a->w, a->num_levels, a->radius, a->div_mode, a->grid_c2w,
                           a->grid_batch_stride, a->scratch, a->fuse_sum ? a->out_own : a->out_other, a->out_channels_last,
-                          a->fuse_sum, st);
+                          a->fuse_sum, st, stage_own ? a->scratch_own : nullptr);
   }
   return 0;
 }

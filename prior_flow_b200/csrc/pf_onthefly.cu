@@ -243,6 +243,6 @@ extern "C" int pf_lookup_onthefly(const pf_onthefly_args *a, void *stream) {
   if (int e = check_launch("pf_lookup_onthefly")) return e;
   if (dual)
     return rotate_forward(a->batch, a->h, a->w, a->num_levels, a->radius, a->div_mode, a->grid_c2w,
-                          a->grid_batch_stride, a->scratch, a->out_other, 0, 0, (cudaStream_t)stream);
+                          a->grid_batch_stride, a->scratch, a->out_other, 0, 0, (cudaStream_t)stream, nullptr);
   return 0;
 }

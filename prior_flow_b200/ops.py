@@ -183,6 +183,10 @@ def lookup(coords: torch.Tensor, pyr_own: Sequence[torch.Tensor], pyr_other: Opt
             a.other = _lib.level_ptrs(other)
             a.grid_w2c, a.grid_c2w, a.grid_batch_stride = gw.data_ptr(), gc.data_ptr(), bs_w
             a.scratch = scratch.data_ptr()
+            if fuse_sum and not channels_last:
+                # the own view is staged channels-last and summed in the rotate kernel's single NCHW write pass
+                scratch_own = torch.empty_like(out_own)
+                a.scratch_own = scratch_own.data_ptr()
             if not fuse_sum:
                 out_other = torch.empty_like(out_own)
                 a.out_other = out_other.data_ptr()
