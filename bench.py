@@ -273,34 +273,57 @@ def main_ours(a):
         pa, pb = ops.volume_pyramid(fm[0], fm[1], 4), ops.volume_pyramid(fm[2], fm[3], 4)
         flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
-        def kernel_ms(fn, reps=30, graph=True):
-            """Average GPU duration of `fn` (CUDA events on the launching stream, L2 flushed before every launch).  The
-            call is replayed from a CUDA graph so that the host side of the call (allocation, ctypes) is not in the
-            measurement — the same way the model step above runs it."""
+        def kernel_ms(fn, reps=30, graph=True, K=10):
+            """Average GPU duration of `fn` with a cold L2 (CUDA events on the launching stream).  The event timer of
+            these boxes ticks in ~2 us steps and a graph launch costs ~4 us, both of the order of the kernels timed here,
+            so K x (flush L2, fn) and K x (flush L2) are each captured in one CUDA graph — the way the model step runs the
+            call, no host work between launches — and the per-call time is the difference of the two replays / K."""
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
-            run = fn
             if graph:
                 try:
-                    side = torch.cuda.Stream()
-                    side.wait_stream(torch.cuda.current_stream())
-                    with torch.cuda.stream(side):
-                        fn()
-                    torch.cuda.current_stream().wait_stream(side)
-                    torch.cuda.synchronize()
-                    g_ = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g_):
-                        keep = fn()   # noqa: F841 - outputs live in the graph's pool
-                    run = g_.replay
-                except Exception:      # noqa: BLE001
-                    run = fn
+                    def capture(body):
+                        side = torch.cuda.Stream()
+                        side.wait_stream(torch.cuda.current_stream())
+                        with torch.cuda.stream(side):
+                            body()
+                        torch.cuda.current_stream().wait_stream(side)
+                        torch.cuda.synchronize()
+                        g_ = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g_):
+                            keep = [body() for _ in range(K)]
+                        return g_, keep
+
+                    def flush_and_call():
+                        flush.zero_()
+                        return fn()
+
+                    g_call, keep1 = capture(flush_and_call)          # noqa: F841 - outputs live in the graph's pool
+                    g_flush, keep2 = capture(lambda: flush.zero_())  # noqa: F841
+
+                    def replay_ms(g_):
+                        ts = []
+                        for _ in range(max(3, reps // K)):
+                            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            s.record()
+                            g_.replay()
+                            e.record()
+                            torch.cuda.synchronize()
+                            ts.append(s.elapsed_time(e))
+                        ts.sort()
+                        return ts[len(ts) // 2]
+
+                    replay_ms(g_call), replay_ms(g_flush)
+                    return (replay_ms(g_call) - replay_ms(g_flush)) / K
+                except Exception as e_:      # noqa: BLE001
+                    print(f"[bench] kernel_ms: graph capture failed ({type(e_).__name__}: {e_}); timing eager launches", file=sys.stderr)
             ts = []
             for _ in range(reps):
                 flush.zero_()
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
-                run()
+                fn()
                 e.record()
                 torch.cuda.synchronize()
                 ts.append(s.elapsed_time(e))
@@ -310,17 +333,23 @@ def main_ours(a):
         fill_gbs = (1 << 30) / kernel_ms(lambda: fill_buf.fill_(1), reps=10, graph=False) / 1e6   # what a write-only stream sustains here
         del fill_buf
         look_ms = kernel_ms(lambda: ops.lookup(coords, pa, pb, grids["A2B_W2C_8x"], grids["B2A_8x"], 4))
+        fused_ms = kernel_ms(lambda: ops.lookup(coords, pa, pb, grids["A2B_W2C_8x"], grids["B2A_8x"], 4, fuse_sum=True))
         vol_ms = kernel_ms(lambda: ops.volume_pyramid(fm[0], fm[1], 4))
         look_bytes = B * (N * 2 * 4 * 100 * 4 + 2 * N * 324 * 4 + 3 * 2 * N * 4)          # 47.45 MB at B=1
         vol_bytes = B * (sum(N * (h >> l) * (w >> l) * 4 for l in range(4)) + 2 * 256 * N * 4)
         achieved = look_bytes / look_ms / 1e6
-        roofline = {"kernel": "DCCL lookup call: lookup_kernel<4> + rotate_kernel (24 calls per pair)", "bound": "hbm",
+        roofline = {"kernel": "DCCL lookup call: lookup_rows_kernel + rotate_fwd_kernel (24 calls per pair)", "bound": "hbm",
                     "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
-                    # dram__bytes_read.sum + dram__bytes_write.sum of lookup_kernel + rotate_fwd_kernel, one launch each, ncu --set
-                    # full, cold cache (profiles/r01e_ncu_raw_*.csv; B = 1, 64x128): 53.68 + 1.85 + 9.63 + 0 MB
-                    "traffic": 65.16e6 if (B, h, w) == (1, 64, 128) else None,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of lookup_rows_kernel + rotate_fwd_kernel, one launch each, ncu
+                    # --set full, cold cache (profiles/r02e_ncu_raw_*.csv; B = 1, 64x128): 56.30 + 3.54 + 9.62 + 0 MB.  Reads are
+                    # 2.1x the algorithmic 26.2 MB because a 40-byte footprint row straddles 32-byte sectors; the outputs
+                    # (21.2 MB) are still dirty in L2 when the kernels end
+                    "traffic": 69.46e6 if (B, h, w) == (1, 64, 128) else None,
                     "peak_source": peak_src, "ms_per_launch": round(look_ms, 4),
                     "algorithmic_bytes_per_launch": look_bytes,
+                    # the call as the model issues it (own + other summed, core/prior_raft.py:187): one output tensor
+                    "ms_per_launch_fused_sum": round(fused_ms, 4),
+                    "timing": "difference of 10 x (L2 flush, call) and 10 x (L2 flush) CUDA-graph replays / 10, CUDA events",
                     "other_kernels": {"volume_pyramid(tcgen05, fp32 split) per view": {
                         "ms": round(vol_ms, 4), "GB/s": round(vol_bytes / vol_ms / 1e6, 1), "frac_hbm": round(vol_bytes / vol_ms / 1e6 / hbm, 4),
                         "frac_of_write_only_stream": round(vol_bytes / vol_ms / 1e6 / fill_gbs, 4), "write_only_stream_GB/s": round(fill_gbs, 1),
