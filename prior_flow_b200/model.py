@@ -218,9 +218,13 @@ class PriOrRAFT(nn.Module):
         self.update_block = UpdateBlock(cor_planes, 128)
 
     def to_channels_last(self):
-        """NHWC weights + NHWC lookup outputs: cuDNN's tensor-core kernels run without NCHW<->NHWC conversions."""
+        """NHWC weights for the context encoder and the two update blocks + NHWC lookup outputs: cuDNN's tensor-core
+        kernels then run without an NCHW<->NHWC conversion around every convolution.  The feature encoder stays NCHW:
+        its InstanceNorm layers are NCHW-only in ATen and would convert back and forth at full resolution."""
         self.channels_last = True
-        return self.to(memory_format=torch.channels_last)
+        for m in (self.cnet, self.ODDC, self.update_block):
+            m.to(memory_format=torch.channels_last)
+        return self
 
     def freeze_bn(self):
         for m in self.modules():
@@ -286,6 +290,11 @@ class PriOrRAFT(nn.Module):
                 # corr_A + corr_B_A and corr_B + corr_A_B (prior_raft.py:185-188), the adds fused into the rotate kernel
                 corr_A = lookup.summed(coords1_A, pyr_A, pyr_B, g["A2B_W2C_8x"], g["B2A_8x"], self.channels_last)
                 corr_B = lookup.summed(coords1_B, pyr_B, pyr_A, g["B2A_W2C_8x"], g["A2B_8x"], self.channels_last)
+                if self.channels_last:
+                    # torch.cat falls back to NCHW as soon as ONE input is NCHW (and every convolution behind it then
+                    # pays a layout copy): hand the update blocks their 2- and 4-channel inputs in NHWC as well
+                    cl = lambda t: t.contiguous(memory_format=torch.channels_last)
+                    flow_A, flow_B, flow_B_A, flaw_A, flaw_B_A = cl(flow_A), cl(flow_B), cl(flow_B_A), cl(flaw_A), cl(flaw_B_A)
                 net_A, mask_A, d_A = self.ODDC(net_A, inp_A, flow_A, corr_A, flaw_A, flow_B_A, flaw_B_A, want_mask=want_up)
                 net_B, mask_B, d_B = self.update_block(net_B, inp_B, corr_B, flow_B, want_mask=want_up and not test_mode)
             coords1_A = coords1_A + d_A

@@ -68,6 +68,21 @@ def test_flow_matches_eager_path_on_same_gpu(models):
     assert mean_epe(a.cpu().numpy(), b.cpu().numpy()) < 1e-3
 
 
+def test_channels_last_model_matches_golden(models):
+    """NHWC context encoder / update blocks + NHWC fused lookups (model.to_channels_last()): same flow as the reference."""
+    from prior_flow_b200.model import PriOrRAFT
+    ours, _, im1, im2 = models
+    cl = PriOrRAFT().cuda().eval()
+    cl.load_state_dict(ours.state_dict(), strict=True)
+    cl = cl.to_channels_last()
+    g = golden("e2e")
+    with torch.no_grad():
+        flow12 = cl(im1, im2, iters=12, test_mode=True)
+        flow_init = cl(im1, im2, iters=2, init_flow=torch.from_numpy(cases.flow(seed=9, B=1, sigma=2.0)).cuda(), test_mode=True)
+    assert mean_epe(flow12.cpu().numpy(), g["flow12"]) < 1e-3
+    assert mean_epe(flow_init.cpu().numpy(), g["flow_init"]) < 1e-3
+
+
 def test_fast_volume_mode_is_separately_toleranced(models):
     """f16 single-product volume (TF32-class): stated tolerance 5e-3 px mean EPE at 4 iterations."""
     ours, _, im1, im2 = models
