@@ -93,6 +93,19 @@ class Encoder(nn.Module):
 
 
 # --------------------------------------------------------------------------------------- update blocks
+FUSE_CONV_RELU = True   # inference only; set False to run every conv -> bias add -> ReLU as three ATen launches
+
+
+def _conv_relu(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    """F.relu(conv(x)).  In fp32 inference on CUDA this is ONE cuDNN launch (conv + bias + ReLU in the epilogue) instead
+    of cudnn_convolution, a separate bias add and a clamp — 168 of the ~420 element-wise launches of a 12-iteration
+    forward (profiles/r02e_e2e_breakdown.txt)."""
+    if (FUSE_CONV_RELU and x.is_cuda and x.dtype == torch.float32 and conv.bias is not None and not torch.is_grad_enabled()
+            and not torch.is_autocast_enabled()):
+        return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+    return F.relu(conv(x))
+
+
 class FlowHead(nn.Module):
     def __init__(self, cin: int = 128, hidden: int = 256):
         super().__init__()
@@ -101,7 +114,7 @@ class FlowHead(nn.Module):
         self.relu = nn.ReLU(inplace=True)
 
     def forward(self, x):
-        return self.conv2(self.relu(self.conv1(x)))
+        return self.conv2(_conv_relu(self.conv1, x))
 
 
 class SepConvGRU(nn.Module):
@@ -134,9 +147,9 @@ class MotionEncoder(nn.Module):
         self.conv = nn.Conv2d(64 + 192, 128 - 2, 3, padding=1)
 
     def forward(self, flow, corr):
-        cor = F.relu(self.convc2(F.relu(self.convc1(corr))))
-        flo = F.relu(self.convf2(F.relu(self.convf1(flow))))
-        return torch.cat([F.relu(self.conv(torch.cat([cor, flo], dim=1))), flow], dim=1)
+        cor = _conv_relu(self.convc2, _conv_relu(self.convc1, corr))
+        flo = _conv_relu(self.convf2, _conv_relu(self.convf1, flow))
+        return torch.cat([_conv_relu(self.conv, torch.cat([cor, flo], dim=1)), flow], dim=1)
 
 
 class DualMotionEncoder(nn.Module):
@@ -155,11 +168,11 @@ class DualMotionEncoder(nn.Module):
         self.conv_A = nn.Conv2d(128 + 64 + 64 + 16, 128 - 4, 3, padding=1)
 
     def forward(self, flow_A, corr_A, flaw_A, flow_B_A, flaw_B_A):
-        cor = F.relu(self.convc2_A(F.relu(self.convc1_A(corr_A))))
-        fa = F.relu(self.convf2_A(F.relu(self.convf1_A(flow_A))))
-        fb = F.relu(self.convf2_B(F.relu(self.convf1_B(flow_B_A))))
-        conf = F.relu(self.conv_conf2(F.relu(self.conv_conf1(torch.cat([flaw_A, flaw_B_A], dim=1)))))
-        out = F.relu(self.conv_A(torch.cat([cor, fa, fb, conf], dim=1)))
+        cor = _conv_relu(self.convc2_A, _conv_relu(self.convc1_A, corr_A))
+        fa = _conv_relu(self.convf2_A, _conv_relu(self.convf1_A, flow_A))
+        fb = _conv_relu(self.convf2_B, _conv_relu(self.convf1_B, flow_B_A))
+        conf = _conv_relu(self.conv_conf2, _conv_relu(self.conv_conf1, torch.cat([flaw_A, flaw_B_A], dim=1)))
+        out = _conv_relu(self.conv_A, torch.cat([cor, fa, fb, conf], dim=1))
         return torch.cat([out, flow_A, flow_B_A], dim=1)
 
 
@@ -173,7 +186,7 @@ class _UpdateBase(nn.Module):
 
     def _step(self, net, inp, motion, want_mask=True):
         net = self.gru(net, torch.cat([inp, motion], dim=1))
-        mask = 0.25 * self.mask(net) if want_mask else None
+        mask = 0.25 * self.mask[2](_conv_relu(self.mask[0], net)) if want_mask else None
         return net, mask, self.flow_head(net)
 
 
