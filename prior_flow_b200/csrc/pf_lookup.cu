@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(kLookupThreads, 4) lookup_kernel(const LookupP
 //     levels 1-3 — and an all-interior shortcut (one base pointer, no clamps).
 //   * the lattice assumption (corner sharing between neighbouring cells) is verified per triple with one vote;
 //     the rare exceptions (a coordinate within an ulp of an integer) take a direct four-load path.
-//   * outputs go through one [81][97] shared tile per CTA (96 queries x one level x one branch) and leave as
+//   * outputs go through one [81][Q|1] shared tile per CTA (Q = 48 queries x one level x one branch) and leave as
 //     128-byte rows (NCHW) or 324-byte channel runs (channels-last scratch).
 // Coordinate arithmetic is shortened with exact identities only (see sample_coord_x): results are bit-identical
 // to the long chain, which the debug dump (kDbg) still proves tap by tap.
@@ -431,7 +431,7 @@ template <int kDiv, bool kDbg, int kRowsQ, int BRANCH>
 __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const int lvl) {
   constexpr int kRowsPitch = kRowsQ | 1;   // tile pitch (odd -> conflict-free both ways)
   extern __shared__ float4 smem4[];
-  float *tile = reinterpret_cast<float *>(smem4);                                  // [81][97]
+  float *tile = reinterpret_cast<float *>(smem4);                                  // [81][Q|1]
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   float *wbase = tile + ((kRowsK2 * kRowsPitch + 3) & ~3) + warp * kRowsWarpWords;
   int *tyo0 = reinterpret_cast<int *>(wbase);            // [3][12] row offsets of tap y0 (entry 9 = o1 of row 8)
