@@ -20,7 +20,7 @@ int check_launch(const char *what);
 // pf_lookup.cu: img_rotate of a channels-last [B, N, L*K2] map into [B, L*K2, N]
 int rotate_forward(int batch, int h, int w, int num_levels, int radius, int div_mode, const float *grid_c2w,
                    long long grid_bs, const float *raw, float *out, int channels_last, int fuse_sum, cudaStream_t st,
-                   const float *own_cl);
+                   const float *own_cl, bool after_lookup_rows = false);
 
 #define PF_REQUIRE(cond, ...)            \
   do {                                   \

@@ -689,6 +689,9 @@ template <int kDiv, bool kDbg, int kRowsQ, int kMinCtas>
 __global__ void __launch_bounds__(kRowsThreads, kMinCtas) lookup_rows_kernel(const LookupParams p) {
   // heaviest CTAs first: other view level 0..L-1, then own view
   const int y = blockIdx.y;
+  // lets the dependent rotate kernel be scheduled as soon as the LAST CTA of this grid has started (it still waits for
+  // this grid's completion before reading anything this grid writes)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (p.dual && y < p.L)
     lookup_rows_body<kDiv, kDbg, kRowsQ, 1>(p, y);
   else
@@ -774,6 +777,10 @@ __global__ void __launch_bounds__(kRotThreads) rotate_fwd_kernel(const RotatePar
     t.o_nw *= C4, t.o_ne *= C4, t.o_sw *= C4, t.o_se *= C4;   // float4 offsets into the channels-last map
     taps[threadIdx.x] = t;
   }
+  // programmatic dependent launch: everything above reads only grid_c2w (an input), so this CTA may be resident and
+  // have its taps ready while the last CTAs of lookup_rows_kernel are still running; raw / own_cl / out are touched
+  // only after the primary grid has completed and flushed (no-op when launched without the attribute)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
   const float4 *src = reinterpret_cast<const float4 *>(opaque(p.raw + (long long)b * p.N * C));
   float4 *out_cl = reinterpret_cast<float4 *>(opaque(p.out + (long long)b * p.N * C));
@@ -996,7 +1003,7 @@ static int launch_lookup(const LookupParams &p, int radius, bool dual, cudaStrea
 // img_rotate of a channels-last pre-rotation map, shared with the on-the-fly path (pf_onthefly.cu).
 int rotate_forward(int batch, int h, int w, int num_levels, int radius, int div_mode, const float *grid_c2w,
                    long long grid_bs, const float *raw, float *out, int channels_last, int fuse_sum, cudaStream_t st,
-                   const float *own_cl) {
+                   const float *own_cl, bool after_lookup_rows) {
   const int k = 2 * radius + 1;
   RotateParams rp;
   rp.B = batch;
@@ -1020,7 +1027,22 @@ int rotate_forward(int batch, int h, int w, int num_levels, int radius, int div_
   if (C % 4 == 0 && (((uintptr_t)raw | (uintptr_t)out) & 15) == 0) {
     const size_t smem = rotate_fwd_smem_bytes(C, channels_last);
     if (smem > 48 * 1024) cudaFuncSetAttribute(rotate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    rotate_fwd_kernel<<<dim3(ceil_div(rp.N, kRotFwdPixels), rp.B), kRotThreads, smem, st>>>(rp);
+    // PF_ROTATE_PDL=0 disables the programmatic dependent launch (A/B timing / old drivers)
+    static const bool pdl = !(getenv("PF_ROTATE_PDL") != nullptr && getenv("PF_ROTATE_PDL")[0] == '0');
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ceil_div(rp.N, kRotFwdPixels), rp.B);
+    cfg.blockDim = dim3(kRotThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && after_lookup_rows) ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, rotate_fwd_kernel, rp) != cudaSuccess) {
+      (void)cudaGetLastError();   // e.g. a driver without programmatic dependent launch: plain launch
+      rotate_fwd_kernel<<<cfg.gridDim, cfg.blockDim, smem, st>>>(rp);
+    }
     return check_launch("rotate_fwd_kernel");
   }
   dim3 grid(ceil_div(rp.N, kRotPixels), rp.L, rp.B);   // odd channel counts: scalar per-level kernel
@@ -1064,7 +1086,7 @@ extern "C" int pf_lookup_dual(const pf_lookup_args *a, void *stream) {
     // core/corr.py:137-138 — img_rotate of the [B, L*81, h, w] map with grid_c2w.
     return rotate_forward(a->batch, a->h, a->w, a->num_levels, a->radius, a->div_mode, a->grid_c2w,
                           a->grid_batch_stride, a->scratch, a->fuse_sum ? a->out_own : a->out_other, a->out_channels_last,
-                          a->fuse_sum, st, stage_own ? a->scratch_own : nullptr);
+                          a->fuse_sum, st, stage_own ? a->scratch_own : nullptr, a->radius == 4 && !legacy);
   }
   return 0;
 }
