@@ -9,7 +9,8 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 timeout 300 python scripts/kbench.py --iters 20 > gpurun_out/kbench.log 2>&1
 timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; tail -1 gpurun_out/bench.log | cut -c1-400; tail -3 gpurun_out/bench.err
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.log 2> gpurun_out/bench_reference.err; tail -1 gpurun_out/bench_reference.log | cut -c1-300
-PF_TAG=final PF_CUDNN_BENCHMARK=1 timeout 300 python scripts/e2e_breakdown.py > gpurun_out/e2e.log 2>&1
+PF_TAG=final_cl PF_CHANNELS_LAST=1 PF_CUDNN_BENCHMARK=1 timeout 300 python scripts/e2e_breakdown.py > gpurun_out/e2e.log 2>&1
+PF_TAG=final_nchw PF_CUDNN_BENCHMARK=1 timeout 300 python scripts/e2e_breakdown.py >> gpurun_out/e2e.log 2>&1
 bash scripts/profile.sh lookup_rows_kernel rotate_fwd_kernel volume_tc_kernel > gpurun_out/profile.log 2>&1
 # launch list of the bench command itself (eager launches, 1 timed step), as the profiling recipe asks
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_bench.csv \

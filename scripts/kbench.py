@@ -24,49 +24,26 @@ def peaks():
         return 6650.0, 1590.0, "fallback"
 
 
-def timeit(fn, iters, flush, K=10):
-    """Per-call GPU time with a cold L2: K x (flush, fn) and K x (flush) captured in one CUDA graph each, difference of
-    the replays / K (the event timer ticks in ~2 us steps and an eager ctypes call costs more host time than these
-    kernels run, so single eager launches between events measure the host).  Falls back to eager timing for callables
-    that cannot be captured."""
+def timeit(fn, iters, flush):
+    """Per-call GPU time, conservative: the call is captured in a CUDA graph (no host work in the timed region), the L2
+    is flushed with a memset before every replay and CUDA events bracket ONE replay — so a number includes the graph
+    launch latency (~4 us), the 2 us tick of the event timer and the write-back of the flush's dirty lines.  bench.py's
+    `roofline` uses K calls on K different working sets in one graph instead; use that for the small kernels."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-
-    def capture(body):
+    run = fn
+    try:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            body()
+            fn()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            keep = [body() for _ in range(K)]
-        return g, keep
-
-    def replay_ms(g, n):
-        ts = []
-        for _ in range(n):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            g.replay()
-            e.record()
-            torch.cuda.synchronize()
-            ts.append(s.elapsed_time(e))
-        ts.sort()
-        return ts
-
-    try:
-        def both():
-            flush.zero_()
-            return fn()
-        g1, k1 = capture(both)                    # noqa: F841
-        g0, k0 = capture(lambda: flush.zero_())   # noqa: F841
-        n = max(3, iters // 2)
-        replay_ms(g1, 1), replay_ms(g0, 1)
-        t1, t0 = replay_ms(g1, n), replay_ms(g0, n)
-        return (t1[len(t1) // 2] - t0[len(t0) // 2]) / K, (t1[0] - t0[len(t0) // 2]) / K
+            keep = fn()  # noqa: F841
+        run = g.replay
     except Exception as ex:  # noqa: BLE001
         print(f"[kbench] graph capture failed ({type(ex).__name__}); eager timing", file=sys.stderr)
     ts = []
@@ -74,7 +51,7 @@ def timeit(fn, iters, flush, K=10):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        fn()
+        run()
         e.record()
         torch.cuda.synchronize()
         ts.append(s.elapsed_time(e))
