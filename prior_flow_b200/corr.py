@@ -20,9 +20,10 @@ import torch
 
 from . import ops
 
-# Above this many query pixels the O(N^2) volume stops paying (4 GiB/view at 1024x2048) and DCCL switches to
-# the on-the-fly lookup unless told otherwise.
-ONTHEFLY_MIN_PIXELS = 128 * 256
+# mode="auto": materialise both views' pyramids while they fit comfortably in device memory — on a 180 GB B200 that
+# includes 1024x2048 (2 x 5.7 GB), where the materialised lookups are 2.9x faster end to end than the on-the-fly
+# kernel (profiles/r02f_bench_hires_*.json) — and fall back to the volume-free on-the-fly lookup beyond that.
+AUTO_MATERIALIZE_FRACTION = 0.4     # of the currently free device memory, for the two pyramids + split workspace
 
 
 class CostVolume:
@@ -72,14 +73,24 @@ class DCCL:
         if mode not in ("auto", "materialized", "onthefly"):
             raise ValueError("mode must be auto | materialized | onthefly")
         self.num_levels, self.radius, self.mode, self.volume_mode = num_levels, radius, mode, volume_mode
+        self._auto = {}
 
-    def _use_onthefly(self, h: int, w: int) -> bool:
-        return self.mode == "onthefly" or (self.mode == "auto" and h * w >= ONTHEFLY_MIN_PIXELS)
+    def _use_onthefly(self, fmap: torch.Tensor) -> bool:
+        if self.mode != "auto":
+            return self.mode == "onthefly"
+        key = (tuple(fmap.shape), str(fmap.device))
+        if key not in self._auto:      # decided once per instance and shape: both views must take the same path
+            B, C, h, w = fmap.shape
+            n = h * w
+            need = 2 * (B * n * n * 4 * sum(0.25 ** l for l in range(self.num_levels)) + 4 * B * n * C * 2)   # both views
+            free = torch.cuda.mem_get_info(fmap.device)[0] if fmap.is_cuda else 0
+            self._auto[key] = need > AUTO_MATERIALIZE_FRACTION * free
+        return self._auto[key]
 
     def build_pyramid(self, cost_volume_8):
         if isinstance(cost_volume_8, CostVolume):
             f1, f2 = cost_volume_8.fmap1, cost_volume_8.fmap2
-            if self._use_onthefly(f1.shape[2], f1.shape[3]):
+            if self._use_onthefly(f1):
                 if torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad):
                     raise NotImplementedError("the on-the-fly lookup is inference-only; use mode='materialized' to train")
                 return FeaturePyramid(f1, f2, self.num_levels)
