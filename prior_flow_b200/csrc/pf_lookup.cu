@@ -1,30 +1,26 @@
 // (b) Dual-cost pyramid lookup — DCCL.__call__ (PriOr-RAFT/core/corr.py:113-144) and
 // CorrBlock.__call__ (core/corr.py:30-51): one gather launch serving both views + one rotate launch.
 //
-// lookup_kernel — grid = (ceil(N/32) query chunks, levels x branches, batch), 256 threads.
-//   A CTA owns 32 consecutive query pixels of one level of one branch; each warp walks 4 queries.
+// Forward, radius 4 (the model's):  lookup_rows_kernel  ->  rotate_fwd_kernel   (documented where they are defined)
+// Forward, other radii; backward:   lookup_kernel<R, kBwd>  ->  rotate_fwd_kernel / rotate_kernel<kBwd>
+//
+// lookup_kernel (r01; generic radius and the scatter/backward instantiation) — grid = (ceil(N/32) query chunks,
+//   levels x branches, batch), 256 threads.  A CTA owns 32 consecutive query pixels of one level of one branch; each
+//   warp walks 4 queries, a lane owns a tap.
 //   * Window coordinates are separable: the 2r+1 x-coordinates and 2r+1 y-coordinates of a window
 //     go through the (remainder, normalise, unnormalise, floor, clamp) chain once each, on lanes
 //     0..2k-1, into a per-warp shared-memory table of {clamped offsets, validity-folded weights};
 //     a tap is then two 16-byte table reads, four adds and four multiplies away from its loads.
-//     Instruction issue — not memory — limited the earlier versions (ncu r01a: 76 % issue-slot
-//     utilisation at 13 % DRAM; r01b: 25 instructions per load, half of them integer address math).
 //   * The (k+1)^2 footprint the window touches — of the query's private plane (own view) or of the
 //     two channels of the level-0 rotation grid (other view) — is staged in shared memory with
-//     cooperative loads (one warp-wide load = ~3 coalesced row segments) whenever consecutive
-//     window cells share a corner (always, except across the x seam); taps then blend from smem.
+//     cooperative loads whenever consecutive window cells share a corner; taps then blend from smem.
 //   * Branch 0 (own view): the blend is the result.  NCHW output goes through a shared-memory
 //     transpose and is written as full 128-byte rows; channels-last output is written directly.
 //   * Branch 1 (other view): the blend of the grid is the mapped point; pyr_other[l][n] is sampled
-//     there (scale mixing is the reference's) with an interior fast path
-//     (one base pointer, immediate offsets) and no loads at all for taps entirely outside the
-//     plane.  The pre-rotation map goes to `scratch` CHANNELS-LAST ([B, N, L*81]) so that
-//     rotate_kernel reads whole 1296-byte vectors.
-// rotate_kernel — img_rotate(., grid_c2w) of that map (core/corr.py:137-138): a cross-pixel
-//   gather, hence a second pass; 32 output pixels x one level per CTA, lanes across channels, four
-//   coalesced vector reads per pixel (the 10.6 MB intermediate stays in L2), shared-memory
-//   transpose, 128-byte output rows.
-// Both kernels have a kBwd instantiation (scatter instead of gather) for training.
+//     there (scale mixing is the reference's).  The pre-rotation map goes to
+//     `scratch` CHANNELS-LAST ([B, N, L*81]) so that the rotate kernels read whole 1296-byte vectors.
+// rotate_kernel<kBwd> — scalar img_rotate(., grid_c2w) of that map (core/corr.py:137-138) and its adjoint: 32 pixels x
+//   one level per CTA, lanes across channels.  The forward of the model's shapes runs rotate_fwd_kernel (float4).
 // Coordinates are bit-exact restatements (pf_common.cuh); values are ATen's FMA chain.
 #include "pf_common.cuh"
 
