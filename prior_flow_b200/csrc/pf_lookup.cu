@@ -568,6 +568,27 @@ __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const in
         }
       } else {
         const float *gxc = opaque(gridx + col), *gyc = opaque(gxc + p.N);
+        if (!kDbg && Hl < p.h) {
+          // Scale-mixed levels: the mapped y of a tap is a convex combination of the footprint's grid-y values (all four
+          // corners of every first-sampler tap inside the grid => weights sum to 1 up to rounding).  If even the smallest
+          // of them lies below the level-l plane by a margin far above the chain's rounding (1e-2 px vs < 1e-4 px), every
+          // tap of the triple has floor(iy) >= Hl and the result is exact zeros — without touching the x channel, the
+          // coordinate chains or the other view's volume.  ~55 % of the level 1-3 triples leave here.
+          const int *yall = tyo0 + qq * 12;
+          float gmin = __ldg(gyc + yall[0]);
+#pragma unroll
+          for (int r = 1; r < 10; ++r) gmin = fminf(gmin, __ldg(gyc + yall[r]));
+          const bool inside = !act || (ex.o1 == ex.o0 + 1 && ey.o1 == ey.o0 + size1x);
+          const bool all_inside = __all_sync(0xffffffffu, inside);
+          const int gmin_bits = __reduce_min_sync(0xffffffffu, __float_as_int(gmin));   // int order == float order for values >= 0
+          if (all_inside && gmin_bits > __float_as_int((float)Hl + 0.01f)) {
+            if (act) {
+#pragma unroll
+              for (int bb = 0; bb < kRowsK; ++bb) tcol[bb * kRowsPitch + ql] = 0.f;
+            }
+            continue;
+          }
+        }
         // three window rows at a time: four rows of both grid channels (L1-resident; reloading the shared row per group
         // costs two loads and keeps the kernel at 64 registers = 4 CTAs per SM), first sampler, then the second sampler
         // with 12 plane loads per lane in flight
