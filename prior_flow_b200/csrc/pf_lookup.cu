@@ -733,8 +733,8 @@ static void launch_rows_shape(const LookupParams &p, bool dual, int q, int occ, 
     return;                                                                                         \
   }
   if constexpr (kDiv == PF_DIV_ATEN_CUDA && !kDbg) {   // the tuning shapes exist for the production flavour only
-    PF_ROWS_SHAPE(96, 3) PF_ROWS_SHAPE(96, 4) PF_ROWS_SHAPE(48, 3) PF_ROWS_SHAPE(48, 4) PF_ROWS_SHAPE(48, 6)
-    PF_ROWS_SHAPE(24, 4) PF_ROWS_SHAPE(24, 6) PF_ROWS_SHAPE(24, 8)
+    PF_ROWS_SHAPE(96, 3) PF_ROWS_SHAPE(96, 4) PF_ROWS_SHAPE(48, 3) PF_ROWS_SHAPE(48, 4) PF_ROWS_SHAPE(48, 5) PF_ROWS_SHAPE(48, 6)
+    PF_ROWS_SHAPE(72, 4) PF_ROWS_SHAPE(72, 5) PF_ROWS_SHAPE(24, 6)
   }
   q = PF_ROWS_Q, occ = PF_ROWS_MIN_CTAS;
   PF_ROWS_SHAPE(PF_ROWS_Q, PF_ROWS_MIN_CTAS)
