@@ -180,6 +180,7 @@ __device__ __forceinline__ float split_scale(uint32_t amax_bits) {
 // blockIdx.y selects the operand (0: fmap1, 1: fmap2); float4 loads, one atomicMax per warp.
 __global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ x0, const float *__restrict__ x1, long long n,
                                                       uint32_t *__restrict__ out) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // split_transpose_kernel may start loading its tiles
   const float *x = blockIdx.y ? x1 : x0;
   const float4 *x4 = reinterpret_cast<const float4 *>(x);
   const long long n4 = n >> 2;
@@ -202,18 +203,24 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float *__res
                                                               int C, int N, const uint32_t *__restrict__ amax_bits,
                                                               int want_lo) {
   __shared__ float t[64][33];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // lets volume_tc_kernel's prologue overlap this grid's tail
   const int which = blockIdx.z / B, b = blockIdx.z - which * B;
   const float *x = which ? x1 : x0;
   __half *hi = which ? hi1 : hi0, *lo = which ? lo1 : lo0;
-  const float s = split_scale(amax_bits[which]);
   const int c0 = blockIdx.y * 64, n0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const float *xb = x + (long long)b * C * N;
+  float raw[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = c0 + ty + i * 8;
-    t[ty + i * 8][tx] = (c < C && n0 + tx < N) ? xb[(long long)c * N + n0 + tx] * s : 0.f;
+    raw[i] = (c < C && n0 + tx < N) ? xb[(long long)c * N + n0 + tx] : 0.f;
   }
+  // programmatic dependent of absmax_kernel: the tile above is an input; only the scale needs that grid's result
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const float s = split_scale(amax_bits[which]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[ty + i * 8][tx] = raw[i] * s;
   __syncthreads();
   // each thread writes one half2 (channels 2*tx, 2*tx+1) for rows ty, ty+8, ...
 #pragma unroll
@@ -289,6 +296,10 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   else
     __syncthreads();
   tc_fence_after();
+  // programmatic dependent launch: the prologue above (barrier init, TMEM allocation, cluster sync) touches no global
+  // data and overlaps the tail of split_transpose_kernel; the operand planes and the absmax words are read only after
+  // that grid has completed (no-op when launched without the attribute)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0;
   // work items: kCluster consecutive M-tiles of one patch per cluster, so the peers share the B tile
@@ -568,7 +579,24 @@ int volume_build_tc(const pf_volume_args *a, cudaStream_t st) {
   const unsigned rblocks = (unsigned)((total / 4 + 255) / 256 < 592 ? (total / 4 + 255) / 256 : 592);
   absmax_kernel<<<dim3(rblocks, 2), 256, 0, st>>>(a->fmap1, a->fmap2, total, amax);
   dim3 tgrid(ceil_div(N, 32), ceil_div(C, 64), 2 * B);
-  split_transpose_kernel<<<tgrid, 256, 0, st>>>(a->fmap1, a->fmap2, a_hi, a_lo, b_hi, b_lo, B, C, N, amax, split ? 1 : 0);
+  {
+    static const bool pdl_prep = !(getenv("PF_VOLUME_PDL") != nullptr && getenv("PF_VOLUME_PDL")[0] == '0');
+    cudaLaunchConfig_t pc = {};
+    pc.gridDim = tgrid;
+    pc.blockDim = dim3(256);
+    pc.stream = st;
+    cudaLaunchAttribute pa[1];
+    pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pa[0].val.programmaticStreamSerializationAllowed = 1;
+    pc.attrs = pa;
+    pc.numAttrs = pdl_prep ? 1 : 0;
+    const uint32_t *amax_c = amax;
+    if (cudaLaunchKernelEx(&pc, split_transpose_kernel, a->fmap1, a->fmap2, a_hi, a_lo, b_hi, b_lo, B, C, N, amax_c, split ? 1 : 0) !=
+        cudaSuccess) {
+      (void)cudaGetLastError();
+      split_transpose_kernel<<<tgrid, 256, 0, st>>>(a->fmap1, a->fmap2, a_hi, a_lo, b_hi, b_lo, B, C, N, amax, split ? 1 : 0);
+    }
+  }
   if (int e = check_launch("pf_volume_build(prep)")) return e;
 
   // ---- tensor maps
@@ -621,13 +649,16 @@ int volume_build_tc(const pf_volume_args *a, cudaStream_t st) {
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kTcThreads);
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = !(getenv("PF_VOLUME_PDL") != nullptr && getenv("PF_VOLUME_PDL")[0] == '0');
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   auto launch = [&](auto kern, int smem) -> cudaError_t {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cfg.dynamicSmemBytes = smem;
