@@ -85,3 +85,22 @@ def test_two_rank_gloo_plumbing():
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "rank0 ok" in out.stdout and "rank1 ok" in out.stdout
+
+
+def test_dccl_auto_mode_decides_by_free_memory_once(monkeypatch):
+    """mode="auto": materialise while both pyramids fit in a fraction of the free device memory, else the volume-free
+    lookup; decided once per instance and shape so that both views take the same path."""
+    from types import SimpleNamespace
+    from prior_flow_b200 import corr as pcorr
+
+    fmap = SimpleNamespace(shape=(1, 256, 128, 256), device="cuda:0", is_cuda=True)     # 1024x2048 ERP: 2 x 5.7 GB
+    free = {"bytes": 170 << 30}
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda dev=None: (free["bytes"], 180 << 30))
+    big = pcorr.DCCL(4, 4, mode="auto")
+    assert big._use_onthefly(fmap) is False              # fits on a 180 GB B200
+    free["bytes"] = 1 << 30
+    assert big._use_onthefly(fmap) is False              # the first decision stands for the second view
+    small = pcorr.DCCL(4, 4, mode="auto")
+    assert small._use_onthefly(fmap) is True             # 1 GiB free: volume-free lookup
+    assert pcorr.DCCL(4, 4, mode="onthefly")._use_onthefly(fmap) is True
+    assert pcorr.DCCL(4, 4, mode="materialized")._use_onthefly(fmap) is False
