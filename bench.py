@@ -163,7 +163,7 @@ def main_ours(a):
     import torch.distributed as dist
     from prior_flow_b200 import ops
     from prior_flow_b200.model import PriOrRAFT
-    from oracle import torch_oracle as TO   # only for the baseline leg and synthetic coords (checker side)
+    from prior_flow_b200 import geometry as geo
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -278,7 +278,7 @@ def main_ours(a):
         for i in range(n_sets):
             fm = [torch.randn(B, 256, h, w, device=dev, generator=g) * 1.45 for _ in range(4)]
             sets.append((fm, ops.volume_pyramid(fm[0], fm[1], 4), ops.volume_pyramid(fm[2], fm[3], 4)))
-        coords = [TO.coords_grid(B, h, w, dev) + torch.randn(B, 2, h, w, device=dev, generator=g) * 5.0 for _ in range(8)]
+        coords = [geo.coords_grid(B, h, w, dev) + torch.randn(B, 2, h, w, device=dev, generator=g) * 5.0 for _ in range(8)]
 
         def graph_ms(calls, reps=15):
             """median replay time of one graph holding `calls` (a list of thunks) / len(calls), in ms"""

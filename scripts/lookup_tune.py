@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from prior_flow_b200 import ops  # noqa: E402
 from prior_flow_b200.model import PriOrRAFT  # noqa: E402
-from oracle import torch_oracle as TO  # noqa: E402
+from prior_flow_b200 import geometry as geo  # noqa: E402
 
 
 def main():
@@ -28,9 +28,9 @@ def main():
     fm = [torch.randn(B, 256, h, w, device=dev, generator=g) * 1.45 for _ in range(4)]
     if a.smooth:
         low = torch.randn(B, 2, h // 8, w // 8, device=dev, generator=g) * 5
-        coords = TO.coords_grid(B, h, w, dev) + torch.nn.functional.interpolate(low, size=(h, w), mode="bicubic", align_corners=True)
+        coords = geo.coords_grid(B, h, w, dev) + torch.nn.functional.interpolate(low, size=(h, w), mode="bicubic", align_corners=True)
     else:
-        coords = TO.coords_grid(B, h, w, dev) + torch.randn(B, 2, h, w, device=dev, generator=g) * 5.0
+        coords = geo.coords_grid(B, h, w, dev) + torch.randn(B, 2, h, w, device=dev, generator=g) * 5.0
     grids = PriOrRAFT()._grids(H, W, dev)
     pa, pb = ops.volume_pyramid(fm[0], fm[1], 4), ops.volume_pyramid(fm[2], fm[3], 4)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
