@@ -46,7 +46,9 @@ class CostVolume:
 
 
 class Pyramid(list):
-    """Materialised pyramid: a list of [B*h*w, 1, h>>l, w>>l] tensors (the reference's layout, core/corr.py:99-111)."""
+    """Materialised pyramid: a list of [B*h*w, 1, h>>l, w>>l] tensors (the reference's layout, core/corr.py:99-111).
+    `grad_sink` (training, opt-in): the shared in-place accumulator of the lookups' gradients, see ops.GradSink."""
+    grad_sink = None
 
 
 class FeaturePyramid:
@@ -69,10 +71,14 @@ def corr(fmap1: torch.Tensor, fmap2: torch.Tensor) -> CostVolume:
 class DCCL:
     """Dual-cost correlation lookup — core/corr.py:94-144."""
 
-    def __init__(self, num_levels: int = 4, radius: int = 4, mode: str = "auto", volume_mode: Optional[str] = None):
+    def __init__(self, num_levels: int = 4, radius: int = 4, mode: str = "auto", volume_mode: Optional[str] = None,
+                 accumulate_grads: bool = False):
         if mode not in ("auto", "materialized", "onthefly"):
             raise ValueError("mode must be auto | materialized | onthefly")
         self.num_levels, self.radius, self.mode, self.volume_mode = num_levels, radius, mode, volume_mode
+        # training: let all lookups of one backward pass scatter into ONE gradient pyramid per view (ops.GradSink); only
+        # valid when the pyramids are consumed by lookups alone and backpropagated once, hence opt-in
+        self.accumulate_grads = accumulate_grads
         self._auto = {}
 
     def _use_onthefly(self, fmap: torch.Tensor) -> bool:
@@ -94,7 +100,10 @@ class DCCL:
                 if torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad):
                     raise NotImplementedError("the on-the-fly lookup is inference-only; use mode='materialized' to train")
                 return FeaturePyramid(f1, f2, self.num_levels)
-            return Pyramid(ops.volume_pyramid_autograd(f1, f2, self.num_levels, cost_volume_8.mode or self.volume_mode))
+            pyr = Pyramid(ops.volume_pyramid_autograd(f1, f2, self.num_levels, cost_volume_8.mode or self.volume_mode))
+            if self.accumulate_grads and torch.is_grad_enabled() and pyr[0].requires_grad:
+                pyr.grad_sink = ops.GradSink()
+            return pyr
         # a materialised [B,h,w,h,w] tensor, as the reference passes (core/corr.py:102-109)
         B, h1, w1, h2, w2 = cost_volume_8.shape
         lvl = cost_volume_8.reshape(B * h1 * w1, 1, h2, w2).float()
@@ -110,7 +119,8 @@ class DCCL:
             return ops.lookup_onthefly(coords, corr_pyramid_A.f1, corr_pyramid_A.f2, corr_pyramid_B.f1, corr_pyramid_B.f2,
                                        sample_grid_A2B_W2C_8x, sample_grid_B2A_8x, self.radius, cyclic=True)
         return ops.lookup_autograd(coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x,
-                                   self.radius, cyclic=True)
+                                   self.radius, cyclic=True, sink_own=getattr(corr_pyramid_A, "grad_sink", None),
+                                   sink_other=getattr(corr_pyramid_B, "grad_sink", None))
 
     def summed(self, coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x,
                channels_last: bool = False):
@@ -121,7 +131,9 @@ class DCCL:
             a, b = self(coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x)
             return a + b
         return ops.lookup_autograd(coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x,
-                                   self.radius, cyclic=True, channels_last=channels_last, fuse_sum=True)
+                                   self.radius, cyclic=True, channels_last=channels_last, fuse_sum=True,
+                                   sink_own=getattr(corr_pyramid_A, "grad_sink", None),
+                                   sink_other=getattr(corr_pyramid_B, "grad_sink", None))
 
 
 class CorrBlock:

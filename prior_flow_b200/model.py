@@ -17,6 +17,7 @@ all in *how* the hot-path lines are executed:
 """
 from __future__ import annotations
 
+import os
 from types import SimpleNamespace
 from typing import List, Optional, Tuple
 
@@ -224,6 +225,8 @@ class PriOrRAFT(nn.Module):
         self.hidden_dim = self.context_dim = 128
         self.corr_mode, self.volume_mode = corr_mode, volume_mode
         self.channels_last = False      # set by .to_channels_last(): lookups then emit torch.channels_last tensors
+        # training: all lookups of a backward pass scatter into one gradient pyramid per view (ops.GradSink)
+        self.accumulate_grads = os.environ.get("PF_GRAD_SINK", "1") != "0"
         cor_planes = 4 * 9 * 9
         self.fnet = Encoder(256, "instance", dropout)
         self.cnet = Encoder(256, "batch", dropout)
@@ -277,7 +280,7 @@ class PriOrRAFT(nn.Module):
             net_B, inp_B = torch.tanh(cB[:, :128]), torch.relu(cB[:, 128:])
             f1A, f2A, f1B, f2B = (f.float() for f in self.fnet([image1, image2, image1_B, image2_B]))
 
-        lookup = DCCL(4, 4, mode=self.corr_mode, volume_mode=self.volume_mode)
+        lookup = DCCL(4, 4, mode=self.corr_mode, volume_mode=self.volume_mode, accumulate_grads=self.accumulate_grads)
         pyr_A = lookup.build_pyramid(CostVolume(f1A, f2A))
         pyr_B = lookup.build_pyramid(CostVolume(f1B, f2B))
 
