@@ -27,11 +27,14 @@ def main():
     ap.add_argument("--height", type=int, default=512)
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--iters", type=int, default=12)
+    ap.add_argument("--memory-format", default="nchw", choices=["nchw", "channels_last"])
     a = ap.parse_args()
     ctx = pfd.init_from_env("nccl")
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(0)
     model = PriOrRAFT().to(ctx.device)
+    if a.memory_format == "channels_last":
+        model = model.to_channels_last()
     model.train()
     model.freeze_bn()
     ddp = pfd.wrap_ddp(model, ctx)
