@@ -41,6 +41,25 @@ def _norm(kind: str, ch: int) -> nn.Module:
     return nn.Sequential()
 
 
+FOLD_BN_INFERENCE = True   # eval-mode BatchNorm of the context encoder folded into the preceding convolution (inference only)
+
+
+def _conv_norm_act(conv: nn.Conv2d, norm: nn.Module, x: torch.Tensor, relu: bool) -> torch.Tensor:
+    """relu?(norm(conv(x))).  For an eval-mode BatchNorm in fp32 inference the normalisation is a per-channel affine map
+    of the convolution's output, so it is folded into the weights and bias and the whole thing is ONE cuDNN launch
+    (conv + bias [+ ReLU]) instead of conv, bias add, a bandwidth-bound BN pass over a full-resolution tensor and a clamp."""
+    if (FOLD_BN_INFERENCE and isinstance(norm, nn.BatchNorm2d) and not norm.training and norm.track_running_stats
+            and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and not torch.is_autocast_enabled()):
+        scale = norm.weight * torch.rsqrt(norm.running_var + norm.eps)
+        w = conv.weight * scale.view(-1, 1, 1, 1)
+        b = (conv.bias - norm.running_mean) * scale + norm.bias
+        if relu:
+            return torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+        return F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+    y = norm(conv(x))
+    return F.relu(y) if relu else y
+
+
 class ResidualBlock(nn.Module):
     def __init__(self, cin: int, cout: int, norm_fn: str, stride: int = 1):
         super().__init__()
@@ -54,9 +73,10 @@ class ResidualBlock(nn.Module):
             self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride), self.norm3)
 
     def forward(self, x):
-        y = self.relu(self.norm1(self.conv1(x)))
-        y = self.relu(self.norm2(self.conv2(y)))
-        return self.relu((x if self.downsample is None else self.downsample(x)) + y)
+        y = _conv_norm_act(self.conv1, self.norm1, x, relu=True)
+        y = _conv_norm_act(self.conv2, self.norm2, y, relu=True)
+        skip = x if self.downsample is None else _conv_norm_act(self.downsample[0], self.downsample[1], x, relu=False)
+        return self.relu(skip + y)
 
 
 class Encoder(nn.Module):
@@ -86,7 +106,7 @@ class Encoder(nn.Module):
         if many:
             n = x[0].shape[0]
             x = torch.cat(x, dim=0)
-        x = self.relu1(self.norm1(self.conv1(x)))
+        x = _conv_norm_act(self.conv1, self.norm1, x, relu=True)
         x = self.conv2(self.layer3(self.layer2(self.layer1(x))))
         if self.training and self.dropout is not None:
             x = self.dropout(x)
