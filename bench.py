@@ -326,10 +326,10 @@ def main_ours(a):
         roofline = {"kernel": "DCCL lookup call: lookup_rows_kernel + rotate_fwd_kernel (24 calls per pair)", "bound": "hbm",
                     "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
                     # dram__bytes_read.sum + dram__bytes_write.sum of lookup_rows_kernel + rotate_fwd_kernel, one launch each, ncu
-                    # --set full, cold cache (profiles/r02g_ncu_raw_*.csv; B = 1, 64x128): 56.30 + 3.34 + 9.63 + 0 MB.  Reads are
+                    # --set full, cold cache (profiles/r02h_ncu_raw_*.csv; B = 1, 64x128): 56.31 + 2.91 + 9.62 + 0 MB.  Reads are
                     # 2.1x the algorithmic 26.2 MB because a 40-byte footprint row straddles 32-byte sectors; the outputs
                     # (21.2 MB) are still dirty in L2 when the kernels end
-                    "traffic": 69.27e6 if (B, h, w) == (1, 64, 128) else None,
+                    "traffic": 68.84e6 if (B, h, w) == (1, 64, 128) else None,
                     "peak_source": peak_src, "ms_per_launch": round(look_ms, 4),
                     "algorithmic_bytes_per_launch": look_bytes,
                     # the call as the model issues it (own + other summed, core/prior_raft.py:187): one output tensor
