@@ -100,9 +100,10 @@ class DCCL:
                 if torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad):
                     raise NotImplementedError("the on-the-fly lookup is inference-only; use mode='materialized' to train")
                 return FeaturePyramid(f1, f2, self.num_levels)
-            pyr = Pyramid(ops.volume_pyramid_autograd(f1, f2, self.num_levels, cost_volume_8.mode or self.volume_mode))
-            if self.accumulate_grads and torch.is_grad_enabled() and pyr[0].requires_grad:
-                pyr.grad_sink = ops.GradSink()
+            sink = ops.GradSink() if (self.accumulate_grads and torch.is_grad_enabled()
+                                      and (f1.requires_grad or f2.requires_grad)) else None
+            pyr = Pyramid(ops.volume_pyramid_autograd(f1, f2, self.num_levels, cost_volume_8.mode or self.volume_mode, sink))
+            pyr.grad_sink = sink
             return pyr
         # a materialised [B,h,w,h,w] tensor, as the reference passes (core/corr.py:102-109)
         B, h1, w1, h2, w2 = cost_volume_8.shape

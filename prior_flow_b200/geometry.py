@@ -46,9 +46,40 @@ def rotation_matrix_host(theta_list: Optional[Sequence[float]] = None,
     return R
 
 
+_rot_cache: Dict[Tuple, torch.Tensor] = {}      # (axes, thetas, device) -> device tensor (shared, read-only)
+_rot_host: Dict[Tuple, torch.Tensor] = {}       # (data_ptr, strides, device) -> the same matrix on the host
+
+
+def _remember_host(R_dev: torch.Tensor, R_host: torch.Tensor) -> None:
+    dev = (R_dev.device.type, R_dev.device.index)
+    _rot_host[(R_dev.data_ptr(), tuple(R_dev.stride()), dev)] = R_host.contiguous()
+    _rot_host[(R_dev.data_ptr(), tuple(R_dev.T.stride()), dev)] = R_host.T.contiguous()   # `R.T` is a view of the same storage
+
+
+def _host_matrix(R: torch.Tensor) -> torch.Tensor:
+    """The 3x3 matrix on the host without a device synchronisation when it is one `generate_rotation_metrix` handed out
+    (or its `.T` view) — which keeps a forward of the patched reference free of D2H copies, i.e. CUDA-graph capturable."""
+    if not R.is_cuda:
+        return R.detach().float().contiguous()
+    hit = _rot_host.get((R.data_ptr(), tuple(R.stride()), (R.device.type, R.device.index)))
+    if hit is not None:
+        return hit
+    return R.detach().float().cpu().contiguous()
+
+
 def generate_rotation_metrix(axis_list=None, theta_list=None) -> torch.Tensor:
-    """core/utils/projection_prim_ortho.py:23-48 — returns a CUDA tensor like the reference."""
-    return rotation_matrix_host(theta_list, axis_list).cuda()
+    """core/utils/projection_prim_ortho.py:23-48 — returns a CUDA tensor like the reference.  The tensor is cached per
+    (axes, angles, device) and shared between calls: treat it as read-only (every caller in the reference does)."""
+    axes = tuple(["z", "y", "x"] if axis_list is None else axis_list)
+    thetas = tuple(float(t) for t in ([0.0, 0.0, 0.0] if theta_list is None else theta_list))
+    key = (axes, thetas, torch.cuda.current_device())
+    R = _rot_cache.get(key)
+    if R is None:
+        R_host = rotation_matrix_host(list(thetas), list(axes))
+        R = R_host.cuda()
+        _rot_cache[key] = R
+        _remember_host(R, R_host)
+    return R
 
 
 # ---------------------------------------------------------------------------- sample grids (cached)
@@ -57,6 +88,8 @@ _grid_cache: Dict[Tuple, torch.Tensor] = {}
 
 def clear_cache() -> None:
     _grid_cache.clear()
+    _rot_cache.clear()
+    _rot_host.clear()
 
 
 def samplegrid_cached(H: int, W: int, R_host: torch.Tensor, device) -> torch.Tensor:
@@ -76,7 +109,7 @@ def generate_samplegrid(tensor_size, rotate_metrix: torch.Tensor) -> torch.Tenso
     """core/utils/projection_prim_ortho.py:432-443 -> [B,2,H,W] fp32 (a fresh, writable tensor per call)."""
     B, _, H, W = (int(s) for s in tensor_size)
     dev = rotate_metrix.device if rotate_metrix.is_cuda else torch.device("cuda")
-    g = samplegrid_cached(H, W, rotate_metrix.detach().float().cpu().contiguous(), dev)
+    g = samplegrid_cached(H, W, _host_matrix(rotate_metrix), dev)
     return g.expand(B, 2, H, W).contiguous() if B > 1 else g.clone()
 
 
@@ -133,6 +166,7 @@ def flo_rotate(flow: torch.Tensor, EulerAngles_zyx=None, sample_grid_W2C: Option
             sample_grid_W2C = samplegrid_cached(H, W, R.T.contiguous(), flow.device)
         if sample_grid_C2W is None:
             sample_grid_C2W = samplegrid_cached(H, W, R, flow.device)
+    ops._no_grad_wrt(flow, "the flow passed to flo_rotate")
     return ops.flo_rotate(flow.detach().float(), sample_grid_W2C, sample_grid_C2W)
 
 

@@ -445,13 +445,13 @@ def warp_groupcorr_backward(fmap1, fmap2, coords, dout, groups: int = 4):
 # ------------------------------------------------------------------------------------------ autograd
 class _VolumePyramidFn(torch.autograd.Function):
     """volume_pyramid with gradients to the feature maps: fold the level gradients into level 0
-    (pf_pyramid_fold_bwd), then dF1 = dV F2^T / sqrt(C) and dF2 = dV^T F1 / sqrt(C) — two plain library
-    GEMMs (cuBLAS through torch.matmul)."""
+    (pf_pyramid_fold_bwd), then dF1 = dV F2^T / sqrt(C) and dF2 = dV^T F1 / sqrt(C) (volume_backward)."""
 
     @staticmethod
-    def forward(ctx, fmap1, fmap2, num_levels, mode):
+    def forward(ctx, fmap1, fmap2, num_levels, mode, sink):
         ctx.save_for_backward(fmap1, fmap2)
         ctx.num_levels = num_levels
+        ctx.sink = sink
         return tuple(volume_pyramid(fmap1, fmap2, num_levels, mode))
 
     @staticmethod
@@ -459,24 +459,43 @@ class _VolumePyramidFn(torch.autograd.Function):
         fmap1, fmap2 = ctx.saved_tensors
         B, Cn, h, w = fmap1.shape
         N = h * w
+        sink = ctx.sink
+        if sink is not None and sink.bufs is not None:
+            # the sink's in-place scatters are only valid if autograd handed us the very storage they went into: a
+            # pyramid level with a consumer besides the DCCL lookups makes the engine sum out of place and lose them
+            for g, buf in zip(grads, sink.bufs):
+                if g is not None and g.data_ptr() != buf.data_ptr():
+                    sink.reset()
+                    raise RuntimeError("prior_flow_b200.GradSink: a pyramid level was consumed by something other than DCCL "
+                                       "lookups; build the DCCL with accumulate_grads=False for this graph")
+            sink.reset()     # the pass is over for this pyramid: a second backward (retain_graph) starts from zero
         gs = []
         for l, g in enumerate(grads):
             if g is None:
                 gs.append(torch.zeros((B * N, 1, h >> l, w >> l), device=fmap1.device))
             else:
-                gs.append(g.contiguous().clone() if l == 0 else g.contiguous())  # level 0 is folded into in place
+                gs.append(g.contiguous().clone() if (l == 0 and sink is None) else g.contiguous())  # level 0 is folded into in place
         g0 = pyramid_fold_backward(gs).view(B, N, N)
-        scale = 1.0 / (Cn ** 0.5)
-        f1 = fmap1.reshape(B, Cn, N)
-        f2 = fmap2.reshape(B, Cn, N)
-        d1 = torch.matmul(f2, g0.transpose(1, 2)).mul_(scale).view_as(fmap1) if ctx.needs_input_grad[0] else None
-        d2 = torch.matmul(f1, g0).mul_(scale).view_as(fmap2) if ctx.needs_input_grad[1] else None
-        return d1, d2, None, None
+        d1, d2 = volume_backward(fmap1, fmap2, g0, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return d1, d2, None, None, None
 
 
-def volume_pyramid_autograd(fmap1, fmap2, num_levels=4, mode=None):
+def volume_backward(fmap1, fmap2, g0, need1=True, need2=True):
+    """Adjoints of the volume GEMM (autograd of core/prior_raft.py:73-75): dF1[c,n] = sum_m dV[n,m] F2[c,m] / sqrt(C),
+    dF2[c,m] = sum_n dV[n,m] F1[c,n] / sqrt(C).  g0: [B, N, N]."""
+    B, Cn, h, w = fmap1.shape
+    N = h * w
+    scale = 1.0 / (Cn ** 0.5)
+    f1 = fmap1.reshape(B, Cn, N)
+    f2 = fmap2.reshape(B, Cn, N)
+    d1 = torch.matmul(f2, g0.transpose(1, 2)).mul_(scale).view_as(fmap1) if need1 else None
+    d2 = torch.matmul(f1, g0).mul_(scale).view_as(fmap2) if need2 else None
+    return d1, d2
+
+
+def volume_pyramid_autograd(fmap1, fmap2, num_levels=4, mode=None, sink=None):
     if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
-        return list(_VolumePyramidFn.apply(fmap1, fmap2, num_levels, mode))
+        return list(_VolumePyramidFn.apply(fmap1, fmap2, num_levels, mode, sink))
     return volume_pyramid(fmap1, fmap2, num_levels, mode)
 
 
@@ -518,20 +537,38 @@ class _DualLookupFn(torch.autograd.Function):
                                          into_own=into_own, into_other=into_other, channels_last=channels_last)
         if first_own:
             sink_own.bufs = d_own
+            sink_own.arm()
         if first_other:
             sink_other.bufs = d_other
+            sink_other.arm()
         r_own = d_own if (sink_own is None or first_own) else [None] * L
         r_other = d_other if (sink_other is None or first_other) else [None] * L
         return (None, None, None, None, None, None, None, None, None, *r_own, *r_other)
 
 
 class GradSink:
-    """Opt-in, per pyramid and per backward pass: the shared in-place accumulator of d(loss)/d(pyramid levels) used by
-    `_DualLookupFn.backward` (see there).  Valid when the pyramid's levels are consumed by DCCL lookups only and the
-    graph is backpropagated once — what `PriOrRAFT.forward` builds."""
+    """Opt-in, per pyramid: the shared in-place accumulator of d(loss)/d(pyramid levels) used by
+    `_DualLookupFn.backward` (see there).  Valid when the pyramid's levels are consumed by DCCL lookups only — what
+    `PriOrRAFT.forward` builds; `_VolumePyramidFn.backward` verifies that and raises otherwise.  The buffers live for one
+    backward pass: they are dropped when the pyramid's own backward has consumed them and, as a safety net, by an
+    engine callback at the end of the pass, so a second backward over a retained graph starts from zero again."""
 
     def __init__(self):
         self.bufs = None
+        self._armed = False
+
+    def reset(self):
+        self.bufs = None
+        self._armed = False
+
+    def arm(self):
+        """Called by the first lookup backward of a pass: queue the end-of-pass reset (only legal inside backward)."""
+        if not self._armed:
+            self._armed = True
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(self.reset)
+            except RuntimeError:
+                pass
 
 
 class _SingleLookupFn(torch.autograd.Function):
@@ -576,7 +613,17 @@ class _RemapFn(torch.autograd.Function):
         return remap_backward(g, coords, layout, shape, cyclic), None, None, None
 
 
+def _no_grad_wrt(t: torch.Tensor, what: str) -> None:
+    """The kernels implement d/d(source) only.  The reference's forward never asks for more (coordinates are detached at
+    the top of every iteration, core/prior_raft.py:171,176; the sample grids are constants) — any other caller must hear
+    about it instead of silently training with a missing gradient."""
+    if torch.is_grad_enabled() and t.requires_grad:
+        raise NotImplementedError(f"prior_flow_b200: no gradient with respect to {what} (detach it, as "
+                                  "PriOr_RAFT.forward does, or use the eager sampler)")
+
+
 def remap_autograd(src, coords, layout, cyclic=True):
+    _no_grad_wrt(coords, "sample coordinates")
     if torch.is_grad_enabled() and src.requires_grad:
         return _RemapFn.apply(src, coords.detach(), layout, cyclic)
     return remap(src, coords, layout, cyclic)

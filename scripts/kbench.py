@@ -66,6 +66,8 @@ def main():
     ap.add_argument("--w", type=int, default=128)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--skip-torch", action="store_true")
+    ap.add_argument("--out", default="", help="write the rows as JSON here (never set this for a run under ncu: its times are not timings)")
+    ap.add_argument("--only", default="", help="comma-separated substrings: run only the kernels whose name matches one")
     ap.add_argument("--cpu", action="store_true", help="also time the ATen restatement of each op on the host cores (reference's CPU path)")
     a = ap.parse_args()
     B, h, w, C = a.batch, a.h, a.w, 256
@@ -99,7 +101,11 @@ def main():
             ts.append(_time.perf_counter() - t0)
         return min(ts) * 1e3
 
+    only = [t for t in a.only.split(",") if t]
+
     def rec(name, fn, bytes_=None, flops=None, torch_fn=None, cpu_fn=None):
+        if only and not any(t in name for t in only):
+            return
         med, best = timeit(fn, a.iters, flush)
         r = {"kernel": name, "ms_median": round(med, 4), "ms_best": round(best, 4)}
         if cpu_fn is not None and a.cpu:
@@ -156,9 +162,10 @@ def main():
     cl = lambda t: t.permute(0, 2, 3, 1).contiguous()
     f1a, f2a, f1b, f2b = cl(fm[0]), ops.channels_last_pyramid(fm[1], 4), cl(fm[2]), ops.channels_last_pyramid(fm[3], 4)
     rec("lookup_onthefly", lambda: ops.lookup_onthefly(coords, f1a, f2a, f1b, f2b, gw, gc, 4))
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "kbench.json"), "w") as fh:
-        json.dump(rows, fh, indent=1)
+    if a.out:
+        os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
+        with open(a.out, "w") as fh:
+            json.dump(rows, fh, indent=1)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,162 @@
+"""GPU: the drop-in for real — the UNMODIFIED reference (`baseline/_ref/PriOr-RAFT`, sha256-checked against
+baseline/ref_manifest.json) runs `PriOr_RAFT.forward` once on its own eager ATen ops and once with
+`prior_flow_b200.install()` routing the hot path to the sm_100a kernels (core/prior_raft.py:7-8,69-75,115-127,151-188).
+
+Bar (BASELINE.json north_star): final flow within 1e-3 px mean EPE at 512x1024, 12 iterations, default random init
+(`torch.manual_seed(0)`), cuDNN TF32 off; the eager-vs-eager difference under a 1-ulp perturbation of the volume is
+printed beside it as the noise floor of the recurrent network.  Also: the benchmarked configuration of `model.py`
+(TF32 convolutions, channels_last, folded BN, CUDA-graph replay) against the reference with TF32 on, and gradients of a
+training step through the installed kernels against the reference's autograd.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shim
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not ref_shim.available(), reason="vendored reference missing (scripts/vendor_reference.py)")]
+
+H, W, ITERS = 512, 1024, 12
+
+
+def mean_epe(a, b):
+    return float(torch.sqrt(((a.double() - b.double()) ** 2).sum(1)).mean())
+
+
+def images(h, w, batch=1):
+    g = torch.Generator().manual_seed(1234)
+    return (torch.rand(batch, 3, h, w, generator=g) * 255).cuda(), (torch.rand(batch, 3, h, w, generator=g) * 255).cuda()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    r = ref_shim.load()
+    assert ref_shim.verified(), "baseline/_ref differs from baseline/ref_manifest.json: not the unmodified reference"
+    return r
+
+
+@pytest.fixture()
+def fp32_convs():
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+
+
+def run(model, im1, im2, iters=ITERS, **kw):
+    with torch.no_grad():
+        out = model(im1, im2, iters=iters, test_mode=True, **kw)
+    torch.cuda.synchronize()
+    return out
+
+
+def test_unmodified_reference_with_install_matches_eager_512x1024(ref, fp32_convs):
+    """north_star's gate as stated: 512x1024, 12 iterations, default random init, fp32."""
+    import prior_flow_b200 as pfb
+    model = ref_shim.make_model(ref, seed=0).cuda().eval()
+    im1, im2 = images(H, W)
+    flow_ref = run(model, im1, im2)
+    # noise floor: the same eager path with the volume scaled by (1 + 2^-23), i.e. a 1-ulp relative perturbation
+    orig = ref.prior_raft.PriOr_RAFT.corr
+    ref.prior_raft.PriOr_RAFT.corr = lambda self, a, b: orig(self, a, b) * (1.0 + 2.0 ** -23)
+    try:
+        flow_ulp = run(model, im1, im2)
+    finally:
+        ref.prior_raft.PriOr_RAFT.corr = orig
+    pfb.install()
+    try:
+        assert ref.prior_raft.DCCL is pfb.DCCL
+        flow_ours = run(model, im1, im2)
+    finally:
+        pfb.uninstall()
+    epe, floor = mean_epe(flow_ours, flow_ref), mean_epe(flow_ulp, flow_ref)
+    mag = float(torch.sqrt((flow_ref.double() ** 2).sum(1)).mean())
+    print(f"\n[dropin 512x1024/12it fp32] mean EPE installed-vs-eager {epe:.3e} px; eager-vs-eager(1-ulp volume) {floor:.3e} px; "
+          f"mean |flow| {mag:.3f} px")
+    assert flow_ours.shape == flow_ref.shape == (1, 2, H, W)
+    assert epe <= 1e-3
+
+
+def test_installed_reference_with_init_flow_and_batch2(ref, fp32_convs):
+    import prior_flow_b200 as pfb
+    model = ref_shim.make_model(ref, seed=0).cuda().eval()
+    im1, im2 = images(128, 256, batch=2)
+    g = torch.Generator().manual_seed(5)
+    init = (torch.randn(2, 2, 16, 32, generator=g) * 2).cuda()
+    a = run(model, im1, im2, iters=4, init_flow=init)
+    pfb.install()
+    try:
+        b = run(model, im1, im2, iters=4, init_flow=init)
+    finally:
+        pfb.uninstall()
+    epe = mean_epe(a, b)
+    print(f"\n[dropin 128x256 B=2 init_flow] mean EPE {epe:.3e} px")
+    assert epe <= 1e-3
+
+
+def test_installed_reference_train_step_gradients(ref, fp32_convs):
+    """train mode: predictions and the gradient that reaches the feature encoder through lookup -> pyramid -> volume
+    (our backward kernels) against the reference's own autograd."""
+    import prior_flow_b200 as pfb
+    model = ref_shim.make_model(ref, seed=0).cuda()
+    im1, im2 = images(128, 256)
+    res = []
+    for installed in (False, True):
+        model.train()
+        model.freeze_bn()
+        model.zero_grad(set_to_none=True)
+        if installed:
+            pfb.install()
+        try:
+            pa, pb = model(im1, im2, iters=3)
+            loss = sum(p.abs().mean() for p in pa) + sum(p.abs().mean() for p in pb)
+            loss.backward()
+        finally:
+            if installed:
+                pfb.uninstall()
+        res.append((pa[-1].detach().clone(), model.fnet.conv1.weight.grad.detach().clone(), model.fnet.conv2.weight.grad.detach().clone()))
+    (fa, g1a, g2a), (fb, g1b, g2b) = res
+    print(f"\n[dropin train] pred EPE {mean_epe(fa, fb):.3e}; grad rel diff conv1 {float((g1a - g1b).abs().max() / g1a.abs().max()):.2e}, "
+          f"conv2 {float((g2a - g2b).abs().max() / g2a.abs().max()):.2e}")
+    assert mean_epe(fa, fb) <= 1e-3
+    assert float((g1a - g1b).abs().max() / g1a.abs().max()) < 5e-3    # atomics order + cuDNN sampler in the eager path
+    assert float((g2a - g2b).abs().max() / g2a.abs().max()) < 5e-3
+
+
+def test_benchmarked_configuration_matches_reference_with_tf32(ref):
+    """What bench.py times — model.py with channels_last, folded BN, fused conv+ReLU, TF32 convolutions, CUDA-graph replay —
+    against the unmodified reference run the way it runs on a GPU by default (cuDNN TF32 on).  The noise floor printed
+    beside it is the reference against itself with cuDNN's autotuner on (other TF32 kernels, same math)."""
+    from prior_flow_b200.model import PriOrRAFT
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        model = ref_shim.make_model(ref, seed=0).cuda().eval()
+        im1, im2 = images(H, W)
+        torch.backends.cudnn.benchmark = False
+        flow_ref = run(model, im1, im2)
+        torch.backends.cudnn.benchmark = True
+        flow_ref_tuned = run(model, im1, im2)
+        ours = PriOrRAFT().cuda().eval()
+        ours.load_state_dict(model.state_dict(), strict=True)
+        ours = ours.to_channels_last()
+        run(ours, im1, im2)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run(ours, im1, im2)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            with torch.no_grad():
+                static_out = ours(im1, im2, iters=ITERS, test_mode=True)
+        graph.replay()
+        torch.cuda.synchronize()
+        epe, floor = mean_epe(static_out, flow_ref), mean_epe(flow_ref_tuned, flow_ref)
+        print(f"\n[bench config 512x1024/12it tf32] mean EPE ours(graph, channels_last, folded BN)-vs-reference {epe:.3e} px; "
+              f"reference-vs-reference(cudnn.benchmark) {floor:.3e} px")
+        assert epe <= max(1e-3, 3 * floor)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = old
