@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 3
+#define PF_ABI_VERSION 4
 #define PF_MAX_LEVELS 4
 
 /* `tensor / python_scalar`: IEEE division on CPU, multiply by fp32 reciprocal in ATen's CUDA
@@ -43,7 +43,7 @@ enum pf_volume_mode {
 
 int pf_abi_version(void);
 const char *pf_last_error(void);
-/* Compile-time facts of the build: "sm_100a;tcgen05;tma;abi=3". */
+/* Compile-time facts of the build: "sm_100a;tcgen05;tma;abi=4". */
 const char *pf_build_info(void);
 
 /* ------------------------------------------------------------------------------------------------
@@ -189,6 +189,15 @@ int pf_pyramid_fold_bwd(float *const *glevel, int num_levels, long long planes, 
 int pf_warp_groupcorr_bwd(const float *fmap1, const float *fmap2, const float *coords, const float *dout,
                           float *dfmap1, float *dfmap2, int batch, int channels, int h, int w, int groups,
                           int div_mode, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Measurement aids (bench.py): no reference counterpart.
+ * pf_probe_gather issues exactly the loads of an own-view level-0 lookup (core/corr.py:128: per plane a 10x10 footprint at
+ * pos_xy[2n], pos_xy[2n+1], ten coalesced 40-byte row segments) and nothing else; its time is the HBM floor of that access
+ * pattern.  pf_probe_stream_read reads `count` floats once (read-only streaming ceiling).  `sink` is one float. */
+int pf_probe_gather(const float *vol /*[planes,H,W]*/, long long planes, int H, int W, const int *pos_xy /*[planes,2]*/,
+                    float *sink, void *stream);
+int pf_probe_stream_read(const float *src, long long count, float *sink, void *stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import threading
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libpriorcorr.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_LEVELS = 4
 
 DIV_IEEE, DIV_ATEN_CUDA = 0, 1
@@ -80,6 +80,8 @@ SIGNATURES = {
     "pf_remap_bwd": (C.c_int, [C.POINTER(RemapArgs), _fp, _fp, _fp]),
     "pf_pyramid_fold_bwd": (C.c_int, [C.POINTER(_fp), C.c_int, C.c_longlong, C.c_int, C.c_int, _fp]),
     "pf_warp_groupcorr_bwd": (C.c_int, [_fp] * 6 + [C.c_int] * 6 + [_fp]),
+    "pf_probe_gather": (C.c_int, [_fp, C.c_longlong, C.c_int, C.c_int, _fp, _fp, _fp]),
+    "pf_probe_stream_read": (C.c_int, [_fp, C.c_longlong, _fp, _fp]),
 }
 
 _lib = None

@@ -34,6 +34,6 @@ int pf_abi_version(void) { return PF_ABI_VERSION; }
 
 const char *pf_last_error(void) { return pf::g_error; }
 
-const char *pf_build_info(void) { return "sm_100a;tcgen05;tma;abi=3"; }
+const char *pf_build_info(void) { return "sm_100a;tcgen05;tma;abi=4"; }
 
 }  // extern "C"

@@ -41,6 +41,15 @@ __device__ __forceinline__ T *opaque(T *p) {
   return p;
 }
 
+// Plain (coherent, L1-allocating) 16-byte load: never .nc.  For data written by a grid that may still be running when
+// the reading kernel starts (programmatic dependent launch): PTX requires ld.global.nc data to be read-only for the whole
+// lifetime of the kernel, so __ldg is off the table there even after griddepcontrol.wait.
+__device__ __forceinline__ float4 ld_f4(const float4 *p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 // torch.remainder(x, m) for m > 0: fmod, then + m when the result is negative (may return m itself
 // for tiny negative x — SURVEY.md §A.2).  The three fast paths are exact restatements of
 // fmodf + fix-up for |x| < 2m (fmod is exact; x - m is exact by Sterbenz for m <= x < 2m) and
@@ -149,6 +158,59 @@ __device__ __forceinline__ float blend4(const float *__restrict__ plane, const T
   acc = __fmaf_rn(__ldg(plane + c.o_sw), c.sw, acc);
   acc = __fmaf_rn(__ldg(plane + c.o_se), c.se, acc);
   return acc;
+}
+
+// One axis of one window, resolved once per query: clamped element offsets of the two taps and their
+// weights with the zero-padding validity folded in (0 * finite == 0 reproduces ATen's skipped tap, and
+// nw = w0x * w0y is the same rounded product as (ix_se - ix) * (iy_se - iy) when both taps are valid).
+struct AxisEntry {
+  int o0, o1;      // clamp(i0) * stride, clamp(i0 + 1) * stride
+  float w0, w1;    // (i0+1 - s) if i0 in range else 0 ; (s - i0) if i0+1 in range else 0
+};
+
+template <int kDiv>
+__device__ __forceinline__ float sample_coord(float p, const Axis ax) {   // to_sample_coord, div mode resolved at compile time
+  const float t = __fmul_rn(2.f, p);
+  float g = (kDiv == PF_DIV_ATEN_CUDA) ? __fmul_rn(t, ax.inv_m1) : __fdiv_rn(t, ax.size_m1);
+  g = __fsub_rn(g, 1.f);
+  float v = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), ax.size_m1);
+  if (!(fabsf(v) <= 2147483648.f)) v = -100.f;   // non-finite or outside the int range (safe_downgrade_to_int_range)
+  return v;
+}
+
+__device__ __forceinline__ AxisEntry make_axis_entry(float s, int size, int stride) {
+  const float fl = floorf(s);
+  const int i0 = (int)fl;
+  AxisEntry e;
+  e.w1 = ((unsigned)(i0 + 1) < (unsigned)size) ? __fsub_rn(s, fl) : 0.f;
+  e.w0 = ((unsigned)i0 < (unsigned)size) ? __fsub_rn(__fadd_rn(fl, 1.f), s) : 0.f;
+  e.o0 = min(max(i0, 0), size - 1) * stride;
+  e.o1 = min(max(i0 + 1, 0), size - 1) * stride;
+  return e;
+}
+
+// to_sample_coord with the exact scalings folded: 2p*inv == 2*(p*inv) (power-of-two scaling), fl(2q - 1) is one FMA,
+// and ((g+1) * 0.5) * (W-1) == (g+1) * ((W-1)/2) because the halving is exact.  4 instructions instead of 6.
+template <int kDiv>
+__device__ __forceinline__ float sample_coord_x(float p, const Axis ax, const float half_m1) {
+  const float q = (kDiv == PF_DIV_ATEN_CUDA) ? __fmul_rn(p, ax.inv_m1) : __fdiv_rn(p, ax.size_m1);
+  const float g = __fmaf_rn(q, 2.f, -1.f);
+  float v = __fmul_rn(__fadd_rn(g, 1.f), half_m1);
+  if (!(fabsf(v) <= 2147483648.f)) v = -100.f;
+  return v;
+}
+
+// torch.remainder(x, m), m > 0.  For a power-of-two m the quotient, its truncation, the product and the
+// difference are all exact, so three instructions reproduce fmodf; otherwise the general routine.
+static __device__ __noinline__ float remainder_general(float x, float m) { return remainder_pos(x, m); }   // one copy of fmodf's slow path
+__device__ __forceinline__ float remainder_sel(float x, const Axis ax, const bool pow2) {
+  if (pow2) {
+    const float t = truncf(__fmul_rn(x, 1.0f / ax.size));
+    float r = __fmaf_rn(-t, ax.size, x);
+    if (r < 0.f) r = __fadd_rn(r, ax.size);
+    return r;
+  }
+  return remainder_general(x, ax.size);
 }
 
 }  // namespace pf

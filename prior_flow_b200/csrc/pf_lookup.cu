@@ -63,35 +63,6 @@ __device__ __forceinline__ void scatter_zeros(float *__restrict__ plane, int H, 
   if (yin1 && xin1) atomicAdd(r1 + 1, g * t.se);
 }
 
-// One axis of one window, resolved once per query: clamped element offsets of the two taps and their
-// weights with the zero-padding validity folded in (0 * finite == 0 reproduces ATen's skipped tap, and
-// nw = w0x * w0y is the same rounded product as (ix_se - ix) * (iy_se - iy) when both taps are valid).
-struct AxisEntry {
-  int o0, o1;      // clamp(i0) * stride, clamp(i0 + 1) * stride
-  float w0, w1;    // (i0+1 - s) if i0 in range else 0 ; (s - i0) if i0+1 in range else 0
-};
-
-template <int kDiv>
-__device__ __forceinline__ float sample_coord(float p, const Axis ax) {   // to_sample_coord, div mode resolved at compile time
-  const float t = __fmul_rn(2.f, p);
-  float g = (kDiv == PF_DIV_ATEN_CUDA) ? __fmul_rn(t, ax.inv_m1) : __fdiv_rn(t, ax.size_m1);
-  g = __fsub_rn(g, 1.f);
-  float v = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), ax.size_m1);
-  if (!(fabsf(v) <= 2147483648.f)) v = -100.f;   // non-finite or outside the int range (safe_downgrade_to_int_range)
-  return v;
-}
-
-__device__ __forceinline__ AxisEntry make_axis_entry(float s, int size, int stride) {
-  const float fl = floorf(s);
-  const int i0 = (int)fl;
-  AxisEntry e;
-  e.w1 = ((unsigned)(i0 + 1) < (unsigned)size) ? __fsub_rn(s, fl) : 0.f;
-  e.w0 = ((unsigned)i0 < (unsigned)size) ? __fsub_rn(__fadd_rn(fl, 1.f), s) : 0.f;
-  e.o0 = min(max(i0, 0), size - 1) * stride;
-  e.o1 = min(max(i0 + 1, 0), size - 1) * stride;
-  return e;
-}
-
 // Per-warp shared-memory scratch of lookup_kernel (sizes for window edge k = 2r+1):
 //   T   [32] AxisEntry     one entry per window column (lanes 0..k-1) and row (lanes k..2k-1)
 //   pos [2][16] int        the k+1 distinct x (resp. y*stride) offsets of the footprint
@@ -398,30 +369,6 @@ constexpr int kRowsK = 9, kRowsK2 = 81;
 #endif
 constexpr bool kOwnStream = PF_OWN_STREAM;   // own-view footprint rows are read exactly once: evict-first loads keep L1 for the grid
 constexpr int kRowsWarpWords = 3 * 12 * 2 + 3 * 10 * 2 + 32;   // o0 rows, o1 rows (int, pitch 12), weights (float2, pitch 10), dbg y
-
-// to_sample_coord with the exact scalings folded: 2p*inv == 2*(p*inv) (power-of-two scaling), fl(2q - 1) is one FMA,
-// and ((g+1) * 0.5) * (W-1) == (g+1) * ((W-1)/2) because the halving is exact.  4 instructions instead of 6.
-template <int kDiv>
-__device__ __forceinline__ float sample_coord_x(float p, const Axis ax, const float half_m1) {
-  const float q = (kDiv == PF_DIV_ATEN_CUDA) ? __fmul_rn(p, ax.inv_m1) : __fdiv_rn(p, ax.size_m1);
-  const float g = __fmaf_rn(q, 2.f, -1.f);
-  float v = __fmul_rn(__fadd_rn(g, 1.f), half_m1);
-  if (!(fabsf(v) <= 2147483648.f)) v = -100.f;
-  return v;
-}
-
-// torch.remainder(x, m), m > 0.  For a power-of-two m the quotient, its truncation, the product and the
-// difference are all exact, so three instructions reproduce fmodf; otherwise the general routine.
-__device__ __noinline__ float remainder_general(float x, float m) { return remainder_pos(x, m); }   // one copy of fmodf's slow path
-__device__ __forceinline__ float remainder_sel(float x, const Axis ax, const bool pow2) {
-  if (pow2) {
-    const float t = truncf(__fmul_rn(x, 1.0f / ax.size));
-    float r = __fmaf_rn(-t, ax.size, x);
-    if (r < 0.f) r = __fadd_rn(r, ax.size);
-    return r;
-  }
-  return remainder_general(x, ax.size);
-}
 
 template <int kDiv, bool kDbg, int kRowsQ, int BRANCH>
 __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const int lvl) {
@@ -810,8 +757,8 @@ __global__ void __launch_bounds__(kRotThreads) rotate_fwd_kernel(const RotatePar
     float4 r[kPerWarp];
 #pragma unroll
     for (int i = 0; i < kPerWarp; ++i) {
-      const float4 a = __ldg(src + t[i].o_nw + c4), bq = __ldg(src + t[i].o_ne + c4);
-      const float4 c = __ldg(src + t[i].o_sw + c4), d = __ldg(src + t[i].o_se + c4);
+      const float4 a = ld_f4(src + t[i].o_nw + c4), bq = ld_f4(src + t[i].o_ne + c4);   // never .nc: the producer grid may
+      const float4 c = ld_f4(src + t[i].o_sw + c4), d = ld_f4(src + t[i].o_se + c4);    // still be running when this kernel starts
       r[i].x = __fmaf_rn(d.x, t[i].se, __fmaf_rn(c.x, t[i].sw, __fmaf_rn(bq.x, t[i].ne, __fmul_rn(a.x, t[i].nw))));
       r[i].y = __fmaf_rn(d.y, t[i].se, __fmaf_rn(c.y, t[i].sw, __fmaf_rn(bq.y, t[i].ne, __fmul_rn(a.y, t[i].nw))));
       r[i].z = __fmaf_rn(d.z, t[i].se, __fmaf_rn(c.z, t[i].sw, __fmaf_rn(bq.z, t[i].ne, __fmul_rn(a.z, t[i].nw))));
@@ -831,7 +778,7 @@ __global__ void __launch_bounds__(kRotThreads) rotate_fwd_kernel(const RotatePar
         }
       } else {
         if (p.own_cl != nullptr) {   // corr_A + corr_B_A with the own view read as one coalesced float4
-          const float4 own = __ldg(reinterpret_cast<const float4 *>(p.own_cl + (long long)b * p.N * C) + (long long)min(n0 + q0 + i, p.N - 1) * C4 + c4);
+          const float4 own = ld_f4(reinterpret_cast<const float4 *>(p.own_cl + (long long)b * p.N * C) + (long long)min(n0 + q0 + i, p.N - 1) * C4 + c4);
           r[i].x = __fadd_rn(own.x, r[i].x), r[i].y = __fadd_rn(own.y, r[i].y);
           r[i].z = __fadd_rn(own.z, r[i].z), r[i].w = __fadd_rn(own.w, r[i].w);
         }
@@ -1082,18 +1029,18 @@ extern "C" int pf_lookup_dual(const pf_lookup_args *a, void *stream) {
     PF_REQUIRE(!dual || a->other[l] != nullptr, "pf_lookup_dual: other[%d] is null", l);
   }
   cudaStream_t st = (cudaStream_t)stream;
+  const int C_all = p.L * (2 * a->radius + 1) * (2 * a->radius + 1);
+  // radius 4 (the model's) runs the column-walk kernel; other radii the generic tap-per-lane kernel
+  // (PF_LOOKUP_LEGACY=1 forces the latter, for A/B timing only)
+  static const bool legacy = getenv("PF_LOOKUP_LEGACY") != nullptr && getenv("PF_LOOKUP_LEGACY")[0] == '1';
   // fused sum into an NCHW tensor: stage the own view channels-last (coalesced 324-byte runs, no transpose tile) and
   // let the rotate kernel add it while it transposes — one write pass over out_own instead of write + read-modify-write
-  const int C_all = p.L * (2 * a->radius + 1) * (2 * a->radius + 1);
   const bool stage_own = dual && a->fuse_sum && !a->out_channels_last && a->scratch_own != nullptr && C_all % 4 == 0 &&
                          (((uintptr_t)a->scratch_own | (uintptr_t)a->scratch | (uintptr_t)a->out_own) & 15) == 0;
   if (stage_own) {
     p.channels_last = 1;
     p.out_own = a->scratch_own;
   }
-  // radius 4 (the model's) runs the column-walk kernel; other radii the generic tap-per-lane kernel
-  // (PF_LOOKUP_LEGACY=1 forces the latter, for A/B timing only)
-  static const bool legacy = getenv("PF_LOOKUP_LEGACY") != nullptr && getenv("PF_LOOKUP_LEGACY")[0] == '1';
   if (a->radius == 4 && !legacy) {
     if (int e = launch_lookup_rows(p, dual, st, "pf_lookup_dual")) return e;
   } else {

@@ -351,6 +351,30 @@ def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence
     return (out_own, out_other) if dual else out_own
 
 
+# ------------------------------------------------------------------------------------------ measurement aids
+def probe_gather(vol: torch.Tensor, pos_xy: torch.Tensor) -> None:
+    """Issues the loads of an own-view lookup of `vol` [planes,H,W] at integer footprint corners pos_xy [planes,2] (int32) and
+    nothing else — the HBM floor of the lookup's access pattern (bench.py times it beside the kernel)."""
+    lib = _lib.load()
+    _chk(vol, "vol", 3)
+    if pos_xy.dtype != torch.int32 or not pos_xy.is_cuda or tuple(pos_xy.shape) != (vol.shape[0], 2):
+        raise ValueError("pos_xy must be a CUDA int32 tensor [planes, 2]")
+    vol, pos_xy = vol.contiguous(), pos_xy.contiguous()
+    with torch.cuda.device(vol.device):
+        sink = torch.empty(1, device=vol.device)
+        _lib.check(lib.pf_probe_gather(vol.data_ptr(), vol.shape[0], vol.shape[1], vol.shape[2], pos_xy.data_ptr(),
+                                       sink.data_ptr(), _stream()), "pf_probe_gather")
+
+
+def probe_stream_read(buf: torch.Tensor) -> None:
+    """Reads a contiguous fp32 CUDA tensor once (read-only streaming ceiling)."""
+    lib = _lib.load()
+    _chk(buf, "buf")
+    with torch.cuda.device(buf.device):
+        sink = torch.empty(1, device=buf.device)
+        _lib.check(lib.pf_probe_stream_read(buf.data_ptr(), buf.numel(), sink.data_ptr(), _stream()), "pf_probe_stream_read")
+
+
 # ------------------------------------------------------------------------------------------ (e)
 def _grad_layout(g: torch.Tensor, channels_last: bool) -> torch.Tensor:
     """Brings an incoming [B,C,h,w] gradient into the memory layout the backward kernels read."""

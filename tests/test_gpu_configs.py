@@ -1,0 +1,165 @@
+"""GPU: op-level parity at the shapes of BASELINE configs 3, 4 and 5 — what the 1024x2048 and batched bench records rest on.
+
+  config 3 / 5: batch 8 at 512x1024 (8 pairs per GPU)        -> B = 8, 64x128 features, N = 8192
+  config 4:     1024x2048 ERP, fully materialised and on-the-fly -> B = 1, 128x256 features, N = 32768 (level 0 = 4 GiB / view)
+
+Reference = the ATen ops the reference executes (oracle/torch_oracle.py on the device, ATen's native grid_sampler kernel:
+see tests/test_gpu_torch_parity.py for why not cuDNN's).  Bars: lookups bit-exact; volume 1e-5 of max|ref| (max-abs error over
+max-abs reference, conftest.rel_to_max); on-the-fly 1e-5 of max|ref| against the materialised lookup.
+Also here: sample grids bit-exact against the UNMODIFIED reference on CUDA, and the GradSink double-backward regression.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shim
+from oracle import torch_oracle as TO
+from test_gpu_torch_parity import native_aten
+
+pytestmark = pytest.mark.gpu
+C = 256
+
+
+def rel(a, b):
+    """max |a-b| / max |b| on the device (the tensors here are up to 4 GiB)."""
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def make_scene(B, h, w, seed):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    fm = [torch.randn(B, C, h, w, device="cuda", generator=g) * 1.45 for _ in range(4)]
+    coords = TO.coords_grid(B, h, w, "cuda") + torch.randn(B, 2, h, w, device="cuda", generator=g) * 5.0
+    Ra = TO.rotation_matrix([0., 0., -np.pi / 2], device="cuda")
+    Rb = TO.rotation_matrix([0., 0., np.pi / 2], device="cuda")
+    gw = TO.generate_samplegrid((B, 3, h, w), Ra.T.contiguous())
+    gc = TO.generate_samplegrid((B, 3, h, w), Rb)
+    return fm, coords, gw, gc
+
+
+def test_config4_shape_128x256_features():
+    """1024x2048 ERP: N = 32768 query pixels, level 0 of one view = 4 GiB."""
+    from prior_flow_b200 import ops
+    B, h, w = 1, 128, 256
+    fm, coords, gw, gc = make_scene(B, h, w, 41)
+    pa = ops.volume_pyramid(fm[0], fm[1], 4, "fp32")
+    ref_a = TO.build_pyramid(TO.corr_volume(fm[0], fm[1]))
+    for l in range(4):
+        assert pa[l].shape == ref_a[l].shape == (B * h * w, 1, h >> l, w >> l)
+        e = rel(pa[l], ref_a[l])
+        assert e < 1e-5, (l, e)
+    del pa
+    ref_b = TO.build_pyramid(TO.corr_volume(fm[2], fm[3]))
+    own, other = ops.lookup(coords, ref_a, ref_b, gw, gc, 4)
+    with native_aten():
+        want_own, want_other = TO.dccl_lookup(coords, ref_a, ref_b, gw, gc, 4)
+    assert torch.equal(own, want_own)
+    assert torch.equal(other, want_other)
+    fused = ops.lookup(coords, ref_a, ref_b, gw, gc, 4, fuse_sum=True)
+    assert torch.equal(fused, want_own + want_other)
+    del ref_a, ref_b
+    torch.cuda.empty_cache()
+    cl = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    o2, x2 = ops.lookup_onthefly(coords, cl(fm[0]), ops.channels_last_pyramid(fm[1], 4), cl(fm[2]),
+                                 ops.channels_last_pyramid(fm[3], 4), gw, gc, 4)
+    e_own, e_other = rel(o2, want_own), rel(x2, want_other)
+    print(f"\n[config 4 shape] on-the-fly vs materialised: own {e_own:.2e}, other {e_other:.2e} of max|ref|")
+    assert e_own < 1e-5 and e_other < 1e-5
+
+
+def test_config3_shape_batch8_at_64x128_features():
+    """8 pairs per GPU at 512x1024: every kernel with B = 8 against the per-sample results and against ATen."""
+    from prior_flow_b200 import ops
+    B, h, w = 8, 64, 128
+    fm, coords, gw, gc = make_scene(B, h, w, 43)
+    pa, pb = ops.volume_pyramid(fm[0], fm[1], 4, "fp32"), ops.volume_pyramid(fm[2], fm[3], 4, "fp32")
+    N = h * w
+    for b in (0, 3, 7):        # batched build == per-sample build, bit for bit
+        one = ops.volume_pyramid(fm[0][b:b + 1], fm[1][b:b + 1], 4, "fp32")
+        for l in range(4):
+            assert torch.equal(pa[l][b * N:(b + 1) * N], one[l]), (b, l)
+    ref_a = TO.build_pyramid(TO.corr_volume(fm[0], fm[1]))
+    for l in range(4):
+        assert rel(pa[l], ref_a[l]) < 1e-5, l
+    del ref_a
+    own, other = ops.lookup(coords, pa, pb, gw, gc, 4)
+    with native_aten():
+        want_own, want_other = TO.dccl_lookup(coords, pa, pb, gw, gc, 4)
+    assert torch.equal(own, want_own)
+    assert torch.equal(other, want_other)
+    fused_cl = ops.lookup(coords, pa, pb, gw, gc, 4, channels_last=True, fuse_sum=True)
+    assert torch.equal(fused_cl, want_own + want_other)
+    flow = coords - TO.coords_grid(B, h, w, "cuda")
+    assert torch.equal(ops.flo_rotate(flow, gw, gc), TO.flo_rotate(flow, gw, gc))
+    got = ops.warp_groupcorr(fm[0], fm[1], coords, 4)
+    assert rel(got, TO.warp_groupcorr(fm[0], fm[1], coords, 4)) < 1e-5
+    cl = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    o2, x2 = ops.lookup_onthefly(coords, cl(fm[0]), ops.channels_last_pyramid(fm[1], 4), cl(fm[2]),
+                                 ops.channels_last_pyramid(fm[3], 4), gw, gc, 4)
+    assert rel(o2, want_own) < 1e-5 and rel(x2, want_other) < 1e-5
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="vendored reference missing (scripts/vendor_reference.py)")
+def test_samplegrids_bit_exact_against_the_unmodified_reference_on_cuda():
+    """generate_samplegrid (projection_prim_ortho.py:432-443) run by the reference itself on this GPU vs pf_samplegrid:
+    every one of the eight grids `PriOr_RAFT.forward` builds (prior_raft.py:115-125), `==`.  (For these rotations the
+    3x3 product of rotate_cartesian has entries 0, +-1 and -4.37e-8, so cuBLAS's accumulation order cannot matter; a general
+    rotation is only pinned to 2 ulp by tests/test_gpu_torch_parity.py::test_samplegrids_full_size.)"""
+    from prior_flow_b200 import geometry as geo
+    from prior_flow_b200 import ops
+    ref = ref_shim.load()
+    assert ref_shim.verified()
+    for H, W in ((64, 128), (128, 256), (512, 1024)):
+        for ang in (-np.pi / 2, np.pi / 2):
+            R = ref.ppo.generate_rotation_metrix(theta_list=[0., 0., ang])
+            assert torch.equal(R, geo.generate_rotation_metrix(theta_list=[0., 0., ang]))
+            for Rm in (R, R.T):
+                want = ref.ppo.generate_samplegrid((1, 3, H, W), Rm)
+                got = ops.samplegrid((1, 3, H, W), Rm.contiguous())
+                assert torch.equal(got, want), (H, W, ang)
+                assert torch.equal(geo.generate_samplegrid((1, 3, H, W), Rm), want)
+
+
+def test_grad_sink_survives_a_second_backward():
+    """with the shared gradient sink a second backward over a retained graph used to scatter into stale buffers and
+    hand the volume zero gradient.  Two backward passes must each equal the sink-free result."""
+    from prior_flow_b200.corr import DCCL, CostVolume
+    B, h, w = 1, 16, 32
+    fm, coords, gw, gc = make_scene(B, h, w, 47)
+
+    def run(accumulate):
+        f = [t.clone().requires_grad_(True) for t in fm]
+        look = DCCL(4, 4, mode="materialized", accumulate_grads=accumulate)
+        pa, pb = look.build_pyramid(CostVolume(f[0], f[1])), look.build_pyramid(CostVolume(f[2], f[3]))
+        loss = 0
+        for k in range(3):      # three iterations, both call directions, like PriOr_RAFT.forward
+            c = coords + 0.37 * k
+            loss = loss + look.summed(c, pa, pb, gw, gc).square().mean() + look.summed(c, pb, pa, gc, gw).abs().mean()
+        grads = []
+        for _ in range(2):
+            for t in f:
+                t.grad = None
+            loss.backward(retain_graph=True)
+            grads.append([t.grad.clone() for t in f])
+        return grads
+
+    plain, sunk = run(False), run(True)
+    for pass_ in range(2):
+        for a, b in zip(plain[pass_], sunk[pass_]):
+            assert float(b.abs().max()) > 0
+            assert float((a - b).abs().max() / a.abs().max()) < 1e-4      # atomics order only
+    for a, b in zip(sunk[0], sunk[1]):
+        assert float((a - b).abs().max() / a.abs().max()) < 1e-4
+
+
+def test_grad_sink_refuses_a_foreign_consumer():
+    """A pyramid level that also feeds something other than a DCCL lookup invalidates the in-place sink: loud error, not a
+    silently wrong gradient."""
+    from prior_flow_b200.corr import DCCL, CostVolume
+    fm, coords, gw, gc = make_scene(1, 16, 32, 53)
+    f = [t.clone().requires_grad_(True) for t in fm]
+    look = DCCL(4, 4, mode="materialized", accumulate_grads=True)
+    pa, pb = look.build_pyramid(CostVolume(f[0], f[1])), look.build_pyramid(CostVolume(f[2], f[3]))
+    loss = look.summed(coords, pa, pb, gw, gc).mean() + look.summed(coords + 1, pa, pb, gw, gc).mean() + pa[0].mean()
+    with pytest.raises(RuntimeError, match="GradSink"):
+        loss.backward()
