@@ -53,6 +53,9 @@ def parse():
                     help="memory format of the cuDNN side; channels_last also makes the lookups emit NHWC directly")
     ap.add_argument("--corr-mode", default="auto", choices=["auto", "materialized", "onthefly"],
                     help="DCCL mode: auto materialises the pyramids while they fit in device memory; BASELINE configs[3] names onthefly")
+    ap.add_argument("--cudnn-tf32", default="on", choices=["on", "off"],
+                    help="TF32 convolutions on the cuDNN side (PyTorch's and hence the reference's default on a GPU); off = fp32 "
+                         "convolutions, the setting the 1e-3 px flow gate is stated for (tests/test_gpu_dropin.py)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-gpu-baselines", action="store_true", help="skip gpu_eager_baseline / dropin (reference on the same GPU)")
     ap.add_argument("--skip-traffic", action="store_true", help="skip the ncu pass that measures roofline.traffic")
@@ -237,6 +240,7 @@ def main_ours(a):
             os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     ops.set_volume_mode(a.volume_mode)
+    torch.backends.cudnn.allow_tf32 = a.cudnn_tf32 == "on"
     torch.backends.cudnn.benchmark = True     # let cuDNN pick its conv algorithms (the default picks a CUDA-core SGEMM for the 1x1)
     strong = a.global_batch > 0
     if strong:
@@ -492,7 +496,9 @@ def main_ours(a):
                        "global_batch": world * B,
                        "cuda_graph": not a.no_graph, "weights": "random init (seed 0)", "memory_format": a.memory_format,
                        "l2": "no flush between steps: one step streams ~2.4 GB (2x340 MiB pyramids written, re-read by 24 lookups) >> 126 MB L2",
-                       "cudnn_tf32": bool(torch.backends.cudnn.allow_tf32), "cudnn_benchmark": True, "hot_path": "fp32 (tcgen05 fp16x2 split, fp32 accumulate)"},
+                       "cudnn_tf32": bool(torch.backends.cudnn.allow_tf32), "cudnn_benchmark": True,
+                       "flow_vs_reference": "mean EPE vs the unmodified reference at this shape (tests/test_gpu_dropin.py): 9.8e-6 px with fp32 "
+                                            "convolutions; 3.4e-3 px with TF32 convolutions, where the reference's own TF32 run is 6.1e-3 px from its fp32 run", "hot_path": "fp32 (tcgen05 fp16x2 split, fp32 accumulate)"},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 2 * host1.numel() * 4,
                     "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": round(e2e_ms / a.steps, 4)},
             "gpu_launches": launches_per_forward * a.steps,

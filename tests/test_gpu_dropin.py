@@ -125,38 +125,47 @@ def test_installed_reference_train_step_gradients(ref, fp32_convs):
     assert float((g2a - g2b).abs().max() / g2a.abs().max()) < 5e-3
 
 
-def test_benchmarked_configuration_matches_reference_with_tf32(ref):
-    """What bench.py times — model.py with channels_last, folded BN, fused conv+ReLU, TF32 convolutions, CUDA-graph replay —
-    against the unmodified reference run the way it runs on a GPU by default (cuDNN TF32 on).  The noise floor printed
-    beside it is the reference against itself with cuDNN's autotuner on (other TF32 kernels, same math)."""
+def test_benchmarked_configuration_matches_reference(ref):
+    """What bench.py times — model.py with channels_last, folded BN, fused conv+ReLU, CUDA-graph replay — against the unmodified
+    reference, (a) with fp32 convolutions: the north_star gate, 1e-3 px; (b) with TF32 convolutions, the reference's default on
+    a GPU and bench.py's default: TF32 is stated separately (north_star), because the reference's own TF32 run is 6e-3 px away
+    from its fp32 run (measured here, printed) — any re-association of a TF32 convolution (NHWC kernels, BN folded into the
+    weights) moves the flow by a fraction of that.  Bar for (b): closer to the reference's TF32 flow than that flow is to the
+    reference's fp32 flow."""
     from prior_flow_b200.model import PriOrRAFT
     old = torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark
-    torch.backends.cudnn.allow_tf32 = True
     try:
         model = ref_shim.make_model(ref, seed=0).cuda().eval()
         im1, im2 = images(H, W)
-        torch.backends.cudnn.benchmark = False
-        flow_ref = run(model, im1, im2)
-        torch.backends.cudnn.benchmark = True
-        flow_ref_tuned = run(model, im1, im2)
         ours = PriOrRAFT().cuda().eval()
         ours.load_state_dict(model.state_dict(), strict=True)
         ours = ours.to_channels_last()
-        run(ours, im1, im2)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
+        res = {}
+        for tf32 in (False, True):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cudnn.benchmark = False
+            flow_ref = run(model, im1, im2)
+            torch.backends.cudnn.benchmark = True           # bench.py's setting
             run(ours, im1, im2)
-        torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            with torch.no_grad():
-                static_out = ours(im1, im2, iters=ITERS, test_mode=True)
-        graph.replay()
-        torch.cuda.synchronize()
-        epe, floor = mean_epe(static_out, flow_ref), mean_epe(flow_ref_tuned, flow_ref)
-        print(f"\n[bench config 512x1024/12it tf32] mean EPE ours(graph, channels_last, folded BN)-vs-reference {epe:.3e} px; "
-              f"reference-vs-reference(cudnn.benchmark) {floor:.3e} px")
-        assert epe <= max(1e-3, 3 * floor)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                run(ours, im1, im2)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                with torch.no_grad():
+                    static_out = ours(im1, im2, iters=ITERS, test_mode=True)
+            graph.replay()
+            torch.cuda.synchronize()
+            res[tf32] = (flow_ref, static_out.clone())
+            del graph
+        epe32 = mean_epe(res[False][1], res[False][0])
+        epe_tf = mean_epe(res[True][1], res[True][0])
+        tf32_noise = mean_epe(res[True][0], res[False][0])
+        print(f"\n[bench config 512x1024/12it] ours(graph, channels_last, folded BN) vs reference: fp32 convs {epe32:.3e} px; "
+              f"TF32 convs {epe_tf:.3e} px; reference TF32 vs reference fp32 {tf32_noise:.3e} px")
+        assert epe32 <= 1e-3
+        assert epe_tf <= tf32_noise
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = old
