@@ -101,8 +101,39 @@ typedef struct pf_lookup_args {
                                        /* fuse_sum and NCHW output the own view is staged here    */
                                        /* channels-last and added in the rotate kernel's single   */
                                        /* write pass instead of a read-modify-write of out_own    */
+  int no_rotate;                       /* 1 (needs out_channels_last): stop after the gather — out_own holds the own view and   */
+                                       /* `scratch` the other view BEFORE img_rotate, both [B, h, w, L*(2r+1)^2]; the consumer  */
+                                       /* is pf_dccl_conv, which rotates, sums and convolves in one kernel                      */
 } pf_lookup_args;
 int pf_lookup_dual(const pf_lookup_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (f1) img_rotate + `own + other` + the motion encoder's first layer, fused: replaces the tail of DCCL.__call__
+ * (core/corr.py:137-138), `corr_A + corr_B_A` (core/prior_raft.py:187-188) and `F.relu(self.convc1_A(corr))` /
+ * `F.relu(self.convc1(corr))` — Conv2d(324, 256, 1) (core/update.py:168,184 and :85,92) — with one tcgen05 kernel:
+ *   out[b, o, n] = relu(bias[o] + sum_c W[o, c] * (own[b, n, c] + img_rotate(raw)[b, n, c]))
+ * Inputs are what pf_lookup_dual leaves behind with no_rotate = 1.  The weights are pre-split once into fp16 planes with
+ * pf_dccl_conv_prepare (pf_dccl_conv_weight_bytes() bytes, 1 KiB aligned; redo it when the weights change).
+ * split = 1: fp16 hi/lo three-product scheme, fp32-class accuracy (stated 1e-5 of max|ref|); split = 0: single fp16
+ * product, TF32-class accuracy (stated 2e-3) — what cuDNN runs for this layer under torch.backends.cudnn.allow_tf32. */
+typedef struct pf_dccl_conv_args {
+  int batch, h, w;                     /* query grid                                               */
+  int in_channels, out_channels;       /* 324, 256                                                 */
+  int div_mode;                        /* enum pf_div_mode (img_rotate's sampler)                  */
+  int split;                           /* 1: fp32-class (3 products); 0: TF32-class (1 product)    */
+  int out_channels_last;               /* 1: out is [B, h, w, 256]; 0: [B, 256, h, w]              */
+  int after_lookup;                    /* 1: launched right behind pf_lookup_dual on the same stream (programmatic dependent launch) */
+  const float *raw;                    /* [B, h, w, 324] other view before img_rotate (`scratch`)  */
+  const float *own_cl;                 /* [B, h, w, 324] own view                                  */
+  const float *grid_c2w;               /* [B, 2, h, w] `sample_grid_*_8x`                          */
+  long long grid_batch_stride;
+  const void *prepared_weight;         /* pf_dccl_conv_prepare output                              */
+  const float *bias;                   /* [256]                                                    */
+  float *out;
+} pf_dccl_conv_args;
+long long pf_dccl_conv_weight_bytes(void);
+int pf_dccl_conv_prepare(const float *weight /*[256, 324]*/, int out_channels, int in_channels, void *prepared, void *stream);
+int pf_dccl_conv(const pf_dccl_conv_args *args, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (c) on-the-fly lookup: same outputs as pf_lookup_dual but straight from the feature maps, no

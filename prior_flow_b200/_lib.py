@@ -36,7 +36,14 @@ class LookupArgs(C.Structure):
                 ("grid_w2c", _fp), ("grid_c2w", _fp), ("grid_batch_stride", C.c_longlong),
                 ("out_own", _fp), ("out_other", _fp), ("scratch", _fp),
                 ("dbg_own_xy", _fp), ("dbg_other_xy", _fp),
-                ("out_channels_last", C.c_int), ("fuse_sum", C.c_int), ("scratch_own", _fp)]
+                ("out_channels_last", C.c_int), ("fuse_sum", C.c_int), ("scratch_own", _fp), ("no_rotate", C.c_int)]
+
+
+class DcclConvArgs(C.Structure):
+    _fields_ = [("batch", C.c_int), ("h", C.c_int), ("w", C.c_int), ("in_channels", C.c_int), ("out_channels", C.c_int),
+                ("div_mode", C.c_int), ("split", C.c_int), ("out_channels_last", C.c_int), ("after_lookup", C.c_int),
+                ("raw", _fp), ("own_cl", _fp), ("grid_c2w", _fp), ("grid_batch_stride", C.c_longlong),
+                ("prepared_weight", _fp), ("bias", _fp), ("out", _fp)]
 
 
 class OnTheFlyArgs(C.Structure):
@@ -80,6 +87,9 @@ SIGNATURES = {
     "pf_remap_bwd": (C.c_int, [C.POINTER(RemapArgs), _fp, _fp, _fp]),
     "pf_pyramid_fold_bwd": (C.c_int, [C.POINTER(_fp), C.c_int, C.c_longlong, C.c_int, C.c_int, _fp]),
     "pf_warp_groupcorr_bwd": (C.c_int, [_fp] * 6 + [C.c_int] * 6 + [_fp]),
+    "pf_dccl_conv_weight_bytes": (C.c_longlong, []),
+    "pf_dccl_conv_prepare": (C.c_int, [_fp, C.c_int, C.c_int, _fp, _fp]),
+    "pf_dccl_conv": (C.c_int, [C.POINTER(DcclConvArgs), _fp]),
     "pf_probe_gather": (C.c_int, [_fp, C.c_longlong, C.c_int, C.c_int, _fp, _fp, _fp]),
     "pf_probe_stream_read": (C.c_int, [_fp, C.c_longlong, _fp, _fp]),
 }

@@ -137,6 +137,17 @@ class DCCL:
                                    sink_other=getattr(corr_pyramid_B, "grad_sink", None))
 
 
+    def summed_conv(self, coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x, conv,
+                    channels_last: bool = False, fp32: bool = True):
+        """`F.relu(conv(corr_own + corr_other))` for the motion encoder's first layer `conv` = Conv2d(324, 256, 1)
+        (core/update.py:168,184 / :85,92) without ever forming the [B,324,h,w] sum: inference only, materialised pyramids."""
+        if isinstance(corr_pyramid_A, FeaturePyramid) or torch.is_grad_enabled() and (conv.weight.requires_grad or corr_pyramid_A[0].requires_grad):
+            x = self.summed(coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x, channels_last)
+            return torch.relu(conv(x))
+        return ops.lookup_conv(coords.float(), corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x,
+                               conv.weight, conv.bias, channels_last=channels_last, fp32=fp32)
+
+
 class CorrBlock:
     """Plain RAFT correlation block — core/corr.py:13-61 (dead code in PriOr_RAFT.forward, kept for the signature)."""
 

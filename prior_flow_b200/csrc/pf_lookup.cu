@@ -1023,7 +1023,8 @@ extern "C" int pf_lookup_dual(const pf_lookup_args *a, void *stream) {
   LookupParams p;
   if (int e = fill_lookup_params(a, p, dual, "pf_lookup_dual")) return e;
   PF_REQUIRE(a->out_own != nullptr, "pf_lookup_dual: out_own is required");
-  PF_REQUIRE(!dual || a->fuse_sum || a->out_other != nullptr, "pf_lookup_dual: out_other is required unless fuse_sum");
+  PF_REQUIRE(!dual || a->fuse_sum || a->no_rotate || a->out_other != nullptr, "pf_lookup_dual: out_other is required unless fuse_sum / no_rotate");
+  PF_REQUIRE(!a->no_rotate || (dual && a->out_channels_last && !a->fuse_sum), "pf_lookup_dual: no_rotate needs the dual lookup with channels-last outputs and no fuse_sum");
   for (int l = 0; l < p.L; ++l) {
     PF_REQUIRE(a->own[l] != nullptr, "pf_lookup_dual: own[%d] is null", l);
     PF_REQUIRE(!dual || a->other[l] != nullptr, "pf_lookup_dual: other[%d] is null", l);
@@ -1046,7 +1047,7 @@ extern "C" int pf_lookup_dual(const pf_lookup_args *a, void *stream) {
   } else {
     if (int e = launch_lookup<false>(p, a->radius, dual, st, "pf_lookup_dual")) return e;
   }
-  if (dual) {
+  if (dual && !a->no_rotate) {
     // core/corr.py:137-138 — img_rotate of the [B, L*81, h, w] map with grid_c2w.
     return rotate_forward(a->batch, a->h, a->w, a->num_levels, a->radius, a->div_mode, a->grid_c2w,
                           a->grid_batch_stride, a->scratch, a->fuse_sum ? a->out_own : a->out_other, a->out_channels_last,

@@ -167,8 +167,9 @@ class MotionEncoder(nn.Module):
         self.convf2 = nn.Conv2d(128, 64, 3, padding=1)
         self.conv = nn.Conv2d(64 + 192, 128 - 2, 3, padding=1)
 
-    def forward(self, flow, corr):
-        cor = _conv_relu(self.convc2, _conv_relu(self.convc1, corr))
+    def forward(self, flow, corr, cor1=None):
+        # cor1: relu(convc1(corr)) already computed by the fused rotate + sum + 1x1-conv kernel (ops.lookup_conv)
+        cor = _conv_relu(self.convc2, cor1 if cor1 is not None else _conv_relu(self.convc1, corr))
         flo = _conv_relu(self.convf2, _conv_relu(self.convf1, flow))
         return torch.cat([_conv_relu(self.conv, torch.cat([cor, flo], dim=1)), flow], dim=1)
 
@@ -188,8 +189,8 @@ class DualMotionEncoder(nn.Module):
         self.conv_conf2 = nn.Conv2d(32, 16, 3, padding=1)
         self.conv_A = nn.Conv2d(128 + 64 + 64 + 16, 128 - 4, 3, padding=1)
 
-    def forward(self, flow_A, corr_A, flaw_A, flow_B_A, flaw_B_A):
-        cor = _conv_relu(self.convc2_A, _conv_relu(self.convc1_A, corr_A))
+    def forward(self, flow_A, corr_A, flaw_A, flow_B_A, flaw_B_A, cor1=None):
+        cor = _conv_relu(self.convc2_A, cor1 if cor1 is not None else _conv_relu(self.convc1_A, corr_A))
         fa = _conv_relu(self.convf2_A, _conv_relu(self.convf1_A, flow_A))
         fb = _conv_relu(self.convf2_B, _conv_relu(self.convf1_B, flow_B_A))
         conf = _conv_relu(self.conv_conf2, _conv_relu(self.conv_conf1, torch.cat([flaw_A, flaw_B_A], dim=1)))
@@ -215,16 +216,16 @@ class UpdateBlock(_UpdateBase):          # BasicUpdateBlock, core/update.py:117-
     def __init__(self, cor_planes: int, hidden: int = 128):
         super().__init__(MotionEncoder(cor_planes), hidden)
 
-    def forward(self, net, inp, corr, flow, want_mask=True):
-        return self._step(net, inp, self.encoder(flow, corr), want_mask)
+    def forward(self, net, inp, corr, flow, want_mask=True, cor1=None):
+        return self._step(net, inp, self.encoder(flow, corr, cor1), want_mask)
 
 
 class DualUpdateBlock(_UpdateBase):      # BasicMultiUpdateBlock ("ODDC"), core/update.py:139-159
     def __init__(self, cor_planes: int, hidden: int = 128):
         super().__init__(DualMotionEncoder(cor_planes), hidden)
 
-    def forward(self, net, inp, flow_A, corr_A, flaw_A, flow_B_A, flaw_B_A, want_mask=True):
-        return self._step(net, inp, self.encoder(flow_A, corr_A, flaw_A, flow_B_A, flaw_B_A), want_mask)
+    def forward(self, net, inp, flow_A, corr_A, flaw_A, flow_B_A, flaw_B_A, want_mask=True, cor1=None):
+        return self._step(net, inp, self.encoder(flow_A, corr_A, flaw_A, flow_B_A, flaw_B_A, cor1), want_mask)
 
 
 # --------------------------------------------------------------------------------------- the model
@@ -247,6 +248,9 @@ class PriOrRAFT(nn.Module):
         self.channels_last = False      # set by .to_channels_last(): lookups then emit torch.channels_last tensors
         # training: all lookups of a backward pass scatter into one gradient pyramid per view (ops.GradSink)
         self.accumulate_grads = os.environ.get("PF_GRAD_SINK", "1") != "0"
+        # inference: img_rotate + `corr_A + corr_B_A` + the motion encoders' first layer (Conv2d(324, 256, 1) + ReLU) as one
+        # tcgen05 kernel behind the gather; the [B,324,h,w] lookup tensor is then never formed
+        self.fuse_conv1 = os.environ.get("PF_FUSE_CONV1", "1") != "0"
         cor_planes = 4 * 9 * 9
         self.fnet = Encoder(256, "instance", dropout)
         self.cnet = Encoder(256, "batch", dropout)
@@ -324,15 +328,25 @@ class PriOrRAFT(nn.Module):
             flaw_B_A = ops.warp_groupcorr_autograd(f1A, f2A, coords0 + flow_B_A, 4)
             with amp():
                 # corr_A + corr_B_A and corr_B + corr_A_B (prior_raft.py:185-188), the adds fused into the rotate kernel
-                corr_A = lookup.summed(coords1_A, pyr_A, pyr_B, g["A2B_W2C_8x"], g["B2A_8x"], self.channels_last)
-                corr_B = lookup.summed(coords1_B, pyr_B, pyr_A, g["B2A_W2C_8x"], g["A2B_8x"], self.channels_last)
+                fused1 = (self.fuse_conv1 and not torch.is_grad_enabled() and not self.args.mixed_precision
+                          and isinstance(pyr_A, list))
+                corr_A = corr_B = cor1_A = cor1_B = None
+                if fused1:
+                    fp32 = not torch.backends.cudnn.allow_tf32     # the precision cuDNN would run this layer in
+                    cor1_A = lookup.summed_conv(coords1_A, pyr_A, pyr_B, g["A2B_W2C_8x"], g["B2A_8x"], self.ODDC.encoder.convc1_A,
+                                                self.channels_last, fp32)
+                    cor1_B = lookup.summed_conv(coords1_B, pyr_B, pyr_A, g["B2A_W2C_8x"], g["A2B_8x"], self.update_block.encoder.convc1,
+                                                self.channels_last, fp32)
+                else:
+                    corr_A = lookup.summed(coords1_A, pyr_A, pyr_B, g["A2B_W2C_8x"], g["B2A_8x"], self.channels_last)
+                    corr_B = lookup.summed(coords1_B, pyr_B, pyr_A, g["B2A_W2C_8x"], g["A2B_8x"], self.channels_last)
                 if self.channels_last:
                     # torch.cat falls back to NCHW as soon as ONE input is NCHW (and every convolution behind it then
                     # pays a layout copy): hand the update blocks their 2- and 4-channel inputs in NHWC as well
                     cl = lambda t: t.contiguous(memory_format=torch.channels_last)
                     flow_A, flow_B, flow_B_A, flaw_A, flaw_B_A = cl(flow_A), cl(flow_B), cl(flow_B_A), cl(flaw_A), cl(flaw_B_A)
-                net_A, mask_A, d_A = self.ODDC(net_A, inp_A, flow_A, corr_A, flaw_A, flow_B_A, flaw_B_A, want_mask=want_up)
-                net_B, mask_B, d_B = self.update_block(net_B, inp_B, corr_B, flow_B, want_mask=want_up and not test_mode)
+                net_A, mask_A, d_A = self.ODDC(net_A, inp_A, flow_A, corr_A, flaw_A, flow_B_A, flaw_B_A, want_mask=want_up, cor1=cor1_A)
+                net_B, mask_B, d_B = self.update_block(net_B, inp_B, corr_B, flow_B, want_mask=want_up and not test_mode, cor1=cor1_B)
             coords1_A = coords1_A + d_A
             coords1_B = coords1_B + d_B
             if want_up:

@@ -207,6 +207,86 @@ def lookup(coords: torch.Tensor, pyr_own: Sequence[torch.Tensor], pyr_other: Opt
     return res
 
 
+# ------------------------------------------------------------------------------------------ (f1)
+_conv_weight_cache = {}
+
+
+def prepare_conv_weight(weight: torch.Tensor) -> torch.Tensor:
+    """Conv2d(324, 256, 1) weight -> the K-major fp16 hi/lo planes pf_dccl_conv streams with TMA (cached per tensor
+    version: call again after an optimizer step)."""
+    lib = _lib.load()
+    _chk(weight, "weight")
+    if weight.dim() == 4:
+        if weight.shape[2:] != (1, 1):
+            raise ValueError("pf_dccl_conv fuses a 1x1 convolution")
+    elif weight.dim() != 2:
+        raise ValueError("weight must be [256, 324] or [256, 324, 1, 1]")
+    key = (weight.data_ptr(), weight._version, str(weight.device))
+    hit = _conv_weight_cache.get(key)
+    if hit is not None:
+        return hit
+    w2 = weight.detach().reshape(weight.shape[0], weight.shape[1]).contiguous()
+    with torch.cuda.device(weight.device):
+        nbytes = lib.pf_dccl_conv_weight_bytes()
+        buf = torch.empty(nbytes + 1024, device=weight.device, dtype=torch.uint8)
+        off = (-buf.data_ptr()) % 1024
+        prepared = buf[off:off + nbytes]
+        _lib.check(lib.pf_dccl_conv_prepare(w2.data_ptr(), w2.shape[0], w2.shape[1], prepared.data_ptr(), _stream()),
+                   "pf_dccl_conv_prepare")
+        _count(2)
+    if len(_conv_weight_cache) > 16:
+        _conv_weight_cache.clear()
+    _conv_weight_cache[key] = prepared
+    return prepared
+
+
+def lookup_conv(coords: torch.Tensor, pyr_own: Sequence[torch.Tensor], pyr_other: Sequence[torch.Tensor], grid_w2c: torch.Tensor,
+                grid_c2w: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, channels_last: bool = False,
+                fp32: bool = True) -> torch.Tensor:
+    """relu(conv1x1(own + other)) of a DCCL call in two launches (core/corr.py:113-144 + core/prior_raft.py:187-188 +
+    core/update.py:168,184 / :85,92): the gather kernel leaves both views channels-last, pf_dccl_conv rotates, sums and
+    convolves on tcgen05 — the [B,324,h,w] tensor never exists.  fp32=True: three-product fp16 split (1e-5 of max|ref|);
+    False: single product, TF32-class (2e-3).  Returns [B,256,h,w] (torch.channels_last memory format if asked)."""
+    lib = _lib.load()
+    _chk(coords, "coords", 4), _chk(bias, "bias", 1)
+    coords = coords.contiguous()
+    B, two, h, w = coords.shape
+    L = len(pyr_own)
+    if L != 4 or two != 2:
+        raise ValueError("lookup_conv is built for the model's 4-level, radius-4 lookup")
+    own = [_chk(t, f"pyr_own[{l}]").contiguous() for l, t in enumerate(pyr_own)]
+    other = [_chk(t, f"pyr_other[{l}]").contiguous() for l, t in enumerate(pyr_other)]
+    h2, w2 = own[0].shape[-2:]
+    prepared = prepare_conv_weight(weight)
+    dev = coords.device
+    with torch.cuda.device(dev):
+        own_cl = torch.empty((B, h, w, 324), device=dev, dtype=torch.float32)
+        raw = torch.empty_like(own_cl)
+        a = _lib.LookupArgs()
+        a.batch, a.h, a.w, a.h2, a.w2 = B, h, w, h2, w2
+        a.radius, a.num_levels, a.cyclic, a.div_mode = 4, L, 1, _state["div_mode"]
+        a.out_channels_last, a.fuse_sum, a.no_rotate = 1, 0, 1
+        a.coords = coords.data_ptr()
+        a.own, a.other = _lib.level_ptrs(own), _lib.level_ptrs(other)
+        gw, bs_w = _grid_arg(grid_w2c, "grid_w2c", B, h, w)
+        gc, bs_c = _grid_arg(grid_c2w, "grid_c2w", B, h, w)
+        if bs_w != bs_c:
+            gw, gc = gw.expand(B, 2, h, w).contiguous(), gc.expand(B, 2, h, w).contiguous()
+            bs_w = gw.stride(0)
+        a.grid_w2c, a.grid_c2w, a.grid_batch_stride = gw.data_ptr(), gc.data_ptr(), bs_w
+        a.out_own, a.scratch = own_cl.data_ptr(), raw.data_ptr()
+        _lib.check(lib.pf_lookup_dual(C.byref(a), _stream()), "pf_lookup_dual")
+        out = torch.empty((B, h, w, 256) if channels_last else (B, 256, h, w), device=dev, dtype=torch.float32)
+        c = _lib.DcclConvArgs()
+        c.batch, c.h, c.w, c.in_channels, c.out_channels = B, h, w, 324, 256
+        c.div_mode, c.split, c.out_channels_last, c.after_lookup = _state["div_mode"], int(fp32), int(channels_last), 1
+        c.raw, c.own_cl, c.grid_c2w, c.grid_batch_stride = raw.data_ptr(), own_cl.data_ptr(), gc.data_ptr(), bs_w
+        c.prepared_weight, c.bias, c.out = prepared.data_ptr(), bias.contiguous().data_ptr(), out.data_ptr()
+        _lib.check(lib.pf_dccl_conv(C.byref(c), _stream()), "pf_dccl_conv")
+        _count(2)
+    return _as_nchw_view(out) if channels_last else out
+
+
 # ------------------------------------------------------------------------------------------ (d)
 def samplegrid(size, R: torch.Tensor, device=None) -> torch.Tensor:
     """generate_samplegrid (core/utils/projection_prim_ortho.py:432-443) -> [B,2,H,W]."""
