@@ -209,6 +209,21 @@ typedef struct pf_lookup_bwd_args {
 } pf_lookup_bwd_args;
 int pf_lookup_dual_bwd(const pf_lookup_bwd_args *args, void *stream);
 
+/* Adjoints of the volume contraction (autograd of core/prior_raft.py:73-75) on tcgen05, both in one launch:
+ *   dfmap1[b,c,n] = sum_m dvolume[b,n,m] fmap2[b,c,m] / sqrt(C)      dfmap2[b,c,m] = sum_n dvolume[b,n,m] fmap1[b,c,n] / sqrt(C)
+ * dvolume is the level-0 gradient after pf_pyramid_fold_bwd.  bf16 hi/lo split of both operands, three products, fp32
+ * accumulation: relative error ~2^-16 (stated tolerance for gradients: 1e-4 of max|ref|).  Needs C == 256, h*w % 128 == 0. */
+typedef struct pf_volume_bwd_args {
+  int batch, channels, h, w;
+  const float *fmap1, *fmap2;          /* [B, C, h, w]                                             */
+  const float *dvolume;                /* [B, h*w, h*w]                                            */
+  float *dfmap1, *dfmap2;              /* [B, C, h, w]; either may be NULL                         */
+  void *workspace;                     /* pf_volume_bwd_workspace_bytes() bytes, 1 KiB aligned     */
+  long long workspace_bytes;
+} pf_volume_bwd_args;
+long long pf_volume_bwd_workspace_bytes(int batch, int channels, int h, int w);
+int pf_volume_bwd(const pf_volume_bwd_args *args, void *stream);
+
 /* Adjoint of pf_remap w.r.t. src: dsrc += scatter(dout) (dsrc must be initialised by the caller). */
 int pf_remap_bwd(const pf_remap_args *args, const float *dout, float *dsrc, void *stream);
 
@@ -220,6 +235,23 @@ int pf_pyramid_fold_bwd(float *const *glevel, int num_levels, long long planes, 
 int pf_warp_groupcorr_bwd(const float *fmap1, const float *fmap2, const float *coords, const float *dout,
                           float *dfmap1, float *dfmap2, int batch, int channels, int h, int w, int groups,
                           int div_mode, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (f2) / (f4): the callers either side of the path that reuse its geometry.
+ */
+/* PriOr_RAFT.upsample_flow (core/prior_raft.py:58-67): flow [B,2,h,w], mask [B,576,h,w] (or channels-last [B,h,w,576];
+ * channel = k*64 + di*8 + dj) -> out [B,2,8h,8w] = sum_k softmax_k(mask) * 8 * flow[3x3 neighbour k], zero padded. */
+int pf_convex_upsample(const float *flow, const float *mask, float *out, int batch, int h, int w, int mask_channels_last,
+                       void *stream);
+/* One term of uniform_loss (train_flow.py:55-79): *acc += term_weight * sum(ok * lat[y] * |pred - gt|_1), with ok [B,H,W] the
+ * 0/1 validity mask, lat [H] the normalised cos-latitude weights (core/utils/spherical.py:11-17); and its gradient
+ * dpred = *upstream * term_weight * ok * lat[y] * sign(pred - gt). */
+int pf_uniform_loss_fwd(const float *pred, const float *gt, const float *ok, const float *lat, float *acc, float term_weight,
+                        int batch, int H, int W, void *stream);
+int pf_uniform_loss_bwd(const float *pred, const float *gt, const float *ok, const float *lat, const float *upstream,
+                        float term_weight, float *dpred, int batch, int H, int W, void *stream);
+/* calculate_great_circle_distance(pred, gt, 'Haversine', R) (core/utils/spherical.py:20-53): [B,2,H,W] x2 -> [B,H,W]. */
+int pf_great_circle(const float *pred, const float *gt, float *out, int batch, int H, int W, float radius, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Measurement aids (bench.py): no reference counterpart.

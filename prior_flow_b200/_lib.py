@@ -46,6 +46,12 @@ class DcclConvArgs(C.Structure):
                 ("prepared_weight", _fp), ("bias", _fp), ("out", _fp)]
 
 
+class VolumeBwdArgs(C.Structure):
+    _fields_ = [("batch", C.c_int), ("channels", C.c_int), ("h", C.c_int), ("w", C.c_int),
+                ("fmap1", _fp), ("fmap2", _fp), ("dvolume", _fp), ("dfmap1", _fp), ("dfmap2", _fp),
+                ("workspace", _fp), ("workspace_bytes", C.c_longlong)]
+
+
 class OnTheFlyArgs(C.Structure):
     _fields_ = [("batch", C.c_int), ("channels", C.c_int), ("h", C.c_int), ("w", C.c_int),
                 ("radius", C.c_int), ("num_levels", C.c_int), ("cyclic", C.c_int), ("div_mode", C.c_int),
@@ -90,6 +96,12 @@ SIGNATURES = {
     "pf_dccl_conv_weight_bytes": (C.c_longlong, []),
     "pf_dccl_conv_prepare": (C.c_int, [_fp, C.c_int, C.c_int, _fp, _fp]),
     "pf_dccl_conv": (C.c_int, [C.POINTER(DcclConvArgs), _fp]),
+    "pf_volume_bwd_workspace_bytes": (C.c_longlong, [C.c_int] * 4),
+    "pf_volume_bwd": (C.c_int, [C.POINTER(VolumeBwdArgs), _fp]),
+    "pf_convex_upsample": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    "pf_uniform_loss_fwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_float, C.c_int, C.c_int, C.c_int, _fp]),
+    "pf_uniform_loss_bwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_float, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    "pf_great_circle": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, _fp]),
     "pf_probe_gather": (C.c_int, [_fp, C.c_longlong, C.c_int, C.c_int, _fp, _fp, _fp]),
     "pf_probe_stream_read": (C.c_int, [_fp, C.c_longlong, _fp, _fp]),
 }

@@ -232,6 +232,9 @@ class DualUpdateBlock(_UpdateBase):      # BasicMultiUpdateBlock ("ODDC"), core/
 def convex_upsample(flow: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """core/prior_raft.py:58-67 — [B,2,h,w] -> [B,2,8h,8w] as a convex combination of the 3x3 neighbourhood."""
     B, _, h, w = flow.shape
+    if flow.is_cuda and flow.dtype == torch.float32 and mask.dtype == torch.float32 and not (
+            torch.is_grad_enabled() and (flow.requires_grad or mask.requires_grad)):
+        return ops.convex_upsample(flow, mask)       # one launch (SURVEY §8 f2); the eager chain below carries the gradients
     mask = torch.softmax(mask.view(B, 1, 9, 8, 8, h, w), dim=2)
     nb = F.unfold(8 * flow, [3, 3], padding=1).view(B, 2, 9, 1, 1, h, w)
     up = torch.sum(mask * nb, dim=2).permute(0, 1, 4, 2, 5, 3)
@@ -265,6 +268,10 @@ class PriOrRAFT(nn.Module):
         for m in (self.cnet, self.ODDC, self.update_block):
             m.to(memory_format=torch.channels_last)
         return self
+
+    def graphed(self, iters: int = 12) -> "GraphedForward":
+        """CUDA-graph replay of `self(image1, image2, iters, test_mode=True)`."""
+        return GraphedForward(self, iters)
 
     def freeze_bn(self):
         for m in self.modules():
@@ -357,3 +364,53 @@ class PriOrRAFT(nn.Module):
         if test_mode:
             return up_A
         return preds_A, preds_B
+
+
+class GraphedForward:
+    """Inference through a CUDA graph: the whole forward — sample-grid lookups, both volume builds, the
+    12-iteration loop with its ~90 launches of ours and ~1100 of cuDNN/ATen — is captured once per input shape and replayed;
+    the Python loop, the allocator and 1200 launch latencies leave the critical path.
+
+        run = model.graphed(iters=12)
+        flow = run(image1, image2)        # [B,2,H,W]; valid until the next call with the same shape (a static buffer)
+
+    Inputs are copied into static buffers (device-to-device, or straight from pinned host memory), so callers may pass fresh
+    tensors every time.  Weights are baked in by address: after `load_state_dict` / an optimizer step that REPLACES parameter
+    tensors call `reset()`; in-place updates are picked up automatically."""
+
+    def __init__(self, model: "PriOrRAFT", iters: int = 12, warmup: int = 2):
+        self.model, self.iters, self.warmup = model, iters, warmup
+        self._graphs = {}
+
+    def reset(self) -> None:
+        self._graphs.clear()
+
+    def _capture(self, image1: torch.Tensor, image2: torch.Tensor):
+        dev = next(self.model.parameters()).device
+        s1 = torch.empty(image1.shape, device=dev, dtype=torch.float32)
+        s2 = torch.empty(image2.shape, device=dev, dtype=torch.float32)
+        s1.copy_(image1), s2.copy_(image2)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(self.warmup):           # cuDNN autotuning, sample-grid cache, prepared conv weights: all before capture
+                self.model(s1, s2, iters=self.iters, test_mode=True)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph), torch.no_grad():
+            out = self.model(s1, s2, iters=self.iters, test_mode=True)
+        return graph, s1, s2, out
+
+    def __call__(self, image1: torch.Tensor, image2: torch.Tensor) -> torch.Tensor:
+        if self.model.training:
+            raise RuntimeError("GraphedForward is an inference path: call model.eval() first")
+        key = (tuple(image1.shape), tuple(image2.shape))
+        entry = self._graphs.get(key)
+        if entry is None:
+            entry = self._graphs[key] = self._capture(image1, image2)
+        graph, s1, s2, out = entry
+        s1.copy_(image1, non_blocking=True)
+        s2.copy_(image2, non_blocking=True)
+        graph.replay()
+        return out

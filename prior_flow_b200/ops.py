@@ -431,6 +431,79 @@ def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence
     return (out_own, out_other) if dual else out_own
 
 
+# ------------------------------------------------------------------------------------------ (f2) / (f4)
+def convex_upsample(flow: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """PriOr_RAFT.upsample_flow (core/prior_raft.py:58-67) in one launch: flow [B,2,h,w], mask [B,576,h,w] (NCHW or
+    torch.channels_last) -> [B,2,8h,8w].  Forward only."""
+    lib = _lib.load()
+    _chk(flow, "flow", 4), _chk(mask, "mask", 4)
+    B, two, h, w = flow.shape
+    if two != 2 or tuple(mask.shape) != (B, 576, h, w):
+        raise ValueError("convex_upsample: flow [B,2,h,w], mask [B,576,h,w]")
+    flow = flow.contiguous()
+    cl = mask.is_contiguous(memory_format=torch.channels_last) and not mask.is_contiguous()
+    if not cl:
+        mask = mask.contiguous()
+    with torch.cuda.device(flow.device):
+        out = torch.empty((B, 2, 8 * h, 8 * w), device=flow.device, dtype=torch.float32)
+        _lib.check(lib.pf_convex_upsample(flow.data_ptr(), mask.data_ptr(), out.data_ptr(), B, h, w, int(cl), _stream()),
+                   "pf_convex_upsample")
+        _count(1)
+    return out
+
+
+class _UniformLossTermFn(torch.autograd.Function):
+    """term_weight * sum(ok * lat[y] * |pred - gt|_1) — one prediction's share of uniform_loss (train_flow.py:66-69)."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, ok, lat, term_weight):
+        lib = _lib.load()
+        pred, gt, ok, lat = pred.contiguous(), gt.contiguous(), ok.contiguous(), lat.contiguous()
+        B, _, H, W = pred.shape
+        with torch.cuda.device(pred.device):
+            acc = torch.zeros(1, device=pred.device, dtype=torch.float32)
+            _lib.check(lib.pf_uniform_loss_fwd(pred.data_ptr(), gt.data_ptr(), ok.data_ptr(), lat.data_ptr(), acc.data_ptr(),
+                                               float(term_weight), B, H, W, _stream()), "pf_uniform_loss_fwd")
+        ctx.save_for_backward(pred, gt, ok, lat)
+        ctx.term_weight = float(term_weight)
+        return acc.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        pred, gt, ok, lat = ctx.saved_tensors
+        B, _, H, W = pred.shape
+        g = g.contiguous().float().view(1)
+        with torch.cuda.device(pred.device):
+            dpred = torch.empty_like(pred)
+            _lib.check(lib.pf_uniform_loss_bwd(pred.data_ptr(), gt.data_ptr(), ok.data_ptr(), lat.data_ptr(), g.data_ptr(),
+                                               ctx.term_weight, dpred.data_ptr(), B, H, W, _stream()), "pf_uniform_loss_bwd")
+        return dpred, None, None, None, None
+
+
+def uniform_loss_term(pred: torch.Tensor, gt: torch.Tensor, ok: torch.Tensor, lat: torch.Tensor, term_weight: float) -> torch.Tensor:
+    """pred, gt [B,2,H,W]; ok [B,H,W] 0/1 floats; lat [H] normalised cos-latitude weights -> scalar tensor (differentiable in pred)."""
+    _chk(pred, "pred", 4), _chk(gt, "gt", 4), _chk(ok, "ok", 3), _chk(lat, "lat", 1)
+    if pred.shape != gt.shape or pred.shape[1] != 2 or tuple(ok.shape) != (pred.shape[0],) + tuple(pred.shape[2:]) or lat.numel() != pred.shape[2]:
+        raise ValueError("uniform_loss_term: shape mismatch")
+    return _UniformLossTermFn.apply(pred, gt, ok, lat, term_weight)
+
+
+def great_circle_distance(pred: torch.Tensor, gt: torch.Tensor, radius: float = 1.0) -> torch.Tensor:
+    """calculate_great_circle_distance(pred, gt, 'Haversine', R) (core/utils/spherical.py:20-53) -> [B,H,W]."""
+    lib = _lib.load()
+    _chk(pred, "pred", 4), _chk(gt, "gt", 4)
+    if pred.shape != gt.shape or pred.shape[1] != 2:
+        raise ValueError("great_circle_distance: [B,2,H,W] flows of equal shape")
+    pred, gt = pred.contiguous(), gt.contiguous()
+    B, _, H, W = pred.shape
+    with torch.cuda.device(pred.device):
+        out = torch.empty((B, H, W), device=pred.device, dtype=torch.float32)
+        _lib.check(lib.pf_great_circle(pred.data_ptr(), gt.data_ptr(), out.data_ptr(), B, H, W, float(radius), _stream()), "pf_great_circle")
+        _count(1)
+    return out
+
+
 # ------------------------------------------------------------------------------------------ measurement aids
 def probe_gather(vol: torch.Tensor, pos_xy: torch.Tensor) -> None:
     """Issues the loads of an own-view lookup of `vol` [planes,H,W] at integer footprint corners pos_xy [planes,2] (int32) and
@@ -584,16 +657,37 @@ class _VolumePyramidFn(torch.autograd.Function):
         return d1, d2, None, None, None
 
 
-def volume_backward(fmap1, fmap2, g0, need1=True, need2=True):
+def volume_backward_shape_ok(channels: int, h: int, w: int) -> bool:
+    return channels == 256 and (h * w) % 128 == 0
+
+
+def volume_backward(fmap1, fmap2, g0, need1=True, need2=True, use_library: bool = False):
     """Adjoints of the volume GEMM (autograd of core/prior_raft.py:73-75): dF1[c,n] = sum_m dV[n,m] F2[c,m] / sqrt(C),
-    dF2[c,m] = sum_n dV[n,m] F1[c,n] / sqrt(C).  g0: [B, N, N]."""
+    dF2[c,m] = sum_n dV[n,m] F1[c,n] / sqrt(C).  g0: [B, N, N].  One tcgen05 launch for both (pf_volume_bwd: bf16 hi/lo
+    split, three products); shapes it does not tile (C != 256 or h*w % 128 != 0) and use_library=True run two library GEMMs."""
     B, Cn, h, w = fmap1.shape
     N = h * w
-    scale = 1.0 / (Cn ** 0.5)
-    f1 = fmap1.reshape(B, Cn, N)
-    f2 = fmap2.reshape(B, Cn, N)
-    d1 = torch.matmul(f2, g0.transpose(1, 2)).mul_(scale).view_as(fmap1) if need1 else None
-    d2 = torch.matmul(f1, g0).mul_(scale).view_as(fmap2) if need2 else None
+    if not (need1 or need2):
+        return None, None
+    if use_library or not volume_backward_shape_ok(Cn, h, w):
+        scale = 1.0 / (Cn ** 0.5)
+        f1 = fmap1.reshape(B, Cn, N)
+        f2 = fmap2.reshape(B, Cn, N)
+        d1 = torch.matmul(f2, g0.transpose(1, 2)).mul_(scale).view_as(fmap1) if need1 else None
+        d2 = torch.matmul(f1, g0).mul_(scale).view_as(fmap2) if need2 else None
+        return d1, d2
+    lib = _lib.load()
+    fmap1, fmap2, g0 = fmap1.contiguous(), fmap2.contiguous(), g0.contiguous()
+    with torch.cuda.device(fmap1.device):
+        d1 = torch.empty_like(fmap1) if need1 else None
+        d2 = torch.empty_like(fmap2) if need2 else None
+        ws_bytes = lib.pf_volume_bwd_workspace_bytes(B, Cn, h, w)
+        ws = torch.empty((ws_bytes + 1024,), device=fmap1.device, dtype=torch.uint8)
+        ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+        a = _lib.VolumeBwdArgs(B, Cn, h, w, fmap1.data_ptr(), fmap2.data_ptr(), g0.data_ptr(),
+                               d1.data_ptr() if need1 else None, d2.data_ptr() if need2 else None, ws_ptr, ws_bytes)
+        _lib.check(lib.pf_volume_bwd(C.byref(a), _stream()), "pf_volume_bwd")
+        ws.record_stream(torch.cuda.current_stream())
     return d1, d2
 
 

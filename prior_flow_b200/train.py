@@ -15,6 +15,7 @@ from typing import Dict, List, Sequence, Tuple
 import torch
 
 from . import geometry as geo
+from . import ops
 from .distributed import Context, ddp_loss_scale
 
 MAX_FLOW = 400.0
@@ -34,8 +35,13 @@ def sequence_loss(preds: Sequence[torch.Tensor], flow_gt: torch.Tensor, valid: t
     ok = ((valid >= 0.5) & (mag < MAX_FLOW)).float()
     loss = flow_gt.new_zeros(())
     n = len(preds)
+    fused = flow_gt.is_cuda and all(p.dtype == torch.float32 for p in preds)
+    lat = weights.reshape(weights.shape[-2], -1)[:, 0].contiguous() if fused else None    # [H]: the weights are constant along a row
     for i, p in enumerate(preds):
-        loss = loss + gamma ** (n - i - 1) * torch.sum(ok * weights * torch.sum((p - flow_gt).abs(), dim=1))
+        if fused:      # one launch per term (and one in backward) instead of sub / abs / sum / mul / mul / sum
+            loss = loss + ops.uniform_loss_term(p, flow_gt, ok, lat, gamma ** (n - i - 1))
+        else:
+            loss = loss + gamma ** (n - i - 1) * torch.sum(ok * weights * torch.sum((p - flow_gt).abs(), dim=1))
     epe = torch.sum((preds[-1].detach() - flow_gt) ** 2, dim=1).sqrt()[ok > 0]
     return loss, {"epe": float(epe.mean()) if epe.numel() else float("nan")}
 
@@ -66,3 +72,8 @@ def train_step(model: torch.nn.Module, optimizer: torch.optim.Optimizer, batch, 
     else:
         optimizer.step()
     return {"loss": float(loss.detach()) / ddp_loss_scale(ctx), "epe_A": met_A["epe"], "epe_B": met_B["epe"]}
+
+
+def spherical_epe(flow_pred: torch.Tensor, flow_gt: torch.Tensor, radius: float = 1.0) -> torch.Tensor:
+    """SEPE map of evaluate.py:354 — great-circle distance between predicted and true ERP endpoints (core/utils/spherical.py:20-53)."""
+    return ops.great_circle_distance(flow_pred.float(), flow_gt.float(), radius)

@@ -145,6 +145,19 @@ def main():
         return lambda: TO.dccl_lookup(c_, pa_, pb_, gw_, gc_, 4)
     rec("lookup_dual", lambda: ops.lookup(coords, pa, pb, gw, gc, 4), look_bytes, None,
         lambda: TO.dccl_lookup(coords, pa, pb, gw.expand(B, -1, -1, -1), gc.expand(B, -1, -1, -1), 4), cpu_lookup)
+    conv = torch.nn.Conv2d(324, 256, 1).cuda()
+    def unfused(tf32):
+        def f():
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.no_grad():
+                return torch.relu(conv(ops.lookup(coords, pa, pb, gw, gc, 4, fuse_sum=True, channels_last=True)))
+        return f
+    conv = conv.to(memory_format=torch.channels_last)
+    rec("lookup_fused_sum(cl) + cuDNN conv1x1 + relu [fp32]", unfused(False), look_bytes)
+    rec("lookup_fused_sum(cl) + cuDNN conv1x1 + relu [tf32]", unfused(True), look_bytes)
+    rec("lookup_conv[fp32, cl] (pf_dccl_conv)", lambda: ops.lookup_conv(coords, pa, pb, gw, gc, conv.weight, conv.bias, channels_last=True, fp32=True), look_bytes)
+    rec("lookup_conv[tf32-class, cl] (pf_dccl_conv)", lambda: ops.lookup_conv(coords, pa, pb, gw, gc, conv.weight, conv.bias, channels_last=True, fp32=False), look_bytes)
+    rec("lookup_fused_sum(cl)", lambda: ops.lookup(coords, pa, pb, gw, gc, 4, fuse_sum=True, channels_last=True), look_bytes)
     rec("lookup_single", lambda: ops.lookup(coords, pa, radius=4, cyclic=True), look_bytes // 2)
     flow = coords - TO.coords_grid(B, h, w, "cuda")
     rec("flo_rotate", lambda: ops.flo_rotate(flow, gw, gc), 4 * B * 2 * N * 4, None,

@@ -28,6 +28,9 @@ def main():
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--iters", type=int, default=12)
     ap.add_argument("--memory-format", default="nchw", choices=["nchw", "channels_last"])
+    ap.add_argument("--ddp", default="ddp", choices=["ddp", "static", "nobroadcast", "none"],
+                    help="ddp: DistributedDataParallel defaults; static: static_graph=True; nobroadcast: broadcast_buffers=False (BN is frozen); "
+                         "none: independent replicas, no gradient all-reduce (isolates host contention from DDP's cost)")
     a = ap.parse_args()
     ctx = pfd.init_from_env("nccl")
     torch.backends.cudnn.benchmark = True
@@ -37,7 +40,11 @@ def main():
         model = model.to_channels_last()
     model.train()
     model.freeze_bn()
-    ddp = pfd.wrap_ddp(model, ctx)
+    if a.ddp == "none" or ctx.world == 1:
+        ddp = model
+    else:
+        ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[ctx.local_rank], gradient_as_bucket_view=True,
+                                                        static_graph=a.ddp == "static", broadcast_buffers=a.ddp == "ddp")
     opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4, weight_decay=1e-5, eps=1e-8)
     g = torch.Generator(device=ctx.device).manual_seed(100 + ctx.rank)
     B, H, W = a.batch, a.height, a.width
@@ -62,7 +69,7 @@ def main():
     if ctx.rank == 0:
         print(json.dumps({"what": "train step (config 5)", "n_gpus": ctx.world, "global_batch": B * ctx.world, "ms_per_step": round(ms, 2),
                           "pairs_per_s": round(B * ctx.world / ms * 1e3, 2), "losses": [round(x, 4) for x in losses],
-                          "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2), "shape": [H, W], "iters": a.iters}), flush=True)
+                          "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2), "shape": [H, W], "iters": a.iters, "ddp": a.ddp if ctx.world > 1 else "n/a", "memory_format": a.memory_format}), flush=True)
     if ctx.world > 1:
         torch.distributed.destroy_process_group()
 
