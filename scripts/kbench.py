@@ -172,6 +172,16 @@ def main():
     rec("samplegrid_fullres", lambda: ops.samplegrid((1, 3, 8 * h, 8 * w), Ra), 2 * 64 * N * 4, None,
         lambda: TO.generate_samplegrid((1, 3, 8 * h, 8 * w), Ra),
         lambda: (lambda r_=Ra.cpu(): TO.generate_samplegrid((1, 3, 8 * h, 8 * w), r_)))
+    dV = torch.randn(B, N, N, device="cuda", generator=g)
+    bwd_flops = 2 * 2.0 * B * N * N * C
+    rec("volume_backward[tcgen05 bf16x2, both gradients]", lambda: ops.volume_backward(fm[0], fm[1], dV), 2 * B * N * N * 4 + 4 * B * C * N * 4, bwd_flops)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rec("volume_backward[cuBLAS fp32, two GEMMs]", lambda: ops.volume_backward(fm[0], fm[1], dV, use_library=True), 2 * B * N * N * 4 + 4 * B * C * N * 4, bwd_flops)
+    del dV
+    mask = torch.randn(B, 576, h, w, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    from prior_flow_b200 import model as M
+    rec("convex_upsample[kernel, channels_last mask]", lambda: ops.convex_upsample(flow, mask), B * (576 + 2 + 128) * N * 4, None,
+        lambda: torch.sum(torch.softmax(mask.view(B, 1, 9, 8, 8, h, w), dim=2) * torch.nn.functional.unfold(8 * flow, [3, 3], padding=1).view(B, 2, 9, 1, 1, h, w), dim=2))
     cl = lambda t: t.permute(0, 2, 3, 1).contiguous()
     f1a, f2a, f1b, f2b = cl(fm[0]), ops.channels_last_pyramid(fm[1], 4), cl(fm[2]), ops.channels_last_pyramid(fm[3], 4)
     rec("lookup_onthefly", lambda: ops.lookup_onthefly(coords, f1a, f2a, f1b, f2b, gw, gc, 4))

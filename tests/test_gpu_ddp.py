@@ -26,9 +26,15 @@ def test_two_gpu_ddp_step_equals_one_gpu_step_with_the_same_global_batch(tmp_pat
     assert r.returncode == 0, r.stderr[-3000:]
     a, b = torch.load(two), torch.load(one)
     assert abs(a["loss"] - b["loss"]) <= 1e-4 * abs(b["loss"])
-    worst = 0.0
+    # per parameter: max |difference| over max |reference|, with a floor of 1e-4 x the largest gradient of the whole model —
+    # conv biases in front of an InstanceNorm have an analytically ZERO gradient, what is left of them is rounding noise
+    gmax = max(float(g.abs().max()) for g in b["grads"].values())
+    worst, worst_name = 0.0, ""
     for k, gb in b["grads"].items():
         ga = a["grads"][k]
-        worst = max(worst, float((ga - gb).abs().max() / (gb.abs().max() + 1e-20)))
-    print(f"\n[ddp] summed loss {a['loss']:.6f} vs {b['loss']:.6f}; worst relative gradient difference {worst:.2e}")
+        e = float((ga - gb).abs().max()) / max(float(gb.abs().max()), 1e-4 * gmax)
+        if e > worst:
+            worst, worst_name = e, k
+    print(f"\n[ddp] summed loss {a['loss']:.6f} vs {b['loss']:.6f}; worst relative gradient difference {worst:.2e} ({worst_name})")
+    assert set(a["grads"]) == set(b["grads"])
     assert worst < 5e-3
