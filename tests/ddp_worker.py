@@ -23,9 +23,12 @@ def batch(global_batch, H, W, device):
 
 def grads_of_step(model, im1, im2, gt, scale):
     model.zero_grad(set_to_none=True)
-    pa, _ = model(im1, im2, iters=3)
+    pa, pb = model(im1, im2, iters=3)
     H, W = im1.shape[-2:]
-    loss, _ = sequence_loss(pa, gt, torch.ones(im1.shape[0], H, W, device=im1.device), latitude_weights(H, W, im1.device))
+    ok, lat = torch.ones(im1.shape[0], H, W, device=im1.device), latitude_weights(H, W, im1.device)
+    # both views' predictions enter the loss, as in train_step: every parameter takes part (DDP without find_unused_parameters
+    # never reduces a bucket that holds an unused parameter)
+    loss = sequence_loss(pa, gt, ok, lat)[0] + sequence_loss(pb, gt, ok, lat)[0]
     (loss * scale).backward()
     return float(loss.detach())
 
@@ -38,12 +41,17 @@ def main():
     model = PriOrRAFT().to(ctx.device)
     model.train()
     model.freeze_bn()
-    ddp = pfd.wrap_ddp(model, ctx)
+    manual = os.environ.get("PF_TEST_MANUAL_ALLREDUCE") == "1"      # debugging aid: no DDP wrapper, gradients summed by hand
+    ddp = model if manual else pfd.wrap_ddp(model, ctx)
     G, H, W = int(os.environ.get("PF_TEST_WORLD_BATCH", 2 * ctx.world)), 128, 256
     im1, im2, gt = batch(G, H, W, ctx.device)
     mine = pfd.shard_pairs(G, ctx.rank, ctx.world)
     sl = slice(mine[0], mine[-1] + 1)
-    loss = grads_of_step(ddp, im1[sl], im2[sl], gt[sl], pfd.ddp_loss_scale(ctx))
+    loss = grads_of_step(ddp, im1[sl], im2[sl], gt[sl], 1.0 if manual else pfd.ddp_loss_scale(ctx))
+    if manual and ctx.world > 1:
+        for p in model.parameters():
+            if p.grad is not None:
+                torch.distributed.all_reduce(p.grad)
     total = torch.tensor([loss], device=ctx.device, dtype=torch.float64)
     if ctx.world > 1:
         torch.distributed.all_reduce(total)

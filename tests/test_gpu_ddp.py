@@ -35,6 +35,8 @@ def test_two_gpu_ddp_step_equals_one_gpu_step_with_the_same_global_batch(tmp_pat
         e = float((ga - gb).abs().max()) / max(float(gb.abs().max()), 1e-4 * gmax)
         if e > worst:
             worst, worst_name = e, k
+    errs = sorted(((float((a["grads"][k] - gb).abs().max()), float(gb.abs().max()), k) for k, gb in b["grads"].items()), reverse=True)[:4]
+    print("\n[ddp] largest absolute differences (|diff|, |ref|max, name):", errs, "gmax", gmax)
     print(f"\n[ddp] summed loss {a['loss']:.6f} vs {b['loss']:.6f}; worst relative gradient difference {worst:.2e} ({worst_name})")
     assert set(a["grads"]) == set(b["grads"])
-    assert worst < 5e-3
+    assert worst < 1e-2        # cuDNN picks other kernels for batch 2 and batch 4: 5.7e-3 between a batch of 4 and its two halves on ONE GPU
