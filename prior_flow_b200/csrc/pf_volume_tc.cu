@@ -46,11 +46,15 @@ constexpr int kTcThreads = 320;         // TMA warp, MMA warp, 2 x 4 epilogue wa
 constexpr int kAccCols = BN;            // fp32 accumulator columns per stage
 constexpr uint32_t kTmemCols = 512;
 
+// Shared memory (r03, A-stationary): the CTA's 128 query rows stay resident for all k (hi [+ lo] planes), the patch
+// operand streams through a ring of 32 KiB units (one k-block of one plane), level 0 leaves through two 16 KiB staging buffers.
 template <bool kSplit>
 struct Cfg {
-  static constexpr int kStages = kSplit ? 2 : 4;
-  static constexpr int kStageBytes = kSplit ? 2 * (A_PLANE + B_PLANE) : (A_PLANE + B_PLANE);
-  static constexpr int kSmemBytes = kStages * kStageBytes + kOutStages * OUT_STAGE + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kPlanes = kSplit ? 2 : 1;
+  static constexpr int kKBlocksMax = 4;                                    // C <= 256
+  static constexpr int kAResBytes = kKBlocksMax * kPlanes * A_PLANE;       // 128 KiB (split) / 64 KiB
+  static constexpr int kRing = kSplit ? 2 : 4;                             // B units in flight
+  static constexpr int kSmemBytes = kAResBytes + kRing * B_PLANE + kOutStages * OUT_STAGE + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, M = 128, N = 256.
@@ -140,33 +144,42 @@ struct TcParams {
 };
 
 // kCluster = 2: CTA pairs (thread-block cluster 2x1x1) work on two M-tiles of the SAME target patch in lockstep; each
-// CTA fetches half of the B (patch) tile and TMA-multicasts it to both, so the L2 -> SM operand traffic per tile drops
-// from A + B to A + B/2 (ncu r01a: that traffic, not the tensor pipe or HBM, bounded the 1-CTA kernel).  A stage is
-// recycled only when BOTH CTAs' MMAs have retired it (commit multicast to both empty barriers, count 2).
+// CTA fetches half of the B (patch) unit and TMA-multicasts it to both.
+// r03 — A-STATIONARY.  ncu r03e of the r02 kernel: 805 MB of TMA operand traffic L2 -> SM per view at 6.7 TB/s for 357 MB of
+// output: every tile re-fetched its A tile (128 rows x C) and its patch, and that traffic — not the tensor pipe (44 %) or HBM
+// (2.5 TB/s of writes) — set the 119 us.  Now a cluster owns a CONTIGUOUS range of (M-pair, patch) work items in M-major
+// order: the CTA's 128 query rows are loaded once per M-pair (128 KiB, all k, both planes) and stay in shared memory while
+// the patches stream past in 32 KiB units (one k-block of one plane: B.hi serves lo_a*hi_b and hi_a*hi_b, B.lo serves
+// hi_a*lo_b), so the operand traffic per tile drops from A + B/2 to B/2.
 template <bool kSplit, int kCluster>
 __global__ void __launch_bounds__(kTcThreads, 1)
 volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                  const __grid_constant__ CUtensorMap map_out, const TcParams p) {
   using C_ = Cfg<kSplit>;
-  constexpr int kStages = C_::kStages;
+  constexpr int kRing = C_::kRing, kPlanes = C_::kPlanes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t *out_stage = smem + kStages * C_::kStageBytes;
+  uint8_t *a_res = smem;                                   // [kb][plane] x 16 KiB
+  uint8_t *b_ring = smem + C_::kAResBytes;                 // kRing x 32 KiB
+  uint8_t *out_stage = b_ring + kRing * B_PLANE;
   uint64_t *bars = reinterpret_cast<uint64_t *>(out_stage + kOutStages * OUT_STAGE);
-  // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base address
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kStages);
-  const uint32_t bar_tfull = smem_u32(bars + 2 * kStages), bar_tempty = smem_u32(bars + 2 * kStages + 2);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+  // bars: b_full[kRing], b_empty[kRing], a_full, a_empty, tmem_full[2], tmem_empty[2]; then the TMEM base address
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kRing);
+  const uint32_t bar_afull = smem_u32(bars + 2 * kRing), bar_aempty = smem_u32(bars + 2 * kRing + 1);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * kRing + 2), bar_tempty = smem_u32(bars + 2 * kRing + 4);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kRing + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = p.C / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kRing; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, kCluster);
     }
+    mbar_init(bar_afull, 1);
+    mbar_init(bar_aempty, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, 4);
@@ -191,47 +204,53 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0;
-  // work items: kCluster consecutive M-tiles of one patch per cluster, so the peers share the B tile
-  const long long first_item = blockIdx.x / kCluster, item_stride = gridDim.x / kCluster;
+  // work items: (M-group, patch) with M-group = kCluster consecutive M-tiles; item t = mgroup_global * P + patch, M-major.
+  // A cluster owns the contiguous range [t_begin, t_end): at most two M-groups for the usual shapes.
+  const int P = p.patches_x * p.patches_y;
   const long long total_items = p.total_tiles / kCluster;
-  const int tiles_m_items = p.tiles_m / kCluster;
+  const long long n_clusters = gridDim.x / kCluster, cluster_id = blockIdx.x / kCluster;
+  const long long t_begin = total_items * cluster_id / n_clusters, t_end = total_items * (cluster_id + 1) / n_clusters;
   constexpr uint16_t kMask = (1u << kCluster) - 1;
 
   if (warp == 0) {
     // ================================================================= TMA producer (one thread)
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long item = first_item; item < total_items; item += item_stride) {
-        const int per_b = tiles_m_items * p.patches_x * p.patches_y;
-        const int b = (int)(item / per_b);
-        int r = (int)(item - (long long)b * per_b);
-        const int mt = (r / (p.patches_x * p.patches_y)) * kCluster + (int)cta_rank;
-        r %= p.patches_x * p.patches_y;
-        const int py = r / p.patches_x, px = r - py * p.patches_x;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          const uint32_t full = bar_full + 8 * stage;
-          mbar_arrive_expect_tx(full, (uint32_t)C_::kStageBytes);
-          const uint32_t sbase = smem_u32(smem + stage * C_::kStageBytes);
-          const int row = b * p.N + mt * BM;
-          tma_load_2d(sbase, &map_a_hi, full, kb * BK, row);
-          if (kSplit) tma_load_2d(sbase + A_PLANE + B_PLANE, &map_a_lo, full, kb * BK, row);
-          if (kCluster == 1) {
-            tma_load_4d(sbase + A_PLANE, &map_b_hi, full, kb * BK, px * PATCH_W, py * PATCH_H, b);
-            if (kSplit) tma_load_4d(sbase + 2 * A_PLANE + B_PLANE, &map_b_lo, full, kb * BK, px * PATCH_W, py * PATCH_H, b);
-          } else {
-            // my half of the patch rows (box height PATCH_H / kCluster), delivered to both CTAs
-            constexpr int kHalfRows = PATCH_H / kCluster, kHalfBytes = B_PLANE / kCluster;
-            const int y = py * PATCH_H + (int)cta_rank * kHalfRows;
-            tma_load_4d_mc(sbase + A_PLANE + cta_rank * kHalfBytes, &map_b_hi, full, kb * BK, px * PATCH_W, y, b, kMask);
-            if (kSplit)
-              tma_load_4d_mc(sbase + 2 * A_PLANE + B_PLANE + cta_rank * kHalfBytes, &map_b_lo, full, kb * BK, px * PATCH_W, y, b,
-                             kMask);
+      int unit = 0;
+      long long cur_group = -1;
+      uint32_t a_loads = 0;
+      for (long long t = t_begin; t < t_end; ++t) {
+        const long long group = t / P;
+        const int patch = (int)(t - group * P);
+        const int py = patch / p.patches_x, px = patch - py * p.patches_x;
+        const int b = (int)(group / (p.tiles_m / kCluster));
+        if (group != cur_group) {
+          // my 128 query rows of this M-group, all k, both planes: resident until the group changes
+          mbar_wait(bar_aempty, (a_loads & 1) ^ 1);              // the MMAs that read the previous rows have retired
+          mbar_arrive_expect_tx(bar_afull, (uint32_t)(kblocks * kPlanes * A_PLANE));
+          const int row = (int)(group * kCluster + cta_rank) * BM;   // == b * N + mt * BM
+          for (int kb = 0; kb < kblocks; ++kb) {
+            tma_load_2d(smem_u32(a_res + (kb * kPlanes) * A_PLANE), &map_a_hi, bar_afull, kb * BK, row);
+            if (kSplit) tma_load_2d(smem_u32(a_res + (kb * kPlanes + 1) * A_PLANE), &map_a_lo, bar_afull, kb * BK, row);
           }
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
+          cur_group = group;
+          ++a_loads;
+        }
+        for (int kb = 0; kb < kblocks; ++kb) {
+#pragma unroll
+          for (int plane = 0; plane < kPlanes; ++plane, ++unit) {
+            const int s = unit % kRing;
+            mbar_wait(bar_empty + 8 * s, ((uint32_t)(unit / kRing) & 1) ^ 1);
+            const uint32_t full = bar_full + 8 * s;
+            mbar_arrive_expect_tx(full, (uint32_t)B_PLANE);
+            const uint32_t dst = smem_u32(b_ring + s * B_PLANE);
+            const CUtensorMap *mb = plane ? &map_b_lo : &map_b_hi;
+            if (kCluster == 1) {
+              tma_load_4d(dst, mb, full, kb * BK, px * PATCH_W, py * PATCH_H, b);
+            } else {
+              // my half of the patch rows (box height PATCH_H / kCluster), delivered to both CTAs
+              constexpr int kHalfRows = PATCH_H / kCluster, kHalfBytes = B_PLANE / kCluster;
+              tma_load_4d_mc(dst + cta_rank * kHalfBytes, mb, full, kb * BK, px * PATCH_W, py * PATCH_H + (int)cta_rank * kHalfRows, b, kMask);
+            }
           }
         }
       }
@@ -239,44 +258,53 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   } else if (warp == 1) {
     // ================================================================= MMA issuer (one thread)
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0, acc = 0, acc_phase = 0;
-      for (long long item = first_item; item < total_items; item += item_stride) {
+      int unit = 0;
+      long long cur_group = -1;
+      uint32_t a_loads = 0, acc = 0, acc_phase = 0;
+      for (long long t = t_begin; t < t_end; ++t) {
+        const long long group = t / P;
+        if (group != cur_group) {
+          mbar_wait(bar_afull, a_loads & 1);
+          cur_group = group;
+          ++a_loads;
+        }
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccCols;
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
-          const uint32_t sbase = smem_u32(smem + stage * C_::kStageBytes);
-          const uint64_t a_hi = make_smem_desc(sbase), b_hi = make_smem_desc(sbase + A_PLANE);
-          const uint64_t a_lo = make_smem_desc(sbase + A_PLANE + B_PLANE);
-          const uint64_t b_lo = make_smem_desc(sbase + 2 * A_PLANE + B_PLANE);
-          if (kSplit) {
-            // small cross terms first, then the leading product
+          const uint64_t a_hi = make_smem_desc(smem_u32(a_res + (kb * kPlanes) * A_PLANE));
+          const uint64_t a_lo = make_smem_desc(smem_u32(a_res + (kb * kPlanes + 1) * A_PLANE));
+          {   // unit B.hi[kb]: the small cross term first, then the leading product
+            const int s = unit % kRing;
+            mbar_wait(bar_full + 8 * s, (uint32_t)(unit / kRing) & 1);
+            tc_fence_after();
+            const uint64_t b_hi = make_smem_desc(smem_u32(b_ring + s * B_PLANE));
+            if (kSplit) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
+              for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, kIdesc, 1u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
+            }
+            // frees the unit when these MMAs retire — in both CTAs, since the peer multicasts into my smem too
+            if (kCluster > 1) umma_commit_mc(bar_empty + 8 * s, kMask); else umma_commit(bar_empty + 8 * s);
+            ++unit;
+          }
+          if (kSplit) {   // unit B.lo[kb]
+            const int s = unit % kRing;
+            mbar_wait(bar_full + 8 * s, (uint32_t)(unit / kRing) & 1);
+            tc_fence_after();
+            const uint64_t b_lo = make_smem_desc(smem_u32(b_ring + s * B_PLANE));
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, kIdesc, 1u);
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, kIdesc, 1u);
-          } else {
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
-          }
-          // frees the smem stage when these MMAs retire — in both CTAs, since the peer multicasts into my smem too
-          if (kCluster > 1)
-            umma_commit_mc(bar_empty + 8 * stage, kMask);
-          else
-            umma_commit(bar_empty + 8 * stage);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
+            if (kCluster > 1) umma_commit_mc(bar_empty + 8 * s, kMask); else umma_commit(bar_empty + 8 * s);
+            ++unit;
           }
         }
         umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
+        if (t + 1 < t_end && (t + 1) / P != group) umma_commit(bar_aempty);   // last tile of the group: the rows may be replaced
         if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
     }
@@ -295,13 +323,13 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     uint32_t acc_phase = 0;
     uint8_t *stage_buf = out_stage + group * OUT_STAGE;
     const int w1 = p.w >> 1, h1 = p.h >> 1, w2 = p.w >> 2, h2 = p.h >> 2, w3 = p.w >> 3, h3 = p.h >> 3;
-    for (long long item = first_item + group * item_stride; item < total_items; item += 2 * item_stride) {
-      const int per_b = tiles_m_items * p.patches_x * p.patches_y;
-      const int b = (int)(item / per_b);
-      int r = (int)(item - (long long)b * per_b);
-      const int mt = (r / (p.patches_x * p.patches_y)) * kCluster + (int)cta_rank;
-      r %= p.patches_x * p.patches_y;
-      const int py = r / p.patches_x, px = r - py * p.patches_x;
+    for (long long t = t_begin + group; t < t_end; t += 2) {
+      const long long mgroup = t / P;
+      const int patch = (int)(t - mgroup * P);
+      const int py = patch / p.patches_x, px = patch - py * p.patches_x;
+      const int groups_per_b = p.tiles_m / kCluster;
+      const int b = (int)(mgroup / groups_per_b);
+      const int mt = (int)(mgroup - (long long)b * groups_per_b) * kCluster + (int)cta_rank;
       const long long qrow = (long long)b * p.N + mt * BM + row;  // global query index (plane index)
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
