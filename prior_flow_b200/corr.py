@@ -26,6 +26,18 @@ from . import ops
 AUTO_MATERIALIZE_FRACTION = 0.4     # of the currently free device memory, for the two pyramids + split workspace
 
 
+def available_device_memory(device) -> int:
+    """Bytes a new allocation can use: what the driver reports free PLUS what PyTorch's caching allocator holds but has not
+    handed out (reserved - allocated).  `mem_get_info` alone shrinks as a long-running process caches freed blocks, which would
+    silently push `mode="auto"` onto the slower volume-free path."""
+    free = torch.cuda.mem_get_info(device)[0]
+    try:
+        free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    except Exception:  # noqa: BLE001 - a mocked / uninitialised device
+        pass
+    return int(free)
+
+
 class CostVolume:
     """Lazy all-pairs volume: what `PriOr_RAFT.corr` returns (core/prior_raft.py:69-75)."""
 
@@ -89,16 +101,18 @@ class DCCL:
             B, C, h, w = fmap.shape
             n = h * w
             need = 2 * (B * n * n * 4 * sum(0.25 ** l for l in range(self.num_levels)) + 4 * B * n * C * 2)   # both views
-            free = torch.cuda.mem_get_info(fmap.device)[0] if fmap.is_cuda else 0
-            self._auto[key] = need > AUTO_MATERIALIZE_FRACTION * free
+            self._auto[key] = need > AUTO_MATERIALIZE_FRACTION * available_device_memory(fmap.device) if fmap.is_cuda else True
         return self._auto[key]
 
     def build_pyramid(self, cost_volume_8):
         if isinstance(cost_volume_8, CostVolume):
             f1, f2 = cost_volume_8.fmap1, cost_volume_8.fmap2
-            if self._use_onthefly(f1):
-                if torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad):
-                    raise NotImplementedError("the on-the-fly lookup is inference-only; use mode='materialized' to train")
+            needs_grad = torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad)
+            if needs_grad and self.mode == "onthefly":
+                raise NotImplementedError("the on-the-fly lookup is inference-only (no volume-free backward yet); "
+                                          "train with mode='materialized' or 'auto'")
+            # mode="auto" under autograd always materialises: the backward kernels need the pyramid layout
+            if not needs_grad and self._use_onthefly(f1):
                 return FeaturePyramid(f1, f2, self.num_levels)
             sink = ops.GradSink() if (self.accumulate_grads and torch.is_grad_enabled()
                                       and (f1.requires_grad or f2.requires_grad)) else None

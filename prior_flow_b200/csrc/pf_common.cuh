@@ -50,6 +50,33 @@ __device__ __forceinline__ float4 ld_f4(const float4 *p) {
   return v;
 }
 
+// L2 eviction policies for the pyramid reads of the lookup (createpolicy + ld.global.nc.L2::cache_hint).  The small levels
+// of a pyramid (levels 2-3: 20 MB per view at 512x1024) are re-read by every one of the 24 lookup calls of a forward, the
+// large ones (levels 0-1: 320 MB) stream through once per call: evict_last for the former keeps them L2-resident across
+// calls even though ~0.5 GB of other traffic passes through the 126 MB L2 in between, evict_first for the latter keeps the
+// stream from displacing them.
+enum L2Policy { kL2Normal = 0, kL2First = 1, kL2Last = 2 };
+__device__ __forceinline__ uint64_t make_l2_policy(int kind) {
+  uint64_t pol;
+  if (kind == kL2Last)
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else if (kind == kL2First)
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float ld_hint(const float *p, uint64_t pol) {            // read-only data, L1 allocate
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ld_hint_stream(const float *p, uint64_t pol) {     // read exactly once by this kernel: no L1 allocate
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 // torch.remainder(x, m) for m > 0: fmod, then + m when the result is negative (may return m itself
 // for tiny negative x — SURVEY.md §A.2).  The three fast paths are exact restatements of
 // fmodf + fix-up for |x| < 2m (fmod is exact; x - m is exact by Sterbenz for m <= x < 2m) and

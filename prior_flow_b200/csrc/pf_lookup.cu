@@ -36,6 +36,7 @@ struct LookupParams {
   int B, N, h, w;  // query grid, N = h*w
   int radius, L, cyclic, div_mode, dual, channels_last, fuse_sum;
   int w_pow2, w2_pow2;                 // the rotation grid's width / the pyramid's level-0 width is a power of two
+  int l2_hint;                         // lookup_rows_kernel: per-level L2 eviction policies on the plane reads (pf_common.cuh)
   const float *coords;
   const float *own[PF_MAX_LEVELS];
   const float *other[PF_MAX_LEVELS];
@@ -402,6 +403,8 @@ __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const in
   const float *cxp = opaque(p.coords + (long long)b * 2 * p.N);
   float *dbg = BRANCH ? p.dbg_other : p.dbg_own;
   float *tcol = tile + a * kRowsK * kRowsPitch;   // + b * pitch + query
+  // planes of the small levels are re-read by the next lookup call, planes of the large ones are not (see pf_common.cuh)
+  const uint64_t pol = make_l2_policy(p.l2_hint ? (lvl >= 2 ? kL2Last : kL2First) : (BRANCH ? kL2Normal : kL2First));
 
   // the coordinates of the warp's next triple are fetched one iteration ahead (the chain below starts with them)
   float ncx, ncy;
@@ -455,7 +458,7 @@ __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const in
         const int yo[10] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w, yc.x, yc.y};
         float v[10], vr[10];
 #pragma unroll
-        for (int r = 0; r < 10; ++r) v[r] = kOwnStream ? __ldcs(plc + yo[r]) : __ldg(plc + yo[r]);
+        for (int r = 0; r < 10; ++r) v[r] = ld_hint_stream(plc + yo[r], pol);
 #pragma unroll
         for (int r = 0; r < 10; ++r) vr[r] = __shfl_down_sync(0xffffffffu, v[r], 1);
 #pragma unroll
@@ -586,7 +589,7 @@ __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const in
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
                 const float *s0 = pl + (act ? y0[j] * Wl + x0[j] : 0);
-                t00[j] = __ldg(s0), t01[j] = __ldg(s0 + 1), t10[j] = __ldg(s0 + Wl), t11[j] = __ldg(s0 + Wl + 1);
+                t00[j] = ld_hint(s0, pol), t01[j] = ld_hint(s0 + 1, pol), t10[j] = ld_hint(s0 + Wl, pol), t11[j] = ld_hint(s0 + Wl + 1, pol);
               }
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
@@ -602,8 +605,8 @@ __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const in
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
                 gxe[j] = make_axis_entry(ix[j], Wl, 1), gye[j] = make_axis_entry(iy[j], Hl, Wl);
-                t00[j] = __ldg(pl + gye[j].o0 + gxe[j].o0), t01[j] = __ldg(pl + gye[j].o0 + gxe[j].o1);
-                t10[j] = __ldg(pl + gye[j].o1 + gxe[j].o0), t11[j] = __ldg(pl + gye[j].o1 + gxe[j].o1);
+                t00[j] = ld_hint(pl + gye[j].o0 + gxe[j].o0, pol), t01[j] = ld_hint(pl + gye[j].o0 + gxe[j].o1, pol);
+                t10[j] = ld_hint(pl + gye[j].o1 + gxe[j].o0, pol), t11[j] = ld_hint(pl + gye[j].o1 + gxe[j].o1, pol);
               }
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
@@ -896,6 +899,8 @@ static int fill_lookup_params(const pf_lookup_args *a, LookupParams &p, bool dua
   p.dual = dual;
   p.w_pow2 = (a->w & (a->w - 1)) == 0;
   p.w2_pow2 = (a->w2 & (a->w2 - 1)) == 0 && (a->w2 >> (a->num_levels - 1)) >= 1;
+  static const bool l2_hint = getenv("PF_LOOKUP_L2HINT") != nullptr && getenv("PF_LOOKUP_L2HINT")[0] == '1';   // A/B (r03)
+  p.l2_hint = l2_hint;
   p.channels_last = a->out_channels_last;
   p.fuse_sum = a->fuse_sum;
   p.coords = a->coords;

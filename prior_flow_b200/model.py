@@ -254,6 +254,7 @@ class PriOrRAFT(nn.Module):
         # inference: img_rotate + `corr_A + corr_B_A` + the motion encoders' first layer (Conv2d(324, 256, 1) + ReLU) as one
         # tcgen05 kernel behind the gather; the [B,324,h,w] lookup tensor is then never formed
         self.fuse_conv1 = os.environ.get("PF_FUSE_CONV1", "1") != "0"
+        self._auto_corr = {}
         cor_planes = 4 * 9 * 9
         self.fnet = Encoder(256, "instance", dropout)
         self.cnet = Encoder(256, "batch", dropout)
@@ -312,6 +313,7 @@ class PriOrRAFT(nn.Module):
             f1A, f2A, f1B, f2B = (f.float() for f in self.fnet([image1, image2, image1_B, image2_B]))
 
         lookup = DCCL(4, 4, mode=self.corr_mode, volume_mode=self.volume_mode, accumulate_grads=self.accumulate_grads)
+        lookup._auto = self._auto_corr          # the materialise / on-the-fly decision is made once per shape for the model's lifetime
         pyr_A = lookup.build_pyramid(CostVolume(f1A, f2A))
         pyr_B = lookup.build_pyramid(CostVolume(f1B, f2B))
 
