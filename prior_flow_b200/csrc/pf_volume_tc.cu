@@ -41,20 +41,28 @@ constexpr int UMMA_K = 16;
 constexpr int A_PLANE = BM * BK * 2;    // 16 KiB
 constexpr int B_PLANE = BN * BK * 2;    // 32 KiB
 constexpr int OUT_STAGE = BM * 32 * 4;  // 16 KiB: 128 rows x one 32-float patch row
-constexpr int kOutStages = 2;
+constexpr int kOutGroups = 2;          // epilogue groups, one staging buffer (or two, see Cfg::kOutBufs) each
 constexpr int kTcThreads = 320;         // TMA warp, MMA warp, 2 x 4 epilogue warps
 constexpr int kAccCols = BN;            // fp32 accumulator columns per stage
 constexpr uint32_t kTmemCols = 512;
 
-template <bool kSplit>
+// kTwoSm: one tcgen05.mma.cta_group::2 spans the CTA pair (M = 256); a CTA stages its own 128 query rows and only ITS HALF
+// of the patch, so a stage is 64 KiB instead of 96 (three stages fit) and a third less operand data crosses L2 -> SM.
+template <bool kSplit, bool kTwoSm = false>
 struct Cfg {
-  static constexpr int kStages = kSplit ? 2 : 4;
-  static constexpr int kStageBytes = kSplit ? 2 * (A_PLANE + B_PLANE) : (A_PLANE + B_PLANE);
-  static constexpr int kSmemBytes = kStages * kStageBytes + kOutStages * OUT_STAGE + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kBBytes = kTwoSm ? B_PLANE / 2 : B_PLANE;
+  static constexpr int kPlaneBytes = A_PLANE + kBBytes;
+  static constexpr int kStageBytes = (kSplit ? 2 : 1) * kPlaneBytes;
+  // 2-SM: the smaller stages leave room for DOUBLE-BUFFERED level-0 staging (the TMA store of patch row c is still reading
+  // its buffer while row c + 1 is being staged into the other one)
+  static constexpr int kOutBufs = kTwoSm ? 2 : 1;
+  static constexpr int kStages = kTwoSm ? (kSplit ? 2 : 4) : (kSplit ? 2 : 4);
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutGroups * kOutBufs * OUT_STAGE + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, M = 128, N = 256.
 constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kIdesc2Sm = umma_idesc_f16(2 * BM, BN);   // cta_group::2: M = 256 across the pair
 
 // Power-of-two scale that maps absmax into [2^13, 2^14): hi = fp16(x*s) cannot overflow.
 __device__ __forceinline__ float split_scale(uint32_t amax_bits) {
@@ -133,6 +141,7 @@ struct TcParams {
   int B, C, N, h, w;
   int num_levels;
   int tiles_m, patches_x, patches_y;  // per batch
+  int contiguous;                     // work-item assignment (see the kernel)
   long long total_tiles;
   float inv_sqrt_c;
   const uint32_t *amax_bits;  // [2]: fmap1, fmap2
@@ -143,17 +152,19 @@ struct TcParams {
 // CTA fetches half of the B (patch) tile and TMA-multicasts it to both, so the L2 -> SM operand traffic per tile drops
 // from A + B to A + B/2 (ncu r01a: that traffic, not the tensor pipe or HBM, bounded the 1-CTA kernel).  A stage is
 // recycled only when BOTH CTAs' MMAs have retired it (commit multicast to both empty barriers, count 2).
-template <bool kSplit, int kCluster>
+template <bool kSplit, int kCluster, bool kTwoSm = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                  const __grid_constant__ CUtensorMap map_out, const TcParams p) {
-  using C_ = Cfg<kSplit>;
+  static_assert(!kTwoSm || kCluster == 2, "cta_group::2 needs the CTA pair");
+  using C_ = Cfg<kSplit, kTwoSm>;
   constexpr int kStages = C_::kStages;
+  constexpr int kPlaneBytes = C_::kPlaneBytes;   // [A 16 KiB | B (half)] of one plane; the lo plane follows the hi plane
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *out_stage = smem + kStages * C_::kStageBytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(out_stage + kOutStages * OUT_STAGE);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(out_stage + kOutGroups * C_::kOutBufs * OUT_STAGE);
   // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base address
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kStages);
   const uint32_t bar_tfull = smem_u32(bars + 2 * kStages), bar_tempty = smem_u32(bars + 2 * kStages + 2);
@@ -165,19 +176,22 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, kCluster);
+      mbar_init(bar_empty + 8 * s, kTwoSm ? 1 : kCluster);   // 2-SM: ONE multicast commit arrives per CTA
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);
+      mbar_init(bar_tempty + 8 * a, kTwoSm ? 4 * kCluster : 4);   // 2-SM: both CTAs' epilogue warps release the leader's MMA thread
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kTwoSm) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   if (kCluster > 1)
@@ -192,8 +206,15 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0;
   // work items: kCluster consecutive M-tiles of one patch per cluster, so the peers share the B tile
-  const long long first_item = blockIdx.x / kCluster, item_stride = gridDim.x / kCluster;
+  // Work items (kCluster M-tiles x one patch) in M-major, patch-minor order.  PF_VOLUME_ORDER (p.contiguous): a cluster takes a
+  // CONTIGUOUS range of them, so its consecutive tiles are neighbouring patches of the same query planes and every plane row
+  // (512 B = four patches) is completed within a few tiles — DRAM sees runs instead of isolated 128-byte lines; otherwise the
+  // r02 round-robin assignment.
   const long long total_items = p.total_tiles / kCluster;
+  const long long n_clusters = gridDim.x / kCluster, cluster_id = blockIdx.x / kCluster;
+  const long long first_item = p.contiguous ? total_items * cluster_id / n_clusters : cluster_id;
+  const long long end_item = p.contiguous ? total_items * (cluster_id + 1) / n_clusters : total_items;
+  const long long item_stride = p.contiguous ? 1 : n_clusters;
   const int tiles_m_items = p.tiles_m / kCluster;
   constexpr uint16_t kMask = (1u << kCluster) - 1;
 
@@ -202,7 +223,7 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long item = first_item; item < total_items; item += item_stride) {
+      for (long long item = first_item; item < end_item; item += item_stride) {
         const int per_b = tiles_m_items * p.patches_x * p.patches_y;
         const int b = (int)(item / per_b);
         int r = (int)(item - (long long)b * per_b);
@@ -212,22 +233,35 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t full = bar_full + 8 * stage;
-          mbar_arrive_expect_tx(full, (uint32_t)C_::kStageBytes);
           const uint32_t sbase = smem_u32(smem + stage * C_::kStageBytes);
           const int row = b * p.N + mt * BM;
-          tma_load_2d(sbase, &map_a_hi, full, kb * BK, row);
-          if (kSplit) tma_load_2d(sbase + A_PLANE + B_PLANE, &map_a_lo, full, kb * BK, row);
-          if (kCluster == 1) {
-            tma_load_4d(sbase + A_PLANE, &map_b_hi, full, kb * BK, px * PATCH_W, py * PATCH_H, b);
-            if (kSplit) tma_load_4d(sbase + 2 * A_PLANE + B_PLANE, &map_b_lo, full, kb * BK, px * PATCH_W, py * PATCH_H, b);
-          } else {
-            // my half of the patch rows (box height PATCH_H / kCluster), delivered to both CTAs
-            constexpr int kHalfRows = PATCH_H / kCluster, kHalfBytes = B_PLANE / kCluster;
+          if (kTwoSm) {
+            // both CTAs' loads complete on the LEADER's barrier: it expects the pair's bytes
+            if (cta_rank == 0) mbar_arrive_expect_tx(full, 2u * (uint32_t)C_::kStageBytes);
+            constexpr int kHalfRows = PATCH_H / 2;
             const int y = py * PATCH_H + (int)cta_rank * kHalfRows;
-            tma_load_4d_mc(sbase + A_PLANE + cta_rank * kHalfBytes, &map_b_hi, full, kb * BK, px * PATCH_W, y, b, kMask);
-            if (kSplit)
-              tma_load_4d_mc(sbase + 2 * A_PLANE + B_PLANE + cta_rank * kHalfBytes, &map_b_lo, full, kb * BK, px * PATCH_W, y, b,
-                             kMask);
+            tma_load_2d_2sm(sbase, &map_a_hi, full, kb * BK, row);
+            tma_load_4d_2sm(sbase + A_PLANE, &map_b_hi, full, kb * BK, px * PATCH_W, y, b);
+            if (kSplit) {
+              tma_load_2d_2sm(sbase + kPlaneBytes, &map_a_lo, full, kb * BK, row);
+              tma_load_4d_2sm(sbase + kPlaneBytes + A_PLANE, &map_b_lo, full, kb * BK, px * PATCH_W, y, b);
+            }
+          } else {
+            mbar_arrive_expect_tx(full, (uint32_t)C_::kStageBytes);
+            tma_load_2d(sbase, &map_a_hi, full, kb * BK, row);
+            if (kSplit) tma_load_2d(sbase + A_PLANE + B_PLANE, &map_a_lo, full, kb * BK, row);
+            if (kCluster == 1) {
+              tma_load_4d(sbase + A_PLANE, &map_b_hi, full, kb * BK, px * PATCH_W, py * PATCH_H, b);
+              if (kSplit) tma_load_4d(sbase + 2 * A_PLANE + B_PLANE, &map_b_lo, full, kb * BK, px * PATCH_W, py * PATCH_H, b);
+            } else {
+              // my half of the patch rows (box height PATCH_H / kCluster), delivered to both CTAs
+              constexpr int kHalfRows = PATCH_H / kCluster, kHalfBytes = B_PLANE / kCluster;
+              const int y = py * PATCH_H + (int)cta_rank * kHalfRows;
+              tma_load_4d_mc(sbase + A_PLANE + cta_rank * kHalfBytes, &map_b_hi, full, kb * BK, px * PATCH_W, y, b, kMask);
+              if (kSplit)
+                tma_load_4d_mc(sbase + 2 * A_PLANE + B_PLANE + cta_rank * kHalfBytes, &map_b_lo, full, kb * BK, px * PATCH_W, y, b,
+                               kMask);
+            }
           }
           if (++stage == kStages) {
             stage = 0;
@@ -238,10 +272,10 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer (one thread)
-    if (lane == 0) {
+    if (lane == 0 && (!kTwoSm || cta_rank == 0)) {     // 2-SM: only the leader CTA issues; its MMAs write both CTAs' TMEM
       int stage = 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0;
-      for (long long item = first_item; item < total_items; item += item_stride) {
+      for (long long item = first_item; item < end_item; item += item_stride) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccCols;
@@ -249,25 +283,30 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sbase = smem_u32(smem + stage * C_::kStageBytes);
+          // stage layout: multicast path [A.hi | B.hi | A.lo | B.lo] with whole patches; 2-SM path the same with HALF patches
           const uint64_t a_hi = make_smem_desc(sbase), b_hi = make_smem_desc(sbase + A_PLANE);
-          const uint64_t a_lo = make_smem_desc(sbase + A_PLANE + B_PLANE);
-          const uint64_t b_lo = make_smem_desc(sbase + 2 * A_PLANE + B_PLANE);
+          const uint64_t a_lo = make_smem_desc(sbase + kPlaneBytes);
+          const uint64_t b_lo = make_smem_desc(sbase + kPlaneBytes + A_PLANE);
+          auto mma = [&](uint64_t da, uint64_t db, uint32_t accum) {
+            if (kTwoSm) umma_f16_2sm(tmem_d, da, db, kIdesc2Sm, accum); else umma_f16(tmem_d, da, db, kIdesc, accum);
+          };
           if (kSplit) {
             // small cross terms first, then the leading product
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) mma(a_lo + 2 * k, b_hi + 2 * k, (kb | k) ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, kIdesc, 1u);
+            for (int k = 0; k < BK / UMMA_K; ++k) mma(a_hi + 2 * k, b_lo + 2 * k, 1u);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, kIdesc, 1u);
+            for (int k = 0; k < BK / UMMA_K; ++k) mma(a_hi + 2 * k, b_hi + 2 * k, 1u);
           } else {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) mma(a_hi + 2 * k, b_hi + 2 * k, (kb | k) ? 1u : 0u);
           }
-          // frees the smem stage when these MMAs retire — in both CTAs, since the peer multicasts into my smem too
-          if (kCluster > 1)
+          // frees the smem stage when these MMAs retire — in both CTAs (multicast path: the peer multicasts into my smem too;
+          // 2-SM path: the MMA read both CTAs' stages)
+          if (kTwoSm)
+            umma_commit_2sm(bar_empty + 8 * stage, kMask);
+          else if (kCluster > 1)
             umma_commit_mc(bar_empty + 8 * stage, kMask);
           else
             umma_commit(bar_empty + 8 * stage);
@@ -276,7 +315,8 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             phase ^= 1;
           }
         }
-        umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (2-SM: of both CTAs)
+        if (kTwoSm) umma_commit_2sm(bar_tfull + 8 * acc, kMask); else umma_commit(bar_tfull + 8 * acc);
         if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
     }
@@ -293,9 +333,9 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const float scale = p.inv_sqrt_c / (split_scale(p.amax_bits[0]) * split_scale(p.amax_bits[1]));
     const uint32_t acc = (uint32_t)group;
     uint32_t acc_phase = 0;
-    uint8_t *stage_buf = out_stage + group * OUT_STAGE;
+    uint8_t *stage_base = out_stage + group * C_::kOutBufs * OUT_STAGE;
     const int w1 = p.w >> 1, h1 = p.h >> 1, w2 = p.w >> 2, h2 = p.h >> 2, w3 = p.w >> 3, h3 = p.h >> 3;
-    for (long long item = first_item + group * item_stride; item < total_items; item += 2 * item_stride) {
+    for (long long item = first_item + group * item_stride; item < end_item; item += 2 * item_stride) {
       const int per_b = tiles_m_items * p.patches_x * p.patches_y;
       const int b = (int)(item / per_b);
       int r = (int)(item - (long long)b * per_b);
@@ -322,10 +362,15 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         } else {                                  // accumulator fully read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+          if (lane == 0) {
+            if (kTwoSm) mbar_arrive_cluster(bar_tempty + 8 * acc, 0); else mbar_arrive(bar_tempty + 8 * acc);
+          }
         }
         // ---- level 0: one patch row through swizzled staging + TMA store
-        if (leader) tma_store_wait_read0();
+        uint8_t *stage_buf = stage_base + (C_::kOutBufs == 2 ? (c & 1) * OUT_STAGE : 0);
+        if (leader) {
+          if (C_::kOutBufs == 2) tma_store_wait_read1(); else tma_store_wait_read0();   // the store that last used THIS buffer has read it
+        }
         epi_bar_sync(group);
         {
           uint8_t *r0 = stage_buf + row * 128;
@@ -398,7 +443,10 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if (kTwoSm)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -500,6 +548,8 @@ int volume_build_tc(const pf_volume_args *a, cudaStream_t st) {
   p.patches_y = h / PATCH_H;
   p.total_tiles = (long long)B * p.tiles_m * p.patches_x * p.patches_y;
   p.inv_sqrt_c = 1.0f / sqrtf((float)C);
+  static const bool contiguous = getenv("PF_VOLUME_ORDER") != nullptr && getenv("PF_VOLUME_ORDER")[0] == '1';
+  p.contiguous = contiguous;
   p.amax_bits = amax;
   p.lvl1 = a->num_levels > 1 ? a->level[1] : nullptr;
   p.lvl2 = a->num_levels > 2 ? a->level[2] : nullptr;
@@ -527,11 +577,19 @@ int volume_build_tc(const pf_volume_args *a, cudaStream_t st) {
     return cudaLaunchKernelEx(&cfg, kern, m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, p);
   };
   cudaError_t err;
-  if (split)
-    err = cluster == 2 ? launch(volume_tc_kernel<true, 2>, Cfg<true>::kSmemBytes) : launch(volume_tc_kernel<true, 1>, Cfg<true>::kSmemBytes);
-  else
-    err = cluster == 2 ? launch(volume_tc_kernel<false, 2>, Cfg<false>::kSmemBytes)
-                       : launch(volume_tc_kernel<false, 1>, Cfg<false>::kSmemBytes);
+  // PF_VOLUME_2SM=1: one tcgen05.mma.cta_group::2 per CTA pair (each CTA stages only its half of the patch, double-buffered level-0
+  // staging) instead of TMA multicast + two cta_group::1 MMAs.  Parity-green and measured equal (129.0 vs 131.1 us per view, r03):
+  // the kernel is bound by the per-group chain (MMA, then an epilogue paced by HBM writes), not by operand delivery — DESIGN §4.1.
+  static const bool two_sm = getenv("PF_VOLUME_2SM") != nullptr && getenv("PF_VOLUME_2SM")[0] == '1';
+  if (split) {
+    if (cluster == 2 && two_sm) err = launch(volume_tc_kernel<true, 2, true>, Cfg<true, true>::kSmemBytes);
+    else if (cluster == 2) err = launch(volume_tc_kernel<true, 2>, Cfg<true>::kSmemBytes);
+    else err = launch(volume_tc_kernel<true, 1>, Cfg<true>::kSmemBytes);
+  } else {
+    if (cluster == 2 && two_sm) err = launch(volume_tc_kernel<false, 2, true>, Cfg<false, true>::kSmemBytes);
+    else if (cluster == 2) err = launch(volume_tc_kernel<false, 2>, Cfg<false>::kSmemBytes);
+    else err = launch(volume_tc_kernel<false, 1>, Cfg<false>::kSmemBytes);
+  }
   if (err != cudaSuccess) {
     set_error("pf_volume_build(tcgen05): launch failed: %s", cudaGetErrorString(err));
     return 2;
