@@ -57,7 +57,10 @@ struct Cfg {
   // its buffer while row c + 1 is being staged into the other one)
   static constexpr int kOutBufs = kTwoSm ? 2 : 1;
   static constexpr int kStages = kTwoSm ? (kSplit ? 2 : 4) : (kSplit ? 2 : 4);
-  static constexpr int kSmemBytes = kStages * kStageBytes + kOutGroups * kOutBufs * OUT_STAGE + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kUsedBytes = kStages * kStageBytes + kOutGroups * kOutBufs * OUT_STAGE + 256 /*barriers*/ + 2048 /*level-3 exchange*/;
+  // the split mode uses 226.25 KiB of the 227 KiB a CTA may have: the 1 KiB alignment slack does not fit entirely.  The dynamic
+  // window starts 1 KiB aligned when the kernel has no static shared memory (it has none); the kernel traps if it ever does not.
+  static constexpr int kSmemBytes = (kUsedBytes + 1024 <= 232448) ? kUsedBytes + 1024 : 232448;
 };
 
 // kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, M = 128, N = 256.
@@ -152,7 +155,10 @@ struct TcParams {
 // CTA fetches half of the B (patch) tile and TMA-multicasts it to both, so the L2 -> SM operand traffic per tile drops
 // from A + B to A + B/2 (ncu r01a: that traffic, not the tensor pipe or HBM, bounded the 1-CTA kernel).  A stage is
 // recycled only when BOTH CTAs' MMAs have retired it (commit multicast to both empty barriers, count 2).
-template <bool kSplit, int kCluster, bool kTwoSm = false>
+// kShare (r03): BOTH epilogue groups drain the SAME tile (group g takes patch rows 4g .. 4g+3), so the MMA of tile t + 1 runs
+// into the other accumulator while tile t is drained.  With one accumulator per group (r02) a group idles for the whole MMA
+// of its next tile: 6.9 tiles x (3.3 us MMA + 14.5 us epilogue) per group in the fp32 split mode.
+template <bool kSplit, int kCluster, bool kTwoSm = false, bool kShare = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -163,6 +169,7 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   constexpr int kPlaneBytes = C_::kPlaneBytes;   // [A 16 KiB | B (half)] of one plane; the lo plane follows the hi plane
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  if (smem + C_::kUsedBytes > smem_raw + C_::kSmemBytes) __trap();   // see Cfg::kSmemBytes
   uint8_t *out_stage = smem + kStages * C_::kStageBytes;
   uint64_t *bars = reinterpret_cast<uint64_t *>(out_stage + kOutGroups * C_::kOutBufs * OUT_STAGE);
   // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base address
@@ -180,7 +187,7 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, kTwoSm ? 4 * kCluster : 4);   // 2-SM: both CTAs' epilogue warps release the leader's MMA thread
+      mbar_init(bar_tempty + 8 * a, (kTwoSm ? 4 * kCluster : 4) * (kShare ? 2 : 1));   // 2-SM: both CTAs' epilogue warps release the leader's MMA thread
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -331,11 +338,14 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int row = quarter * 32 + lane;   // query row inside the tile
     const bool leader = (threadIdx.x & 127) == 64;   // thread 64 (group 0) / 192 (group 1): first lane of a group's first warp
     const float scale = p.inv_sqrt_c / (split_scale(p.amax_bits[0]) * split_scale(p.amax_bits[1]));
-    const uint32_t acc = (uint32_t)group;
+    uint32_t acc = kShare ? 0u : (uint32_t)group;
     uint32_t acc_phase = 0;
+    // kShare: the level-3 pool spans both groups' rows: group 0 hands its half of the sum, (a + b) of avg_pool2d's
+    // ((a + b) + c + d) / 4, to group 1 through this double-buffered exchange (the tail of the barrier block)
+    float *l3_xchg = reinterpret_cast<float *>(bars) + 64;     // [128 rows][4] floats = 2 KiB behind the barriers
     uint8_t *stage_base = out_stage + group * C_::kOutBufs * OUT_STAGE;
     const int w1 = p.w >> 1, h1 = p.h >> 1, w2 = p.w >> 2, h2 = p.h >> 2, w3 = p.w >> 3, h3 = p.h >> 3;
-    for (long long item = first_item + group * item_stride; item < end_item; item += 2 * item_stride) {
+    for (long long item = first_item + (kShare ? 0 : group) * item_stride; item < end_item; item += (kShare ? 1 : 2) * item_stride) {
       const int per_b = tiles_m_items * p.patches_x * p.patches_y;
       const int b = (int)(item / per_b);
       int r = (int)(item - (long long)b * per_b);
@@ -345,19 +355,22 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const long long qrow = (long long)b * p.N + mt * BM + row;  // global query index (plane index)
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
-      acc_phase ^= 1;
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * kAccCols + ((uint32_t)(quarter * 32) << 16);
+      constexpr int kRows = kShare ? PATCH_H / 2 : PATCH_H;      // patch rows this group drains
+      const int c0 = kShare ? group * kRows : 0;
+      float *xchg = l3_xchg + row * 4;
       uint32_t un[32];
-      tmem_ld32(taddr, un);
+      tmem_ld32(taddr + c0 * 32, un);
       float vp[32], l1_prev[16], l2_prev[8];
 #pragma unroll
-      for (int c = 0; c < PATCH_H; ++c) {
+      for (int cc = 0; cc < kRows; ++cc) {
+        const int c = c0 + cc;
         tmem_ld_wait();
         float vc[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) vc[j] = __uint_as_float(un[j]) * scale;
-        if (c + 1 < PATCH_H) {
+        if (cc + 1 < kRows) {
           tmem_ld32(taddr + (c + 1) * 32, un);   // prefetch the next patch row
         } else {                                  // accumulator fully read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
@@ -407,13 +420,28 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 *reinterpret_cast<float4 *>(d2) = make_float4(l2[0], l2[1], l2[2], l2[3]);
                 *reinterpret_cast<float4 *>(d2 + 4) = make_float4(l2[4], l2[5], l2[6], l2[7]);
                 if (p.num_levels > 3) {
+                  if (kShare) {
+                    if (cp == 1) {      // group 0: rows 0-3 done
+                      *reinterpret_cast<float4 *>(xchg) = make_float4(__fadd_rn(l2[0], l2[1]), __fadd_rn(l2[2], l2[3]),
+                                                                      __fadd_rn(l2[4], l2[5]), __fadd_rn(l2[6], l2[7]));
+                    }
+                    asm volatile("bar.sync 3, 256;" ::: "memory");   // both groups, once per tile: the partial sums are visible
+                  }
                   if (cp == 3) {
                     float l3[4];
+                    if (kShare) {
+                      const float4 top = *reinterpret_cast<const float4 *>(xchg);
+                      l3[0] = __fmul_rn(__fadd_rn(__fadd_rn(top.x, l2[0]), l2[1]), 0.25f);
+                      l3[1] = __fmul_rn(__fadd_rn(__fadd_rn(top.y, l2[2]), l2[3]), 0.25f);
+                      l3[2] = __fmul_rn(__fadd_rn(__fadd_rn(top.z, l2[4]), l2[5]), 0.25f);
+                      l3[3] = __fmul_rn(__fadd_rn(__fadd_rn(top.w, l2[6]), l2[7]), 0.25f);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                      l3[j] = __fmul_rn(
-                          __fadd_rn(__fadd_rn(__fadd_rn(l2_prev[2 * j], l2_prev[2 * j + 1]), l2[2 * j]), l2[2 * j + 1]),
-                          0.25f);
+                      for (int j = 0; j < 4; ++j)
+                        l3[j] = __fmul_rn(
+                            __fadd_rn(__fadd_rn(__fadd_rn(l2_prev[2 * j], l2_prev[2 * j + 1]), l2[2 * j]), l2[2 * j + 1]),
+                            0.25f);
+                    }
                     float *d3 = p.lvl3 + (qrow * h3 + py) * w3 + px * (PATCH_W / 8);
                     *reinterpret_cast<float4 *>(d3) = make_float4(l3[0], l3[1], l3[2], l3[3]);
                   } else {
@@ -431,6 +459,11 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) vp[j] = vc[j];
         }
+      }
+      if (kShare) {
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
+      } else {
+        acc_phase ^= 1;
       }
     }
     if (leader) tma_store_wait_all();
@@ -581,7 +614,12 @@ int volume_build_tc(const pf_volume_args *a, cudaStream_t st) {
   // staging) instead of TMA multicast + two cta_group::1 MMAs.  Parity-green and measured equal (129.0 vs 131.1 us per view, r03):
   // the kernel is bound by the per-group chain (MMA, then an epilogue paced by HBM writes), not by operand delivery — DESIGN §4.1.
   static const bool two_sm = getenv("PF_VOLUME_2SM") != nullptr && getenv("PF_VOLUME_2SM")[0] == '1';
-  if (split) {
+  // PF_VOLUME_SHARE=1: both epilogue groups drain the same tile (MMA of the next tile overlaps) — parity-green, measured equal
+  // to the default (131.1 vs 131.1 us, r03), so the default stays the r02 epilogue (each group drains every other tile)
+  static const bool share = getenv("PF_VOLUME_SHARE") != nullptr && getenv("PF_VOLUME_SHARE")[0] == '1';
+  if (cluster == 2 && !two_sm && share && a->num_levels == 4) {
+    err = split ? launch(volume_tc_kernel<true, 2, false, true>, Cfg<true>::kSmemBytes) : launch(volume_tc_kernel<false, 2, false, true>, Cfg<false>::kSmemBytes);
+  } else if (split) {
     if (cluster == 2 && two_sm) err = launch(volume_tc_kernel<true, 2, true>, Cfg<true, true>::kSmemBytes);
     else if (cluster == 2) err = launch(volume_tc_kernel<true, 2>, Cfg<true>::kSmemBytes);
     else err = launch(volume_tc_kernel<true, 1>, Cfg<true>::kSmemBytes);
