@@ -148,7 +148,7 @@ struct TcParams {
   long long total_tiles;
   float inv_sqrt_c;
   const uint32_t *amax_bits;  // [2]: fmap1, fmap2
-  float *lvl1, *lvl2, *lvl3;
+  float *lvl0, *lvl1, *lvl2, *lvl3;
 };
 
 // kCluster = 2: CTA pairs (thread-block cluster 2x1x1) work on two M-tiles of the SAME target patch in lockstep; each
@@ -158,7 +158,10 @@ struct TcParams {
 // kShare (r03): BOTH epilogue groups drain the SAME tile (group g takes patch rows 4g .. 4g+3), so the MMA of tile t + 1 runs
 // into the other accumulator while tile t is drained.  With one accumulator per group (r02) a group idles for the whole MMA
 // of its next tile: 6.9 tiles x (3.3 us MMA + 14.5 us epilogue) per group in the fp32 split mode.
-template <bool kSplit, int kCluster, bool kTwoSm = false, bool kShare = false>
+// kStg (r03): level 0 leaves the staging buffer with coalesced st.global.v4 (8 lanes per 128-byte line, four full lines per
+// warp instruction) instead of one TMA store of 128 separate 128-byte rows per patch row: scripts/probe/write_probe.cu shows
+// that pattern sustaining 4.1 TB/s, while the TMA-store epilogue topped out at ~3.0 TB/s in every variant of the kernel.
+template <bool kSplit, int kCluster, bool kTwoSm = false, bool kShare = false, bool kStg = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -381,7 +384,7 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         }
         // ---- level 0: one patch row through swizzled staging + TMA store
         uint8_t *stage_buf = stage_base + (C_::kOutBufs == 2 ? (c & 1) * OUT_STAGE : 0);
-        if (leader) {
+        if (!kStg && leader) {
           if (C_::kOutBufs == 2) tma_store_wait_read1(); else tma_store_wait_read0();   // the store that last used THIS buffer has read it
         }
         epi_bar_sync(group);
@@ -391,9 +394,19 @@ volume_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4 *>(r0 + ((j ^ (row & 7)) << 4)) = make_float4(vc[4 * j], vc[4 * j + 1], vc[4 * j + 2], vc[4 * j + 3]);
         }
-        fence_async_smem();
+        if (!kStg) fence_async_smem();
         epi_bar_sync(group);
-        if (leader) {
+        if (kStg) {
+          // 128 rows x 128 B: thread t handles 16-byte chunks t, t + 128, ...: 8 consecutive lanes = one full line
+          const int t = threadIdx.x & 127;
+          float *l0 = p.lvl0 + (((long long)b * p.N + mt * BM) * p.h + (py * PATCH_H + c)) * p.w + px * PATCH_W;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int idx = i * 128 + t, rr = idx >> 3, ch = idx & 7;
+            const float4 v = *reinterpret_cast<const float4 *>(stage_buf + rr * 128 + ((ch ^ (rr & 7)) << 4));
+            *reinterpret_cast<float4 *>(l0 + (long long)rr * p.h * p.w + ch * 4) = v;
+          }
+        } else if (leader) {
           tma_store_3d(&map_out, smem_u32(stage_buf), px * PATCH_W, py * PATCH_H + c, b * p.N + mt * BM);
           tma_store_commit();
         }
@@ -584,6 +597,7 @@ int volume_build_tc(const pf_volume_args *a, cudaStream_t st) {
   static const bool contiguous = getenv("PF_VOLUME_ORDER") != nullptr && getenv("PF_VOLUME_ORDER")[0] == '1';
   p.contiguous = contiguous;
   p.amax_bits = amax;
+  p.lvl0 = a->level[0];
   p.lvl1 = a->num_levels > 1 ? a->level[1] : nullptr;
   p.lvl2 = a->num_levels > 2 ? a->level[2] : nullptr;
   p.lvl3 = a->num_levels > 3 ? a->level[3] : nullptr;
@@ -617,7 +631,11 @@ int volume_build_tc(const pf_volume_args *a, cudaStream_t st) {
   // PF_VOLUME_SHARE=1: both epilogue groups drain the same tile (MMA of the next tile overlaps) — parity-green, measured equal
   // to the default (131.1 vs 131.1 us, r03), so the default stays the r02 epilogue (each group drains every other tile)
   static const bool share = getenv("PF_VOLUME_SHARE") != nullptr && getenv("PF_VOLUME_SHARE")[0] == '1';
-  if (cluster == 2 && !two_sm && share && a->num_levels == 4) {
+  // PF_VOLUME_STG=1: level 0 written with coalesced st.global instead of TMA stores (A/B, r03)
+  static const bool stg = getenv("PF_VOLUME_STG") != nullptr && getenv("PF_VOLUME_STG")[0] == '1';
+  if (cluster == 2 && !two_sm && stg) {
+    err = split ? launch(volume_tc_kernel<true, 2, false, false, true>, Cfg<true>::kSmemBytes) : launch(volume_tc_kernel<false, 2, false, false, true>, Cfg<false>::kSmemBytes);
+  } else if (cluster == 2 && !two_sm && share && a->num_levels == 4) {
     err = split ? launch(volume_tc_kernel<true, 2, false, true>, Cfg<true>::kSmemBytes) : launch(volume_tc_kernel<false, 2, false, true>, Cfg<false>::kSmemBytes);
   } else if (split) {
     if (cluster == 2 && two_sm) err = launch(volume_tc_kernel<true, 2, true>, Cfg<true, true>::kSmemBytes);
