@@ -206,6 +206,10 @@ typedef struct pf_lookup_bwd_args {
   const float *grad_own, *grad_other;     /* [B, L*(2r+1)^2, h, w]                                     */
   float *dgrad_own[PF_MAX_LEVELS];        /* += ; [B*h*w, h2>>l, w2>>l]                                */
   float *dgrad_other[PF_MAX_LEVELS];
+  int query_begin, query_count;           /* query_count > 0: scatter only queries [query_begin, +query_count) of every batch item;  */
+                                          /* the gradient pyramids then hold query_count planes per batch item: [B*query_count, ..]  */
+                                          /* (the chunked, volume-free backward of the on-the-fly lookup)                            */
+  int scratch_ready;                      /* 1: fwd.scratch already holds the img_rotate adjoint of grad_other (an earlier chunk)    */
 } pf_lookup_bwd_args;
 int pf_lookup_dual_bwd(const pf_lookup_bwd_args *args, void *stream);
 
@@ -220,6 +224,11 @@ typedef struct pf_volume_bwd_args {
   float *dfmap1, *dfmap2;              /* [B, C, h, w]; either may be NULL                         */
   void *workspace;                     /* pf_volume_bwd_workspace_bytes() bytes, 1 KiB aligned     */
   long long workspace_bytes;
+  /* chunked use (the volume-free backward of the on-the-fly lookup): dvolume holds only the rows of queries
+   * [query_begin, +query_count) — [B, query_count, h*w]; dfmap1 is written for those queries only, dfmap2 is accumulated.   */
+  int query_begin, query_count;        /* query_count == 0: the whole volume; else multiples of 128 / 64                     */
+  int accumulate_dfmap2;               /* 1: dfmap2 += (every chunk after the first)                                         */
+  int planes_ready;                    /* 1: the workspace already holds the bf16 planes of fmap1 / fmap2 (an earlier chunk) */
 } pf_volume_bwd_args;
 long long pf_volume_bwd_workspace_bytes(int batch, int channels, int h, int w);
 int pf_volume_bwd(const pf_volume_bwd_args *args, void *stream);

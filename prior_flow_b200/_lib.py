@@ -49,7 +49,8 @@ class DcclConvArgs(C.Structure):
 class VolumeBwdArgs(C.Structure):
     _fields_ = [("batch", C.c_int), ("channels", C.c_int), ("h", C.c_int), ("w", C.c_int),
                 ("fmap1", _fp), ("fmap2", _fp), ("dvolume", _fp), ("dfmap1", _fp), ("dfmap2", _fp),
-                ("workspace", _fp), ("workspace_bytes", C.c_longlong)]
+                ("workspace", _fp), ("workspace_bytes", C.c_longlong),
+                ("query_begin", C.c_int), ("query_count", C.c_int), ("accumulate_dfmap2", C.c_int), ("planes_ready", C.c_int)]
 
 
 class OnTheFlyArgs(C.Structure):
@@ -71,7 +72,8 @@ class RemapArgs(C.Structure):
 
 class LookupBwdArgs(C.Structure):
     _fields_ = [("fwd", LookupArgs), ("grad_own", _fp), ("grad_other", _fp),
-                ("dgrad_own", _LevelPtrs), ("dgrad_other", _LevelPtrs)]
+                ("dgrad_own", _LevelPtrs), ("dgrad_other", _LevelPtrs),
+                ("query_begin", C.c_int), ("query_count", C.c_int), ("scratch_ready", C.c_int)]
 
 
 # name -> (restype, argtypes); the single source of truth for tests/test_abi.py as well

@@ -64,12 +64,18 @@ class Pyramid(list):
 
 
 class FeaturePyramid:
-    """On-the-fly operands: channels-last query features and the pooled channels-last target pyramid."""
+    """On-the-fly operands: channels-last query features and the pooled channels-last target pyramid.  Built under autograd
+    (`tape` given) the operands carry the volume-free backward of ops.OnTheFlyTape."""
 
-    def __init__(self, fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int):
-        self.f1 = fmap1.permute(0, 2, 3, 1).contiguous()
-        self.f2 = ops.channels_last_pyramid(fmap2, num_levels)
-        self.num_levels = num_levels
+    def __init__(self, fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int, tape=None):
+        self.num_levels, self.tape, self.view_id = num_levels, tape, None
+        if tape is not None:
+            self.view_id = tape.add_view(fmap1, fmap2)
+            out = ops._FeaturePyramidFn.apply(fmap1, fmap2, num_levels, tape, self.view_id)
+            self.f1, self.f2 = out[0], list(out[1:])
+        else:
+            self.f1 = fmap1.permute(0, 2, 3, 1).contiguous()
+            self.f2 = ops.channels_last_pyramid(fmap2, num_levels)
 
     def __len__(self):
         return self.num_levels
@@ -92,6 +98,7 @@ class DCCL:
         # valid when the pyramids are consumed by lookups alone and backpropagated once, hence opt-in
         self.accumulate_grads = accumulate_grads
         self._auto = {}
+        self._tape = None          # on-the-fly mode under autograd: shared by the pyramids this instance builds
 
     def _use_onthefly(self, fmap: torch.Tensor) -> bool:
         if self.mode != "auto":
@@ -108,11 +115,11 @@ class DCCL:
         if isinstance(cost_volume_8, CostVolume):
             f1, f2 = cost_volume_8.fmap1, cost_volume_8.fmap2
             needs_grad = torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad)
-            if needs_grad and self.mode == "onthefly":
-                raise NotImplementedError("the on-the-fly lookup is inference-only (no volume-free backward yet); "
-                                          "train with mode='materialized' or 'auto'")
-            # mode="auto" under autograd always materialises: the backward kernels need the pyramid layout
-            if not needs_grad and self._use_onthefly(f1):
+            if self._use_onthefly(f1):
+                if needs_grad:      # volume-free backward: the lookups of this DCCL instance record on one tape (ops.OnTheFlyTape)
+                    if self._tape is None:
+                        self._tape = ops.OnTheFlyTape(self.radius, self.num_levels)
+                    return FeaturePyramid(f1, f2, self.num_levels, tape=self._tape)
                 return FeaturePyramid(f1, f2, self.num_levels)
             sink = ops.GradSink() if (self.accumulate_grads and torch.is_grad_enabled()
                                       and (f1.requires_grad or f2.requires_grad)) else None
@@ -131,6 +138,9 @@ class DCCL:
     def __call__(self, coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x):
         coords = coords.float()
         if isinstance(corr_pyramid_A, FeaturePyramid):
+            if corr_pyramid_A.tape is not None and torch.is_grad_enabled():
+                return ops.lookup_onthefly_autograd(coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x,
+                                                    sample_grid_B2A_8x, self.radius)
             return ops.lookup_onthefly(coords, corr_pyramid_A.f1, corr_pyramid_A.f2, corr_pyramid_B.f1, corr_pyramid_B.f2,
                                        sample_grid_A2B_W2C_8x, sample_grid_B2A_8x, self.radius, cyclic=True)
         return ops.lookup_autograd(coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x,

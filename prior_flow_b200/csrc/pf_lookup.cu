@@ -37,6 +37,8 @@ struct LookupParams {
   int radius, L, cyclic, div_mode, dual, channels_last, fuse_sum;
   int w_pow2, w2_pow2;                 // the rotation grid's width / the pyramid's level-0 width is a power of two
   int l2_hint;                         // lookup_rows_kernel: per-level L2 eviction policies on the plane reads (pf_common.cuh)
+  int q_begin, q_end;                  // lookup_kernel (backward): queries [q_begin, q_end) of every batch item; the gradient pyramids
+                                       // then hold (q_end - q_begin) planes per batch item (chunked, volume-free backward)
   const float *coords;
   const float *own[PF_MAX_LEVELS];
   const float *other[PF_MAX_LEVELS];
@@ -90,7 +92,7 @@ __device__ __forceinline__ void lookup_body(const LookupParams &p, const int lvl
   float *dbg_tab = fp + 4 * lookup_fp_floats(k);                     // [2][32]
   float *tile = reinterpret_cast<float *>(smem4) + (kLookupThreads / 32) * lookup_warp_floats(k);  // [K2][33], NCHW own view
   const int b = blockIdx.z;
-  const int n0 = blockIdx.x * kQueriesPerCta;
+  const int n0 = p.q_begin + blockIdx.x * kQueriesPerCta;
   const int Hl = p.Hl[lvl], Wl = p.Wl[lvl];
   const Axis axW = p.axW[lvl], axH = p.axH[lvl];
   const float inv_scale = 1.0f / (float)(1 << lvl);  // `coords / 2**i` is exact either way
@@ -102,7 +104,7 @@ __device__ __forceinline__ void lookup_body(const LookupParams &p, const int lvl
   float *io = p.out_own + ((long long)b * p.L + lvl) * K2 * (long long)p.N + n0;
   if constexpr (kBwd) {  // NCHW own branch: stage the incoming gradient tile [K2][32 queries], coalesced rows
     if (use_tile) {
-      if (n0 + lane < p.N)
+      if (n0 + lane < p.q_end)
         for (int ch = warp; ch < K2; ch += kLookupThreads / 32) tile[ch * 33 + lane] = io[(long long)ch * p.N + lane];
       __syncthreads();
     }
@@ -142,7 +144,9 @@ __device__ __forceinline__ void lookup_body(const LookupParams &p, const int lvl
   const long long nq0 = (long long)b * p.N + n0 + q0;   // first (batch, query) row of this warp
   const float *coord_ptr = opaque(p.coords + ((long long)b * 2 + (is_x ? 0 : 1)) * p.N + n0 + q0);
   const float *plane_it = kBwd ? nullptr : opaque(vol + nq0 * plane_sz);
-  float *dplane_it = kBwd ? opaque((branch ? p.d_other[lvl] : p.d_own[lvl]) + nq0 * plane_sz) : nullptr;
+  // gradient planes are indexed relative to the chunk: plane (b, n) lives at b * (q_end - q_begin) + (n - q_begin)
+  const long long dq0 = (long long)b * (p.q_end - p.q_begin) + (n0 + q0 - p.q_begin);
+  float *dplane_it = kBwd ? opaque((branch ? p.d_other[lvl] : p.d_own[lvl]) + dq0 * plane_sz) : nullptr;
   float *out_it = opaque((branch ? p.raw : p.out_own) + (nq0 * p.L + lvl) * K2);   // channels-last row of this query
   const bool has_dbg = dbg != nullptr;
 
@@ -196,7 +200,7 @@ __device__ __forceinline__ void lookup_body(const LookupParams &p, const int lvl
       }
     }
   };
-  const int nq_w = min(kQueriesPerWarp, p.N - n0 - q0);   // live queries of this warp (may be <= 0)
+  const int nq_w = min(kQueriesPerWarp, p.q_end - n0 - q0);   // live queries of this warp (may be <= 0)
   bool fast_next = false;
   if (nq_w > 0) {
     fast_next = resolve(0, 0);
@@ -324,7 +328,7 @@ __device__ __forceinline__ void lookup_body(const LookupParams &p, const int lvl
   if constexpr (!kBwd) {
     if (use_tile) {
       __syncthreads();
-      if (n0 + lane < p.N)
+      if (n0 + lane < p.q_end)
         for (int ch = warp; ch < K2; ch += kLookupThreads / 32) io[(long long)ch * p.N + lane] = tile[ch * 33 + lane];
     }
   }
@@ -899,6 +903,8 @@ static int fill_lookup_params(const pf_lookup_args *a, LookupParams &p, bool dua
   p.dual = dual;
   p.w_pow2 = (a->w & (a->w - 1)) == 0;
   p.w2_pow2 = (a->w2 & (a->w2 - 1)) == 0 && (a->w2 >> (a->num_levels - 1)) >= 1;
+  p.q_begin = 0;
+  p.q_end = p.N;
   static const bool l2_hint = getenv("PF_LOOKUP_L2HINT") != nullptr && getenv("PF_LOOKUP_L2HINT")[0] == '1';   // A/B (r03)
   p.l2_hint = l2_hint;
   p.channels_last = a->out_channels_last;
@@ -952,7 +958,7 @@ static void fill_rotate_params(const pf_lookup_args *a, RotateParams &rp) {
 template <bool kBwd>
 static int launch_lookup(const LookupParams &p, int radius, bool dual, cudaStream_t st, const char *who) {
   const int k = 2 * radius + 1, K2 = k * k;
-  dim3 grid(ceil_div(p.N, kQueriesPerCta), p.L * (dual ? 2 : 1), p.B);
+  dim3 grid(ceil_div(p.q_end - p.q_begin, kQueriesPerCta), p.L * (dual ? 2 : 1), p.B);
   const size_t smem = ((size_t)(kLookupThreads / 32) * lookup_warp_floats(k) + (size_t)K2 * 33) * sizeof(float);
   const bool recip = p.div_mode == PF_DIV_ATEN_CUDA;
   if (radius == 4) {
@@ -1082,8 +1088,14 @@ extern "C" int pf_lookup_dual_bwd(const pf_lookup_bwd_args *ba, void *stream) {
   }
   p.dbg_own = p.dbg_other = nullptr;
   p.out_own = const_cast<float *>(ba->grad_own);
+  if (ba->query_count > 0) {
+    PF_REQUIRE(ba->query_begin >= 0 && ba->query_begin + ba->query_count <= p.N, "pf_lookup_dual_bwd: query range [%d, +%d) outside 0..%d",
+               ba->query_begin, ba->query_count, p.N);
+    p.q_begin = ba->query_begin;
+    p.q_end = ba->query_begin + ba->query_count;
+  }
   cudaStream_t st = (cudaStream_t)stream;
-  if (dual) {
+  if (dual && !ba->scratch_ready) {
     RotateParams rp;
     fill_rotate_params(a, rp);
     const size_t bytes = (size_t)a->batch * rp.L * rp.K2 * rp.N * sizeof(float);

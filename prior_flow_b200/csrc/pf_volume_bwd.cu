@@ -35,10 +35,12 @@ constexpr int VB_SMEM = VB_ASTAGES * 2 * VB_APLANE + VB_BSTAGES * 2 * VB_BPLANE 
 constexpr uint32_t VB_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(VB_C >> 3) << 17) | ((uint32_t)(VB_M >> 4) << 24);
 
 struct VolBwdParams {
-  int B, N;
+  int B, N;                // N = h*w: pitch of the feature planes and of the outputs
+  int Nq, q_begin;         // dV holds the rows of queries [q_begin, q_begin + Nq) only (Nq == N, q_begin == 0: the whole volume)
+  int accumulate2;         // dF2 += instead of = (chunked backward: one chunk of query rows per call)
   float scale;             // 1 / sqrt(C)
-  const float *dV;         // [B, N, N]
-  float *dF1, *dF2;        // [B, C, N] (either may be null)
+  const float *dV;         // [B, Nq, N]
+  float *dF1, *dF2;        // [B, C, N] (either may be null); dF1 is written for the chunk's queries only
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -75,10 +77,11 @@ volume_bwd_kernel(const __grid_constant__ CUtensorMap map_f1_hi, const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int which = blockIdx.y, b = blockIdx.z;
-  const int row0 = blockIdx.x * VB_M;            // first output position (n for dF1, m for dF2)
-  const int kblocks = p.N / VB_BK;
+  const int row0 = blockIdx.x * VB_M;            // first output position (query of the chunk for dF1, target m for dF2)
+  const int rows = which ? p.N : p.Nq;           // output positions of this gradient
+  const int kblocks = (which ? p.Nq : p.N) / VB_BK;   // contraction length: targets for dF1, the chunk's queries for dF2
   float *out = which ? p.dF2 : p.dF1;
-  if (out == nullptr) return;                    // uniform per CTA: that gradient is not wanted
+  if (out == nullptr || row0 >= rows) return;    // uniform per CTA: that gradient is not wanted / beyond its rows
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < VB_ASTAGES; ++s) {
@@ -111,8 +114,9 @@ volume_bwd_kernel(const __grid_constant__ CUtensorMap map_f1_hi, const __grid_co
         const uint32_t full = bar_bfull + 8 * s;
         mbar_arrive_expect_tx(full, 2u * VB_BPLANE);
         const uint32_t dst = smem_u32(bs + s * 2 * VB_BPLANE);
-        tma_load_2d(dst, mh, full, kb * VB_BK, b * VB_C);
-        tma_load_2d(dst + VB_BPLANE, ml, full, kb * VB_BK, b * VB_C);
+        const int k0 = (which ? p.q_begin : 0) + kb * VB_BK;     // dF2 contracts over the chunk's queries: F1 columns q_begin + ...
+        tma_load_2d(dst, mh, full, k0, b * VB_C);
+        tma_load_2d(dst + VB_BPLANE, ml, full, k0, b * VB_C);
       }
     }
   } else if (warp == VB_CONV_WARPS + 1) {
@@ -140,8 +144,8 @@ volume_bwd_kernel(const __grid_constant__ CUtensorMap map_f1_hi, const __grid_co
   } else {
     // ================================================================= converter warps: fp32 dV tile -> bf16 hi/lo A stage
     const int t = threadIdx.x;                               // 0..511
-    const float *dv = p.dV + (long long)b * p.N * p.N;
-    const long long N = p.N;
+    const float *dv = p.dV + (long long)b * p.Nq * p.N;
+    const long long N = p.N;                                  // row pitch of dV
     // which == 0: tile element (r, k) = dV[row0 + r][k0 + k]: chunk id = t + 512 i -> row id >> 3, chunk id & 7 (4 rows x 256 B per warp)
     // which == 1: tile element (r, k) = dV[k0 + k][row0 + r]: chunk id -> row id & 127, chunk id >> 7 (lanes along m: coalesced)
     int r_[2], c_[2];
@@ -196,7 +200,8 @@ volume_bwd_kernel(const __grid_constant__ CUtensorMap map_f1_hi, const __grid_co
       mbar_wait(bar_acc, 0);
       tc_fence_after();
       const int r = warp * 32 + lane;
-      float *o = out + (long long)b * VB_C * N + row0 + r;      // + c * N: a warp writes 32 consecutive positions of channel c
+      float *o = out + (long long)b * VB_C * N + (which ? 0 : p.q_begin) + row0 + r;      // + c * N: a warp writes 32 consecutive positions of channel c
+      const bool acc2 = which && p.accumulate2;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
       for (int cb = 0; cb < VB_C / 32; ++cb) {
@@ -204,7 +209,11 @@ volume_bwd_kernel(const __grid_constant__ CUtensorMap map_f1_hi, const __grid_co
         tmem_ld32(taddr + cb * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) o[(long long)(cb * 32 + j) * N] = __uint_as_float(v[j]) * p.scale;
+        for (int j = 0; j < 32; ++j) {
+          float *dst = o + (long long)(cb * 32 + j) * N;
+          const float val = __uint_as_float(v[j]) * p.scale;
+          *dst = acc2 ? *dst + val : val;
+        }
       }
     }
   }
@@ -244,6 +253,10 @@ extern "C" int pf_volume_bwd(const pf_volume_bwd_args *a, void *stream) {
   PF_REQUIRE(a->dfmap1 || a->dfmap2, "pf_volume_bwd: nothing to compute");
   const int B = a->batch, C = a->channels, N = a->h * a->w;
   PF_REQUIRE(B > 0 && C == VB_C && N % VB_M == 0, "pf_volume_bwd(tcgen05): built for C = %d and h*w %% %d == 0 (got C = %d, h*w = %d)", VB_C, VB_M, C, N);
+  const int Nq = a->query_count > 0 ? a->query_count : N, q_begin = a->query_count > 0 ? a->query_begin : 0;
+  PF_REQUIRE(Nq % VB_M == 0 && q_begin % VB_BK == 0 && q_begin >= 0 && q_begin + Nq <= N,
+             "pf_volume_bwd: the query chunk must be a multiple of %d rows starting at a multiple of %d inside the map (got [%d, +%d) of %d)", VB_M,
+             VB_BK, q_begin, Nq, N);
   PF_REQUIRE(a->workspace_bytes >= pf_volume_bwd_workspace_bytes(B, C, a->h, a->w) && ((uintptr_t)a->workspace & 1023) == 0,
              "pf_volume_bwd: workspace too small or not 1 KiB aligned");
   PF_REQUIRE((((uintptr_t)a->dvolume | (uintptr_t)a->dfmap1 | (uintptr_t)a->dfmap2) & 15) == 0, "pf_volume_bwd: pointers must be 16-byte aligned");
@@ -253,8 +266,10 @@ extern "C" int pf_volume_bwd(const pf_volume_bwd_args *a, void *stream) {
   uint8_t *ws = reinterpret_cast<uint8_t *>(a->workspace);
   __nv_bfloat16 *f1_hi = reinterpret_cast<__nv_bfloat16 *>(ws), *f1_lo = reinterpret_cast<__nv_bfloat16 *>(ws + plane);
   __nv_bfloat16 *f2_hi = reinterpret_cast<__nv_bfloat16 *>(ws + 2 * plane), *f2_lo = reinterpret_cast<__nv_bfloat16 *>(ws + 3 * plane);
-  split_bf16_kernel<<<dim3(592, 2), 256, 0, st>>>(a->fmap1, a->fmap2, f1_hi, f1_lo, f2_hi, f2_lo, n);
-  if (int e = check_launch("pf_volume_bwd(split)")) return e;
+  if (!a->planes_ready) {   // the bf16 planes of the feature maps: once per backward pass, reused by every chunk
+    split_bf16_kernel<<<dim3(592, 2), 256, 0, st>>>(a->fmap1, a->fmap2, f1_hi, f1_lo, f2_hi, f2_lo, n);
+    if (int e = check_launch("pf_volume_bwd(split)")) return e;
+  }
   CUtensorMap m[4];
   __nv_bfloat16 *planes[4] = {f1_hi, f1_lo, f2_hi, f2_lo};
   for (int i = 0; i < 4; ++i) {
@@ -264,7 +279,7 @@ extern "C" int pf_volume_bwd(const pf_volume_bwd_args *a, void *stream) {
     if (int e = encode(&m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, planes[i], dims, strides, box, "fmap plane")) return e;
   }
   VolBwdParams p;
-  p.B = B, p.N = N, p.scale = 1.0f / sqrtf((float)C);
+  p.B = B, p.N = N, p.Nq = Nq, p.q_begin = q_begin, p.accumulate2 = a->accumulate_dfmap2, p.scale = 1.0f / sqrtf((float)C);
   p.dV = a->dvolume, p.dF1 = a->dfmap1, p.dF2 = a->dfmap2;
   cudaFuncSetAttribute(volume_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_SMEM);   // per device: cheap, every call
   volume_bwd_kernel<<<dim3(N / VB_M, 2, B), VB_THREADS, VB_SMEM, st>>>(m[0], m[1], m[2], m[3], p);

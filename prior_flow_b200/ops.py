@@ -431,6 +431,134 @@ def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence
     return (out_own, out_other) if dual else out_own
 
 
+# ------------------------------------------------------------------------------------------ (c) backward
+class OnTheFlyTape:
+    """Volume-free backward of the on-the-fly lookups of one forward (both views).
+
+    A lookup's backward needs d(loss)/d(volume) only as an intermediate: dF1 = dV F2^T, dF2 = dV^T F1.  The materialised path
+    holds dV for the whole volume; here every lookup's backward just RECORDS (coords, grids, incoming gradients), and when autograd
+    reaches the feature pyramids the tape replays all recorded calls chunk by chunk over the query pixels: scatter the chunk's rows
+    of dV for both views (pf_lookup_dual_bwd with a query range), fold the levels, and contract them away at once (pf_volume_bwd
+    on the chunk).  Memory O(chunk x N) instead of O(N^2); the contraction work is the same single pass as the materialised
+    backward's, however many lookup calls there were."""
+
+    CHUNK_BYTES = 1 << 30      # gradient-volume rows held at a time, both views together
+
+    def __init__(self, radius: int, num_levels: int):
+        self.radius, self.num_levels = radius, num_levels
+        self.views = []            # (fmap1 [B,C,h,w], fmap2 [B,C,h,w])
+        self.calls = []
+        self.result = None
+        self.seeded = False
+
+    def add_view(self, fmap1, fmap2) -> int:
+        self.views.append((fmap1, fmap2))
+        return len(self.views) - 1
+
+    def record(self, own_id, other_id, coords, grid_w2c, grid_c2w, g_own, g_other):
+        self.calls.append((own_id, other_id, coords, grid_w2c, grid_c2w, g_own, g_other))
+
+    def _reset(self):
+        self.calls, self.result, self.seeded = [], None, False
+
+    def run(self):
+        """-> [(dfmap1, dfmap2) per view]; computed once per backward pass, then handed to each view's pyramid node."""
+        if self.result is not None:
+            return self.result
+        f1_0 = self.views[0][0]
+        B, Cn, h, w = f1_0.shape
+        N, L, dev = h * w, self.num_levels, f1_0.device
+        nv = len(self.views)
+        per_row = nv * B * N * 4 * sum(0.25 ** l for l in range(L))
+        Q = int(max(128, min(N, (self.CHUNK_BYTES // per_row) // 128 * 128))) if N % 128 == 0 else N
+        d1 = [torch.zeros_like(v[0]) for v in self.views]
+        d2 = [torch.zeros_like(v[1]) for v in self.views]
+        ws = [volume_backward_workspace(v[0]) if volume_backward_shape_ok(Cn, h, w) else None for v in self.views]
+        K2 = (2 * self.radius + 1) ** 2
+        scratch = torch.empty((B, L * K2, h, w), device=dev, dtype=torch.float32)
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(self._reset)     # the tape is per backward pass
+        except RuntimeError:
+            pass
+        for ci, q0 in enumerate(range(0, N, Q)):
+            Qc = min(Q, N - q0)
+            shapes = [(B * Qc, 1, h >> l, w >> l) for l in range(L)]
+            dV = [[torch.zeros(s_, device=dev, dtype=torch.float32) for s_ in shapes] for _ in range(nv)]
+            for own_id, other_id, coords, gw, gc, g_own, g_other in self.calls:
+                lookup_backward(coords, g_own, g_other, shapes, gw, gc, self.radius, into_own=dV[own_id], into_other=dV[other_id],
+                                query_range=(q0, Qc), scratch=scratch)
+            for v in range(nv):
+                g0 = pyramid_fold_backward(dV[v]).view(B, Qc, N)
+                volume_backward_chunk(self.views[v][0], self.views[v][1], g0, q0, d1[v], d2[v], ws[v], first=ci == 0)
+            del dV
+        self.result = list(zip(d1, d2))
+        return self.result
+
+
+class _FeaturePyramidFn(torch.autograd.Function):
+    """fmaps -> the channels-last operands of the on-the-fly lookup, with the tape's volume-free backward attached."""
+
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, num_levels, tape, view_id):
+        ctx.tape, ctx.view_id, ctx.num_levels = tape, view_id, num_levels
+        f1 = fmap1.permute(0, 2, 3, 1).contiguous()
+        return (f1, *channels_last_pyramid(fmap2, num_levels))
+
+    @staticmethod
+    def backward(ctx, g_f1, *g_f2):
+        d1, d2 = ctx.tape.run()[ctx.view_id]
+        # gradients that reached the operands directly (the first lookup of a pass seeds f1 with zeros so that this node runs)
+        if g_f1 is not None and ctx.tape.views and not _is_seed(g_f1):
+            d1 = d1 + g_f1.permute(0, 3, 1, 2)
+        for l, g in enumerate(g_f2):
+            if g is not None:
+                up = g.permute(0, 3, 1, 2)
+                if l:
+                    up = torch.nn.functional.interpolate(up, scale_factor=2 ** l, mode="nearest") / float(4 ** l)
+                d2 = d2 + up
+        return d1, d2, None, None, None
+
+
+_SEEDS = set()
+
+
+def _is_seed(t: torch.Tensor) -> bool:
+    return t.data_ptr() in _SEEDS
+
+
+class _OnTheFlyLookupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coords, grid_w2c, grid_c2w, radius, tape, own_id, other_id, f1_own, f1_other, *f2):
+        L = len(f2) // 2
+        ctx.save_for_backward(coords, grid_w2c, grid_c2w)
+        ctx.meta = (tape, own_id, other_id, tuple(f1_own.shape))
+        return lookup_onthefly(coords, f1_own, list(f2[:L]), f1_other, list(f2[L:]), grid_w2c, grid_c2w, radius, cyclic=True)
+
+    @staticmethod
+    def backward(ctx, g_own, g_other):
+        coords, gw, gc = ctx.saved_tensors
+        tape, own_id, other_id, f1_shape = ctx.meta
+        if g_own is None:
+            g_own = torch.zeros_like(g_other)
+        if g_other is None:
+            g_other = torch.zeros_like(g_own)
+        tape.record(own_id, other_id, coords, gw, gc, g_own.contiguous(), g_other.contiguous())
+        n_f2 = len(ctx.needs_input_grad) - 9
+        seed = None
+        if not tape.seeded:        # one real (zero) gradient per pass makes sure autograd visits the pyramid nodes of BOTH views
+            tape.seeded = True
+            seed = (torch.zeros(f1_shape, device=coords.device), torch.zeros(f1_shape, device=coords.device))
+            _SEEDS.clear()
+            _SEEDS.update(t.data_ptr() for t in seed)
+        return (None, None, None, None, None, None, None, seed[0] if seed else None, seed[1] if seed else None, *([None] * n_f2))
+
+
+def lookup_onthefly_autograd(coords, pyr_own, pyr_other, grid_w2c, grid_c2w, radius=4):
+    """DCCL lookup straight from the features with gradients to the feature maps (pyr_*: corr.FeaturePyramid built under autograd)."""
+    return _OnTheFlyLookupFn.apply(coords.detach(), grid_w2c.detach(), grid_c2w.detach(), radius, pyr_own.tape, pyr_own.view_id,
+                                   pyr_other.view_id, pyr_own.f1, pyr_other.f1, *pyr_own.f2, *pyr_other.f2)
+
+
 # ------------------------------------------------------------------------------------------ (f2) / (f4)
 def convex_upsample(flow: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """PriOr_RAFT.upsample_flow (core/prior_raft.py:58-67) in one launch: flow [B,2,h,w], mask [B,576,h,w] (NCHW or
@@ -535,9 +663,11 @@ def _grad_layout(g: torch.Tensor, channels_last: bool) -> torch.Tensor:
 
 
 def lookup_backward(coords, grad_own, grad_other, level_shapes, grid_w2c=None, grid_c2w=None, radius=4, cyclic=True,
-                    into_own=None, into_other=None, channels_last=False):
+                    into_own=None, into_other=None, channels_last=False, query_range=None, scratch=None):
     """Adjoint of `lookup` w.r.t. the pyramids.  Returns (d_own levels, d_other levels); with `into_*` given the
-    gradients are accumulated (+=) into those tensors instead of fresh zero tensors."""
+    gradients are accumulated (+=) into those tensors instead of fresh zero tensors.  query_range=(begin, count) scatters only
+    those queries of every batch item into gradient pyramids that hold `count` planes per batch item (`level_shapes` must say so):
+    the chunked, volume-free backward of the on-the-fly lookup."""
     lib = _lib.load()
     coords = _chk(coords, "coords", 4).contiguous()
     B, _, h, w = coords.shape
@@ -567,10 +697,13 @@ def lookup_backward(coords, grad_own, grad_other, level_shapes, grid_w2c=None, g
             if bs_w != bs_c:
                 gw, gc = gw.expand(B, 2, h, w).contiguous(), gc.expand(B, 2, h, w).contiguous()
                 bs_w = gw.stride(0)
-            scratch = torch.empty((B, L * K2, h, w), device=dev, dtype=torch.float32)
+            if scratch is None:
+                scratch = torch.empty((B, L * K2, h, w), device=dev, dtype=torch.float32)
             a.grid_w2c, a.grid_c2w, a.grid_batch_stride, a.scratch = gw.data_ptr(), gc.data_ptr(), bs_w, scratch.data_ptr()
             ba.grad_other = grad_other.data_ptr()
             ba.dgrad_other = _lib.level_ptrs(d_other)
+        if query_range is not None:
+            ba.query_begin, ba.query_count = int(query_range[0]), int(query_range[1])
         _lib.check(lib.pf_lookup_dual_bwd(C.byref(ba), _stream()), "pf_lookup_dual_bwd")
     return d_own, d_other
 
@@ -659,6 +792,41 @@ class _VolumePyramidFn(torch.autograd.Function):
 
 def volume_backward_shape_ok(channels: int, h: int, w: int) -> bool:
     return channels == 256 and (h * w) % 128 == 0
+
+
+def volume_backward_chunk(fmap1, fmap2, g0_chunk, q_begin, d1, d2, workspace, first: bool):
+    """One chunk of query rows of the volume adjoints (pf_volume_bwd with query_begin / query_count): g0_chunk [B, Qc, N] holds
+    the level-0 volume gradient of queries [q_begin, q_begin + Qc); d1 [B,C,h,w] receives those queries' columns, d2 [B,C,h,w] is
+    written by the first chunk and accumulated by the others.  `workspace`: the 1 KiB-aligned uint8 tensor of
+    pf_volume_bwd_workspace_bytes(), shared by all chunks (it keeps the bf16 planes of the feature maps)."""
+    lib = _lib.load()
+    B, Cn, h, w = fmap1.shape
+    N = h * w
+    Qc = g0_chunk.shape[1]
+    if not (volume_backward_shape_ok(Cn, h, w) and Qc % 128 == 0 and q_begin % 64 == 0):
+        scale = 1.0 / (Cn ** 0.5)
+        f1, f2 = fmap1.reshape(B, Cn, N), fmap2.reshape(B, Cn, N)
+        d1.view(B, Cn, N)[:, :, q_begin:q_begin + Qc] = torch.matmul(f2, g0_chunk.transpose(1, 2)) * scale
+        upd = torch.matmul(f1[:, :, q_begin:q_begin + Qc], g0_chunk) * scale
+        if first:
+            d2.view(B, Cn, N).copy_(upd)
+        else:
+            d2.view(B, Cn, N).add_(upd)
+        return
+    g0_chunk = g0_chunk.contiguous()
+    with torch.cuda.device(fmap1.device):
+        a = _lib.VolumeBwdArgs(B, Cn, h, w, fmap1.data_ptr(), fmap2.data_ptr(), g0_chunk.data_ptr(), d1.data_ptr(), d2.data_ptr(),
+                               workspace.data_ptr(), workspace.numel(), int(q_begin), int(Qc), int(not first), int(not first))
+        _lib.check(lib.pf_volume_bwd(C.byref(a), _stream()), "pf_volume_bwd")
+
+
+def volume_backward_workspace(fmap: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    B, Cn, h, w = fmap.shape
+    nbytes = lib.pf_volume_bwd_workspace_bytes(B, Cn, h, w)
+    buf = torch.empty(nbytes + 1024, device=fmap.device, dtype=torch.uint8)
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + nbytes]
 
 
 def volume_backward(fmap1, fmap2, g0, need1=True, need2=True, use_library: bool = False):
