@@ -187,3 +187,41 @@ def test_volume_backward_tcgen05_matches_fp32_gemms(B, h, w):
         assert e1 < 1e-4 and e2 < 1e-4
     only1, none2 = ops.volume_backward(f1, f2, dV, need2=False)
     assert none2 is None and torch.equal(only1, d1)
+
+
+@pytest.mark.parametrize("B,h,w,chunk_bytes", [(1, 16, 32, 1 << 30), (2, 16, 32, 3 << 20), (1, 24, 40, 1 << 30)])
+def test_onthefly_backward_matches_materialised_backward(B, h, w, chunk_bytes):
+    """Volume-free backward of the on-the-fly lookup (ops.OnTheFlyTape: recorded calls replayed chunk by chunk over the queries,
+    pf_lookup_dual_bwd with a query range + pf_volume_bwd on the chunk) against the materialised path's backward
+    (gradient pyramids for the whole volume): same loss, gradients to 1e-4 of max|ref| (bf16x2 contraction, atomics order).
+    The second case forces several chunks (3 MB of gradient rows at a time); the third is a shape pf_volume_bwd does not tile
+    (h*w = 960), which takes the library-GEMM branch of volume_backward_chunk."""
+    from prior_flow_b200 import ops
+    from prior_flow_b200.corr import DCCL, CostVolume
+    fm, coords, gw, gc = make_scene(B, h, w, 71)
+    old = ops.OnTheFlyTape.CHUNK_BYTES
+    ops.OnTheFlyTape.CHUNK_BYTES = chunk_bytes
+
+    def run(mode):
+        f = [t.clone().requires_grad_(True) for t in fm]
+        look = DCCL(4, 4, mode=mode)
+        pa, pb = look.build_pyramid(CostVolume(f[0], f[1])), look.build_pyramid(CostVolume(f[2], f[3]))
+        loss = 0
+        for k in range(3):
+            c = coords + 0.41 * k
+            o1, x1 = look(c, pa, pb, gw, gc)
+            o2, x2 = look(c, pb, pa, gc, gw)
+            loss = loss + (o1 * (k + 1)).square().mean() + x1.abs().mean() + (o2 + x2).square().mean()
+        loss.backward()
+        return float(loss), [t.grad.clone() for t in f]
+
+    try:
+        l_mat, g_mat = run("materialized")
+        l_otf, g_otf = run("onthefly")
+    finally:
+        ops.OnTheFlyTape.CHUNK_BYTES = old
+    assert abs(l_mat - l_otf) <= 1e-5 * abs(l_mat)
+    worst = max(rel(a, b) for a, b in zip(g_otf, g_mat))
+    print(f"\n[on-the-fly backward {B}x{h}x{w}] loss {l_otf:.6f} vs {l_mat:.6f}; worst gradient difference {worst:.2e} of max|ref|")
+    assert all(float(g.abs().max()) > 0 for g in g_otf)
+    assert worst < 1e-4

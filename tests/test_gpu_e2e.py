@@ -143,3 +143,27 @@ def test_train_step_reduces_loss():
     losses = [train_step(model, opt, (im1, im2, gt, valid), ctx, iters=3)["loss"] for _ in range(6)]
     print("train losses", losses)
     assert all(np.isfinite(losses)) and min(losses[1:]) < losses[0], losses
+
+
+def test_training_in_onthefly_mode_matches_materialised(models):
+    """The whole model trained with the volume-free lookup + its volume-free backward (ops.OnTheFlyTape): loss and encoder
+    gradients against the materialised mode on the same weights."""
+    ours, _, im1, im2 = models
+    res = []
+    for mode in ("materialized", "onthefly"):
+        ours.corr_mode = mode
+        ours.train()
+        ours.freeze_bn()
+        ours.zero_grad(set_to_none=True)
+        try:
+            pa, pb = ours(im1, im2, iters=2)
+            loss = sum(p.abs().mean() for p in pa) + sum(p.abs().mean() for p in pb)
+            loss.backward()
+            res.append((float(loss), ours.fnet.conv1.weight.grad.detach().clone(), ours.fnet.conv2.weight.grad.detach().clone()))
+        finally:
+            ours.eval()
+            ours.corr_mode = "auto"
+    (la, g1a, g2a), (lb, g1b, g2b) = res
+    assert abs(la - lb) <= 1e-4 * abs(la)
+    assert float((g1a - g1b).abs().max() / g1a.abs().max()) < 5e-3
+    assert float((g2a - g2b).abs().max() / g2a.abs().max()) < 5e-3
