@@ -54,6 +54,21 @@ struct LookupParams {
   float *d_other[PF_MAX_LEVELS];
 };
 
+// p.X[lvl] with a run-time lvl makes nvcc copy the whole parameter array to local memory (r03a: 56-byte stack frame in
+// lookup_rows_kernel, ~200 prologue instructions per warp).  Four selects on constant-bank operands instead.
+template <typename T>
+__device__ __forceinline__ T pick_level(const T (&a)[PF_MAX_LEVELS], int i) {
+  static_assert(PF_MAX_LEVELS == 4, "pick_level is written for four levels");
+  return i == 0 ? a[0] : (i == 1 ? a[1] : (i == 2 ? a[2] : a[3]));
+}
+__device__ __forceinline__ Axis pick_axis(const Axis (&a)[PF_MAX_LEVELS], int i) {
+  Axis r;
+  r.size = i == 0 ? a[0].size : (i == 1 ? a[1].size : (i == 2 ? a[2].size : a[3].size));
+  r.size_m1 = i == 0 ? a[0].size_m1 : (i == 1 ? a[1].size_m1 : (i == 2 ? a[2].size_m1 : a[3].size_m1));
+  r.inv_m1 = i == 0 ? a[0].inv_m1 : (i == 1 ? a[1].inv_m1 : (i == 2 ? a[2].inv_m1 : a[3].inv_m1));
+  return r;
+}
+
 // Adjoint of blend_zeros: scatter g * w into the four in-bounds corners.
 __device__ __forceinline__ void scatter_zeros(float *__restrict__ plane, int H, int W, const Taps &t, float g) {
   const bool xin0 = (unsigned)t.x0 < (unsigned)W, xin1 = (unsigned)(t.x0 + 1) < (unsigned)W;
@@ -387,8 +402,8 @@ __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const in
   float2 *tyw = reinterpret_cast<float2 *>(tyo1 + 36);   // [3][10] (w0, w1) per window row
   float *tdbg = reinterpret_cast<float *>(tyw + 30);     // [27] y sample coordinate (debug dump)
   const int b = blockIdx.z, n0 = blockIdx.x * kRowsQ;
-  const int Hl = p.Hl[lvl], Wl = p.Wl[lvl];
-  const Axis axW = p.axW[lvl], axH = p.axH[lvl];
+  const int Hl = pick_level(p.Hl, lvl), Wl = pick_level(p.Wl, lvl);
+  const Axis axW = pick_axis(p.axW, lvl), axH = pick_axis(p.axH, lvl);
   const float hW = __fmul_rn(0.5f, axW.size_m1), hH = __fmul_rn(0.5f, axH.size_m1);
   const float inv_scale = 1.0f / (float)(1 << lvl);
   const int l10 = lane / 10;
@@ -401,7 +416,7 @@ __device__ __forceinline__ void lookup_rows_body(const LookupParams &p, const in
   const int size1x = BRANCH ? p.w : Wl, size1y = BRANCH ? p.h : Hl;
   const bool wrap1 = BRANCH || p.cyclic;
   const bool pow2_1 = BRANCH ? p.w_pow2 : p.w2_pow2;
-  const float *vol = opaque(BRANCH ? p.other[lvl] : p.own[lvl]);
+  const float *vol = opaque(BRANCH ? pick_level(p.other, lvl) : pick_level(p.own, lvl));
   const int plane_sz = Hl * Wl;
   const float *gridx = opaque(p.grid_w2c + (long long)b * p.grid_bs);
   const float *cxp = opaque(p.coords + (long long)b * 2 * p.N);
