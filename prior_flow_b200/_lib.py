@@ -62,6 +62,14 @@ class OnTheFlyArgs(C.Structure):
                 ("out_own", _fp), ("out_other", _fp), ("scratch", _fp)]
 
 
+class OnTheFlyTcArgs(C.Structure):
+    _fields_ = [("base", OnTheFlyArgs),
+                ("f1_hi_own", _fp), ("f1_lo_own", _fp), ("f2_hi_own", _LevelPtrs), ("f2_lo_own", _LevelPtrs),
+                ("f1_hi_other", _fp), ("f1_lo_other", _fp), ("f2_hi_other", _LevelPtrs), ("f2_lo_other", _LevelPtrs),
+                ("amax_own", _fp), ("amax_other", _fp),
+                ("mini_own", _LevelPtrs), ("mini_other", _LevelPtrs), ("box_lo", _fp), ("box_hi", _fp)]
+
+
 class RemapArgs(C.Structure):
     _fields_ = [("batch", C.c_int), ("channels", C.c_int), ("H", C.c_int), ("W", C.c_int),
                 ("Ho", C.c_int), ("Wo", C.c_int), ("cyclic", C.c_int), ("div_mode", C.c_int),
@@ -86,6 +94,9 @@ SIGNATURES = {
     "pf_avg_pool2x2": (C.c_int, [_fp, _fp, C.c_longlong, C.c_int, C.c_int, _fp]),
     "pf_lookup_dual": (C.c_int, [C.POINTER(LookupArgs), _fp]),
     "pf_lookup_onthefly": (C.c_int, [C.POINTER(OnTheFlyArgs), _fp]),
+    "pf_lookup_onthefly_tc": (C.c_int, [C.POINTER(OnTheFlyTcArgs), _fp]),
+    "pf_onthefly_absmax": (C.c_int, [_fp, C.c_longlong, _fp, _fp]),
+    "pf_onthefly_split": (C.c_int, [_fp, C.c_longlong, _fp, _fp, _fp, C.c_longlong, _fp]),
     "pf_fmap_pyramid": (C.c_int, [_fp, C.POINTER(_fp), C.c_int, C.c_longlong, C.c_int, C.c_int, _fp]),
     "pf_samplegrid": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, _fp]),
     "pf_remap": (C.c_int, [C.POINTER(RemapArgs), _fp]),

@@ -14,6 +14,7 @@ avg-pool kernel), and `CostVolume.materialize()` gives that tensor to callers th
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -76,6 +77,9 @@ class FeaturePyramid:
         else:
             self.f1 = fmap1.permute(0, 2, 3, 1).contiguous()
             self.f2 = ops.channels_last_pyramid(fmap2, num_levels)
+        # tensor-core operands (fp16 hi/lo planes): PF_ONTHEFLY_TC=0 keeps the CUDA-core kernel of r01
+        self.planes = (ops.OnTheFlyPlanes(self.f1, self.f2)
+                       if os.environ.get("PF_ONTHEFLY_TC", "1") != "0" and ops.OnTheFlyPlanes.supported(self.f1) else None)
 
     def __len__(self):
         return self.num_levels
@@ -142,7 +146,8 @@ class DCCL:
                 return ops.lookup_onthefly_autograd(coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x,
                                                     sample_grid_B2A_8x, self.radius)
             return ops.lookup_onthefly(coords, corr_pyramid_A.f1, corr_pyramid_A.f2, corr_pyramid_B.f1, corr_pyramid_B.f2,
-                                       sample_grid_A2B_W2C_8x, sample_grid_B2A_8x, self.radius, cyclic=True)
+                                       sample_grid_A2B_W2C_8x, sample_grid_B2A_8x, self.radius, cyclic=True,
+                                       planes_own=corr_pyramid_A.planes, planes_other=corr_pyramid_B.planes)
         return ops.lookup_autograd(coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x,
                                    self.radius, cyclic=True, sink_own=getattr(corr_pyramid_A, "grad_sink", None),
                                    sink_other=getattr(corr_pyramid_B, "grad_sink", None))

@@ -1,0 +1,610 @@
+// (c) On-the-fly lookup with the dot products on tensor cores.
+//
+// The r01 kernel (pf_onthefly.cu) evaluates, per query, the correlation "plane" on the bounding box of its window with one
+// warp per target pixel — every query re-reads ~100 feature vectors of 1 KB from L2, 6.5 GB per DCCL call at 64x128, and the
+// kernel runs at the L2's bandwidth (725 us).  Neighbouring queries look at neighbouring targets, so the same work is a small
+// dense contraction per TILE of queries:
+//   otf_box_kernel    per query: the sampler's coordinate chain (bit-exact, shared with the blend below) and the integer
+//                     bounding box of its taps; atomically merged into the box of its 8 x 16 query tile
+//   otf_dots_kernel   per tile whose box fits (<= 32 columns x 64 rows, or <= 64 columns x 32 rows of target pixels):
+//                     D[128 queries, box] = F1[tile] . F2_l[box]^T on tcgen05 — both operands are TMA boxes of pre-split fp16
+//                     hi/lo K-major planes ([B, h, w, C], the channels-last convention of `alt_cuda_corr`), three products into
+//                     fp32 TMEM like the volume kernel, written to a per-query local plane of 2048 floats ("mini volume": O(N)
+//                     memory) with TMA stores
+//   otf_blend_kernel  per query: the taps blend from its slice of the local plane in ATen's order; tiles whose box does not fit
+//                     (poles of the rotation map, wild flow) keep the r01 CUDA-core path, query by query, inside the same kernel
+// The ERP seam: the sampler wraps x, so a window across the seam touches columns at both ends of the plane.  Boxes are therefore
+// kept in two "unwrapped" column numberings — u0(x) = x and u1(x) = x + W for x < W/2 — a window narrower than W/2 is contiguous
+// in at least one of them, and the target planes are stored twice side by side ([B, Hl, 2 Wl, C]) so that a box in either
+// numbering is one TMA box.
+// Outputs, layouts and tolerances are those of pf_lookup_onthefly (1e-5 of max|ref| against the materialised lookup).
+#include <climits>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "pf_tc.cuh"
+
+namespace pf {
+
+constexpr int OT_TH = 8, OT_TW = 16;                 // query tile: 8 rows x 16 columns = 128 queries = TMEM lanes
+constexpr int OT_PLANE = 2048;                       // local plane per query: 64 rows x 32 columns or 32 rows x 64 columns
+constexpr int OT_MAXCHUNKS = 8;                      // MMA passes per tile: 256 accumulator columns (8 x 32 or 4 x 64 box pixels) each
+constexpr int OT_BK = 64;
+constexpr int OT_APLANE = 128 * OT_BK * 2;           // 16 KiB
+constexpr int OT_BPLANE = 256 * OT_BK * 2;           // 32 KiB
+constexpr int OT_STAGE = 2 * (OT_APLANE + OT_BPLANE);   // hi + lo: 96 KiB
+constexpr int OT_STAGES = 2;
+constexpr int OT_OUT = 128 * 32 * 4;                 // 16 KiB staging for one box row of all queries
+constexpr int OT_THREADS = 192;                      // TMA warp, MMA warp, 4 epilogue warps
+constexpr int OT_SMEM = OT_STAGES * OT_STAGE + OT_OUT + 256 + 1024;
+constexpr uint32_t OT_IDESC = umma_idesc_f16(128, 256);
+
+constexpr int kBlendThreads = 128;
+constexpr int kBlendQueries = 8;
+constexpr int kBoxDots = 324;    // per-query boxes up to 4 dots per tap are evaluated as a plane, larger ones tap by tap
+constexpr int kMaxBox = kBoxDots;
+constexpr int kMaxTaps = 81;
+constexpr int kMaxVec = 4;
+
+struct OtfTcParams {
+  int B, N, h, w, C, L, div_mode;
+  const float *coords;
+  const float *f1[2];                      // [B, N, C] fp32 (CUDA-core fallback)
+  const float *f2[2][PF_MAX_LEVELS];       // [B, Hl*Wl, C] fp32
+  Axis axW[PF_MAX_LEVELS], axH[PF_MAX_LEVELS], ax_gw, ax_gh;
+  const float *grid_w2c;
+  long long grid_bs;
+  float scale;                             // 1 / sqrt(C)
+  int *box_lo, *box_hi;                    // [2 views][L][B][tiles][4]: (u0, u1, y, -) min / max of the tile's taps
+  float *mini[2][PF_MAX_LEVELS];           // [B, h, w, 2048] local planes
+  const uint32_t *amax[2];                 // per view: absmax bits of {f1, f2} (split scales of the fp16 planes)
+  float *out_own, *out_raw;
+};
+
+__device__ __forceinline__ int tile_of(int n, int w, int &tiles_x) {
+  tiles_x = w / OT_TW;
+  const int y = n / w, x = n - y * w;
+  return (y / OT_TH) * tiles_x + x / OT_TW;
+}
+
+__device__ __forceinline__ float ot_split_scale(uint32_t amax_bits) {
+  int e = (int)((amax_bits >> 23) & 0xff) - 127;
+  if ((amax_bits & 0x7fffffffu) == 0u) e = 13;
+  int se = 13 - e;
+  se = se < -100 ? -100 : (se > 100 ? 100 : se);
+  return __uint_as_float((uint32_t)(se + 127) << 23);
+}
+
+// The sampler's coordinates of tap t of query n (identical to pf_onthefly.cu / lookup_kernel): returns (ix, iy).
+__device__ __forceinline__ void otf_tap_coords(const OtfTcParams &p, int branch, int lvl, float cx, float cy, int t, const float *gridx,
+                                               const float *gridy, const Axis axW, const Axis axH, const Axis ax_gw, const Axis ax_gh,
+                                               float &ix, float &iy) {
+  const int aa = t / 9, bb = t - aa * 9;
+  const float px = __fadd_rn(cx, (float)(aa - 4)), py = __fadd_rn(cy, (float)(bb - 4));
+  float sx = px, sy = py;
+  if (branch) {
+    const float gx = to_sample_coord(remainder_pos(px, ax_gw.size), ax_gw, p.div_mode);
+    const float gy = to_sample_coord(py, ax_gh, p.div_mode);
+    const Taps tg = make_taps(gx, gy);
+    sx = blend_zeros(gridx, p.h, p.w, tg);
+    sy = blend_zeros(gridy, p.h, p.w, tg);
+  }
+  ix = to_sample_coord(remainder_pos(sx, axW.size), axW, p.div_mode);
+  iy = to_sample_coord(sy, axH, p.div_mode);
+}
+
+// ------------------------------------------------------------------------------------------------ boxes
+// s_box = {u0 lo, u0 hi, u1 lo, u1 hi, y lo, y hi} of the corners a tap touches (clamped to the plane like blend_zeros)
+__device__ __forceinline__ void box_reset(int *s_box) {
+  s_box[0] = s_box[2] = s_box[4] = INT_MAX;
+  s_box[1] = s_box[3] = s_box[5] = INT_MIN;
+}
+__device__ __forceinline__ int unwrap1(int x, int Wl) { return x < (Wl >> 1) ? x + Wl : x; }
+__device__ __forceinline__ void box_add_tap(int *s_box, int x0, int y0, int Wl, int Hl) {
+  if (x0 + 1 >= 0 && x0 < Wl && y0 + 1 >= 0 && y0 < Hl) {  // tap touches the plane
+    const int xa = max(x0, 0), xb = min(x0 + 1, Wl - 1);
+    atomicMin(&s_box[0], xa);
+    atomicMax(&s_box[1], xb);
+    const int ua = unwrap1(xa, Wl), ub = unwrap1(xb, Wl);
+    atomicMin(&s_box[2], min(ua, ub));
+    atomicMax(&s_box[3], max(ua, ub));
+    atomicMin(&s_box[4], max(y0, 0));
+    atomicMax(&s_box[5], min(y0 + 1, Hl - 1));
+  }
+}
+
+__global__ void __launch_bounds__(kBlendThreads) otf_box_kernel(const OtfTcParams p) {
+  __shared__ int s_box[6];
+  const int lvl = blockIdx.y % p.L, branch = blockIdx.y / p.L, b = blockIdx.z;
+  const int Hl = p.h >> lvl, Wl = p.w >> lvl;
+  const Axis axW = p.axW[lvl], axH = p.axH[lvl], ax_gw = p.ax_gw, ax_gh = p.ax_gh;
+  const float inv_scale = 1.0f / (float)(1 << lvl);
+  const float *gridx = p.grid_w2c ? p.grid_w2c + (long long)b * p.grid_bs : nullptr, *gridy = gridx ? gridx + p.N : nullptr;
+  const int n0 = blockIdx.x * kBlendQueries;
+  // the 8 queries of a CTA are consecutive in a row and 8 | 16: they share the tile
+  if (threadIdx.x == 0) box_reset(s_box);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kBlendQueries * kMaxTaps; i += kBlendThreads) {
+    const int q = i / kMaxTaps, t = i - q * kMaxTaps, n = n0 + q;
+    if (n >= p.N) break;
+    const float cx = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + 0) * p.N + n), inv_scale);
+    const float cy = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + 1) * p.N + n), inv_scale);
+    float ix, iy;
+    otf_tap_coords(p, branch, lvl, cx, cy, t, gridx, gridy, axW, axH, ax_gw, ax_gh, ix, iy);
+    box_add_tap(s_box, (int)floorf(ix), (int)floorf(iy), Wl, Hl);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 && s_box[4] <= s_box[5]) {
+    int tiles_x;
+    const int tile = tile_of(n0, p.w, tiles_x);
+    const int tiles = tiles_x * (p.h / OT_TH);
+    const long long e = ((((long long)branch * p.L + lvl) * p.B + b) * tiles + tile) * 4 + threadIdx.x;
+    atomicMin(p.box_lo + e, s_box[2 * threadIdx.x]);
+    atomicMax(p.box_hi + e, s_box[2 * threadIdx.x + 1]);
+  }
+}
+
+// The tile's box: which numbering (mode), origin, rows, and the local-plane pitch (32 or 64 columns).
+struct TileBox {
+  int mode, X0, Y0, rows, pitch;
+};
+__device__ __forceinline__ bool tile_box(const OtfTcParams &p, int branch, int lvl, int b, int tile, int tiles, TileBox &tb) {
+  const long long e = ((((long long)branch * p.L + lvl) * p.B + b) * tiles + tile) * 4;
+  const int4 lo = *reinterpret_cast<const int4 *>(p.box_lo + e), hi = *reinterpret_cast<const int4 *>(p.box_hi + e);
+  if (lo.z > hi.z || lo.x > hi.x) return false;
+  const int w0 = hi.x - lo.x + 1, w1 = hi.y - lo.y + 1;
+  tb.mode = w1 < w0 ? 1 : 0;
+  const int bw = tb.mode ? w1 : w0;
+  tb.X0 = tb.mode ? lo.y : lo.x;
+  tb.Y0 = lo.z;
+  tb.rows = hi.z - lo.z + 1;
+  tb.pitch = bw <= 32 ? 32 : 64;
+  return bw <= 64 && tb.rows * tb.pitch <= OT_PLANE;
+}
+
+// ------------------------------------------------------------------------------------------------ dots (tcgen05)
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+
+struct OtfMaps {
+  CUtensorMap f1_hi, f1_lo;                                    // [C, w, h, B] fp16, box {64, 16, 8, 1}
+  CUtensorMap f2_hi[2][PF_MAX_LEVELS], f2_lo[2][PF_MAX_LEVELS];   // [C, 2 Wl, Hl, B] fp16, box {64, 32, 8, 1} / {64, 64, 4, 1}
+  CUtensorMap out[2][PF_MAX_LEVELS];                           // [32, 64, w, h, B] / [64, 32, w, h, B] fp32, box {32, 1, 16, 8, 1}
+};
+
+__global__ void __launch_bounds__(OT_THREADS, 1) otf_dots_kernel(const __grid_constant__ OtfMaps maps, const OtfTcParams p, const int branch) {
+  const int tile = blockIdx.x, lvl = blockIdx.y, b = blockIdx.z;
+  const int tiles_x = p.w / OT_TW, tiles = tiles_x * (p.h / OT_TH);
+  TileBox tb;
+  if (!tile_box(p, branch, lvl, b, tile, tiles, tb)) return;      // uniform: the blend kernel takes the CUDA-core path for this tile
+  const int wide = tb.pitch == 64, rpc = 256 / tb.pitch;          // box rows per MMA pass
+  const int nchunks = (tb.rows + rpc - 1) / rpc, X0 = tb.X0, Y0 = tb.Y0;
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *out_stage = smem + OT_STAGES * OT_STAGE;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(out_stage + OT_OUT);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + OT_STAGES);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * OT_STAGES), bar_tempty = smem_u32(bars + 2 * OT_STAGES + 2);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * OT_STAGES + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = p.C / OT_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < OT_STAGES; ++s) mbar_init(bar_full + 8 * s, 1), mbar_init(bar_empty + 8 * s, 1);
+    for (int a = 0; a < 2; ++a) mbar_init(bar_tfull + 8 * a, 1), mbar_init(bar_tempty + 8 * a, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < nchunks; ++c)
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_arrive_expect_tx(full, (uint32_t)OT_STAGE);
+          const uint32_t sbase = smem_u32(smem + stage * OT_STAGE);
+          // layout of a stage: [A.hi 16K | B.hi 32K | A.lo 16K | B.lo 32K]
+          tma_load_4d(sbase, &maps.f1_hi, full, kb * OT_BK, tx * OT_TW, ty * OT_TH, b);
+          tma_load_4d(sbase + OT_APLANE, &maps.f2_hi[wide][lvl], full, kb * OT_BK, X0, Y0 + c * rpc, b);
+          tma_load_4d(sbase + OT_APLANE + OT_BPLANE, &maps.f1_lo, full, kb * OT_BK, tx * OT_TW, ty * OT_TH, b);
+          tma_load_4d(sbase + 2 * OT_APLANE + OT_BPLANE, &maps.f2_lo[wide][lvl], full, kb * OT_BK, X0, Y0 + c * rpc, b);
+          if (++stage == OT_STAGES) stage = 0, phase ^= 1;
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, acc = 0, acc_phase = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 256;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(smem + stage * OT_STAGE);
+          const uint64_t a_hi = make_smem_desc(sbase), b_hi = make_smem_desc(sbase + OT_APLANE);
+          const uint64_t a_lo = make_smem_desc(sbase + OT_APLANE + OT_BPLANE), b_lo = make_smem_desc(sbase + 2 * OT_APLANE + OT_BPLANE);
+#pragma unroll
+          for (int k = 0; k < OT_BK / 16; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, OT_IDESC, (kb | k) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < OT_BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, OT_IDESC, 1u);
+#pragma unroll
+          for (int k = 0; k < OT_BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, OT_IDESC, 1u);
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == OT_STAGES) stage = 0, phase ^= 1;
+        }
+        umma_commit(bar_tfull + 8 * acc);
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // epilogue: 4 warps, TMEM lane = query of the tile (rx fastest), columns = box pixels of the pass in segments of 32:
+    // segment g = box row g / (pitch / 32), columns 32 (g % (pitch / 32)) ...; one TMA store per segment into the local planes
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    const bool leader = threadIdx.x == 64;
+    const float scale = p.scale / (ot_split_scale(p.amax[branch][0]) * ot_split_scale(p.amax[branch][1]));
+    const int spr = tb.pitch >> 5;   // segments per box row
+    uint32_t acc = 0, acc_phase = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
+      const int nseg = min(8, (tb.rows - c * rpc) * spr);      // segments of this pass that hold box rows
+      uint32_t un[32];
+      tmem_ld32(taddr, un);
+#pragma unroll 1
+      for (int g = 0; g < nseg; ++g) {
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(un[j]) * scale;
+        if (g + 1 < nseg) {
+          tmem_ld32(taddr + (g + 1) * 32, un);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+        if (leader) tma_store_wait_read0();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        {
+          uint8_t *r0 = out_stage + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4 *>(r0 + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        fence_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (leader) {
+          tma_store_5d(&maps.out[wide][lvl], smem_u32(out_stage), (g % spr) * 32, c * rpc + g / spr, tx * OT_TW, ty * OT_TH, b);
+          tma_store_commit();
+        }
+      }
+      if ((acc ^= 1) == 0) acc_phase ^= 1;
+    }
+    if (leader) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ blend
+// Four dot products of the query vector at once: all loads in flight together, then one 6-shuffle reduction for the four sums
+// (fold 4 -> 2 -> 1 values per lane over xor 16 / 8, then a 3-step butterfly).  Every lane of group g = lane >> 3 ends with sum g.
+// Null pointers give 0.  The per-pixel latency (L2 round trip + reduction) is what bounds the CUDA-core path.
+__device__ __forceinline__ float ot_dot4(const float *const (&ptr)[4], const float4 (&q)[kMaxVec], int nvec, int lane) {
+  float4 v[4][kMaxVec];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j)
+      v[c][j] = (j < nvec && ptr[c]) ? __ldg(reinterpret_cast<const float4 *>(ptr[c]) + j * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float a[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      if (j < nvec) {
+        acc = fmaf(q[j].x, v[c][j].x, acc);
+        acc = fmaf(q[j].y, v[c][j].y, acc);
+        acc = fmaf(q[j].z, v[c][j].z, acc);
+        acc = fmaf(q[j].w, v[c][j].w, acc);
+      }
+    }
+    a[c] = acc;
+  }
+  const bool up16 = lane & 16, up8 = lane & 8;
+  // lanes 0-15 keep sums {0, 1}, lanes 16-31 keep {2, 3}
+  const float s0 = (up16 ? a[2] : a[0]) + __shfl_xor_sync(0xffffffffu, up16 ? a[0] : a[2], 16);
+  const float s1 = (up16 ? a[3] : a[1]) + __shfl_xor_sync(0xffffffffu, up16 ? a[1] : a[3], 16);
+  // within each half, lanes with bit 3 clear keep the first, set keep the second
+  float r = (up8 ? s1 : s0) + __shfl_xor_sync(0xffffffffu, up8 ? s0 : s1, 8);
+  r += __shfl_xor_sync(0xffffffffu, r, 4);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
+__global__ void __launch_bounds__(kBlendThreads) otf_blend_kernel(const OtfTcParams p) {
+  __shared__ float s_ix[kMaxTaps], s_iy[kMaxTaps];
+  __shared__ float s_dots[kMaxBox];
+  __shared__ float s_out[kMaxTaps][kBlendQueries + 1];
+  __shared__ int s_box[6];
+  constexpr int K2 = kMaxTaps;
+  // the other view first: its CUDA-core tiles (poles of the rotation map) are the long CTAs and must not start last
+  const int by = gridDim.y - 1 - blockIdx.y;
+  const int lvl = by % p.L, branch = by / p.L, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Hl = p.h >> lvl, Wl = p.w >> lvl;
+  const Axis axW = p.axW[lvl], axH = p.axH[lvl], ax_gw = p.ax_gw, ax_gh = p.ax_gh;
+  const float inv_scale = 1.0f / (float)(1 << lvl);
+  const float *gridx = p.grid_w2c ? p.grid_w2c + (long long)b * p.grid_bs : nullptr, *gridy = gridx ? gridx + p.N : nullptr;
+  const float *f2 = p.f2[branch][lvl] + (long long)b * Hl * Wl * p.C;
+  const float *mini = p.mini[branch][lvl] + (long long)b * p.N * OT_PLANE;
+  const int nvec = p.C / 128;
+  const int n0 = blockIdx.x * kBlendQueries;
+  int tiles_x;
+  const int tile = tile_of(n0, p.w, tiles_x);          // the CTA's 8 queries share the tile
+  TileBox tb;
+  const bool tile_tc = tile_box(p, branch, lvl, b, tile, tiles_x * (p.h / OT_TH), tb);
+
+  for (int q = 0; q < kBlendQueries; ++q) {
+    const int n = n0 + q;
+    if (n >= p.N) break;
+    if (threadIdx.x == 0) box_reset(s_box);
+    __syncthreads();
+    const float cx = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + 0) * p.N + n), inv_scale);
+    const float cy = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + 1) * p.N + n), inv_scale);
+    for (int t = threadIdx.x; t < K2; t += kBlendThreads) {
+      float ix, iy;
+      otf_tap_coords(p, branch, lvl, cx, cy, t, gridx, gridy, axW, axH, ax_gw, ax_gh, ix, iy);
+      s_ix[t] = ix, s_iy[t] = iy;
+      box_add_tap(s_box, (int)floorf(ix), (int)floorf(iy), Wl, Hl);
+    }
+    __syncthreads();
+    const bool empty = s_box[4] > s_box[5];
+    const bool tc = tile_tc && !empty;                                        // block-uniform
+    const int mode = tc ? tb.mode : 0;
+    const int x_lo = s_box[0], x_hi = s_box[1], y_lo = s_box[4], y_hi = s_box[5];      // the CUDA-core path works in plain columns
+    const int bw = empty ? 0 : x_hi - x_lo + 1, bh = empty ? 0 : y_hi - y_lo + 1;
+    const int area = bw * bh;
+    if (tc) {
+      // the tile's dots are in this query's local plane (otf_dots_kernel); a tap reads its four corners from it
+      const float *m = mini + (long long)n * OT_PLANE;
+      for (int t = threadIdx.x; t < K2; t += kBlendThreads) {
+        const Taps tp = make_taps(s_ix[t], s_iy[t]);
+        const bool xin0 = (unsigned)tp.x0 < (unsigned)Wl, xin1 = (unsigned)(tp.x0 + 1) < (unsigned)Wl;
+        const bool yin0 = (unsigned)tp.y0 < (unsigned)Hl, yin1 = (unsigned)(tp.y0 + 1) < (unsigned)Hl;
+        // column of the west corner in the box's numbering (mode 1: unwrapped); the east corner is the next column — a tap
+        // whose corners straddle the numbering's cut would have made the box as wide as the plane, and then mode 0 is chosen
+        const int ux = (mode && xin0) ? unwrap1(tp.x0, Wl) : ((mode && xin1) ? unwrap1(tp.x0 + 1, Wl) - 1 : tp.x0);
+        const float *c0 = m + (tp.y0 - tb.Y0) * tb.pitch + (ux - tb.X0);
+        const float v_nw = (yin0 && xin0) ? __ldg(c0) : 0.f;
+        const float v_ne = (yin0 && xin1) ? __ldg(c0 + 1) : 0.f;
+        const float v_sw = (yin1 && xin0) ? __ldg(c0 + tb.pitch) : 0.f;
+        const float v_se = (yin1 && xin1) ? __ldg(c0 + tb.pitch + 1) : 0.f;
+        float acc = __fmul_rn(v_nw, tp.nw);
+        acc = __fmaf_rn(v_ne, tp.ne, acc);
+        acc = __fmaf_rn(v_sw, tp.sw, acc);
+        acc = __fmaf_rn(v_se, tp.se, acc);
+        s_out[t][q] = acc;
+      }
+    } else {
+      float4 qv[kMaxVec];
+      const float4 *f1v = reinterpret_cast<const float4 *>(p.f1[branch] + ((long long)b * p.N + n) * p.C);
+#pragma unroll
+      for (int j = 0; j < kMaxVec; ++j) qv[j] = (j < nvec) ? __ldg(f1v + j * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (area <= kBoxDots) {
+        // the plane on the query's own box (fewer dot products than four per tap), four pixels per warp step
+        for (int pix = warp * 4; pix < area; pix += kBlendThreads / 8) {
+          const float *ptr[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int pc = pix + c, yy = pc / bw, xx = pc - yy * bw;
+            ptr[c] = pc < area ? f2 + ((long long)(y_lo + yy) * Wl + (x_lo + xx)) * p.C : nullptr;
+          }
+          const float d = ot_dot4(ptr, qv, nvec, lane);
+          if ((lane & 7) == 0 && pix + (lane >> 3) < area) s_dots[pix + (lane >> 3)] = d * p.scale;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < K2; t += kBlendThreads) {
+          const Taps tp = make_taps(s_ix[t], s_iy[t]);
+          const bool xin0 = (unsigned)tp.x0 < (unsigned)Wl, xin1 = (unsigned)(tp.x0 + 1) < (unsigned)Wl;
+          const bool yin0 = (unsigned)tp.y0 < (unsigned)Hl, yin1 = (unsigned)(tp.y0 + 1) < (unsigned)Hl;
+          const int base = (tp.y0 - y_lo) * bw + (tp.x0 - x_lo);
+          const float v_nw = (yin0 && xin0) ? s_dots[base] : 0.f;
+          const float v_ne = (yin0 && xin1) ? s_dots[base + 1] : 0.f;
+          const float v_sw = (yin1 && xin0) ? s_dots[base + bw] : 0.f;
+          const float v_se = (yin1 && xin1) ? s_dots[base + bw + 1] : 0.f;
+          float acc = __fmul_rn(v_nw, tp.nw);
+          acc = __fmaf_rn(v_ne, tp.ne, acc);
+          acc = __fmaf_rn(v_sw, tp.sw, acc);
+          acc = __fmaf_rn(v_se, tp.se, acc);
+          s_out[t][q] = acc;
+        }
+      } else {
+        // large boxes (poles of the rotation map, windows across the seam): a warp per tap, its four corners in one step
+        for (int t = warp; t < K2; t += kBlendThreads / 32) {
+          const Taps tp = make_taps(s_ix[t], s_iy[t]);
+          const float *ptr[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int xx = tp.x0 + (c & 1), yy = tp.y0 + (c >> 1);
+            const bool in = (unsigned)xx < (unsigned)Wl && (unsigned)yy < (unsigned)Hl;
+            ptr[c] = in ? f2 + ((long long)yy * Wl + xx) * p.C : nullptr;
+          }
+          const float d = ot_dot4(ptr, qv, nvec, lane) * p.scale;
+          const float v1 = __shfl_sync(0xffffffffu, d, 8), v2 = __shfl_sync(0xffffffffu, d, 16), v3 = __shfl_sync(0xffffffffu, d, 24);
+          if (lane == 0) {
+            float acc = __fmul_rn(d, tp.nw);
+            acc = __fmaf_rn(v1, tp.ne, acc);
+            acc = __fmaf_rn(v2, tp.sw, acc);
+            acc = __fmaf_rn(v3, tp.se, acc);
+            s_out[t][q] = acc;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (branch == 0) {
+    float *out = p.out_own + ((long long)b * p.L + lvl) * K2 * (long long)p.N + n0;
+    for (int i = threadIdx.x; i < K2 * kBlendQueries; i += kBlendThreads) {
+      const int ch = i / kBlendQueries, q = i - ch * kBlendQueries;
+      if (n0 + q < p.N) out[(long long)ch * p.N + q] = s_out[ch][q];
+    }
+  } else {
+    for (int i = threadIdx.x; i < K2 * kBlendQueries; i += kBlendThreads) {
+      const int q = i / K2, ch = i - q * K2;
+      if (n0 + q < p.N) p.out_raw[(((long long)b * p.N + n0 + q) * p.L + lvl) * K2 + ch] = s_out[ch][q];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ operand planes
+__global__ void __launch_bounds__(256) otf_absmax_kernel(const float *__restrict__ x, long long n, uint32_t *__restrict__ out) {
+  uint32_t m = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = max(m, __float_as_uint(fabsf(x[i])));
+  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+// row_elems > 0: every row of `row_elems` elements (one image row: Wl * C) is written twice, side by side (the seam, see top)
+__global__ void __launch_bounds__(256) otf_split_kernel(const float *__restrict__ x, long long n, const uint32_t *__restrict__ amax, __half *__restrict__ hi,
+                                                        __half *__restrict__ lo, long long row_elems) {
+  const float s = ot_split_scale(*amax);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i] * s;
+    const __half h = __float2half_rn(v), l = __float2half_rn(v - __half2float(h));
+    if (row_elems > 0) {
+      const long long r = i / row_elems, o = i + r * row_elems;
+      hi[o] = h, lo[o] = l;
+      hi[o + row_elems] = h, lo[o + row_elems] = l;
+    } else {
+      hi[i] = h, lo[i] = l;
+    }
+  }
+}
+
+}  // namespace pf
+
+// fp32 channels-last features -> fp16 hi/lo planes of the same layout (dup_row_elems = Wl * C for the target levels: rows doubled).  amax: one uint32 (zeroed by the caller before the FIRST
+// tensor that shares it; the pooled levels of a feature map share level 0's word: |avg| <= max).
+extern "C" int pf_onthefly_absmax(const float *x, long long count, void *amax, void *stream) {
+  using namespace pf;
+  PF_REQUIRE(x && amax && count > 0, "pf_onthefly_absmax: bad arguments");
+  otf_absmax_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(x, count, reinterpret_cast<uint32_t *>(amax));
+  return check_launch("pf_onthefly_absmax");
+}
+extern "C" int pf_onthefly_split(const float *x, long long count, const void *amax, void *hi, void *lo, long long dup_row_elems, void *stream) {
+  using namespace pf;
+  PF_REQUIRE(x && amax && hi && lo && count > 0 && dup_row_elems >= 0, "pf_onthefly_split: bad arguments");
+  PF_REQUIRE(dup_row_elems == 0 || count % dup_row_elems == 0, "pf_onthefly_split: count must be a multiple of the row length");
+  otf_split_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(x, count, reinterpret_cast<const uint32_t *>(amax), reinterpret_cast<__half *>(hi),
+                                                          reinterpret_cast<__half *>(lo), dup_row_elems);
+  return check_launch("pf_onthefly_split");
+}
+
+extern "C" int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *t, void *stream) {
+  using namespace pf;
+  PF_REQUIRE(t != nullptr, "pf_lookup_onthefly_tc: null args");
+  const pf_onthefly_args *a = &t->base;
+  PF_REQUIRE(a->batch > 0 && a->h > 0 && a->w > 0, "pf_lookup_onthefly_tc: bad shape");
+  PF_REQUIRE(a->radius == 4 && a->cyclic == 1, "pf_lookup_onthefly_tc: built for the model's radius-4 cyclic lookup");
+  PF_REQUIRE(a->channels % 128 == 0 && a->channels <= 512 && a->channels % OT_BK == 0, "pf_lookup_onthefly_tc: channels must be a multiple of 128, <= 512");
+  PF_REQUIRE(a->h % OT_TH == 0 && a->w % OT_TW == 0, "pf_lookup_onthefly_tc: the query grid must tile by %dx%d (got %dx%d)", OT_TH, OT_TW, a->h, a->w);
+  PF_REQUIRE(a->num_levels >= 1 && a->num_levels <= PF_MAX_LEVELS, "pf_lookup_onthefly_tc: num_levels must be 1..%d", PF_MAX_LEVELS);
+  PF_REQUIRE(a->coords && a->fmap1_own && a->out_own && t->box_lo && t->box_hi && t->amax_own, "pf_lookup_onthefly_tc: null pointer");
+  const bool dual = a->fmap1_other != nullptr;
+  PF_REQUIRE(!dual || (a->grid_w2c && a->grid_c2w && a->out_other && a->scratch && t->amax_other), "pf_lookup_onthefly_tc: dual lookup needs grids, out_other, scratch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int views = dual ? 2 : 1, L = a->num_levels, B = a->batch, h = a->h, w = a->w, C = a->channels, N = h * w;
+  const int tiles = (h / OT_TH) * (w / OT_TW);
+  OtfTcParams p;
+  p.B = B, p.N = N, p.h = h, p.w = w, p.C = C, p.L = L, p.div_mode = a->div_mode;
+  p.coords = a->coords;
+  p.f1[0] = a->fmap1_own, p.f1[1] = a->fmap1_other;
+  for (int l = 0; l < PF_MAX_LEVELS; ++l) {
+    p.f2[0][l] = l < L ? a->fmap2_own[l] : nullptr;
+    p.f2[1][l] = (dual && l < L) ? a->fmap2_other[l] : nullptr;
+    p.mini[0][l] = l < L ? t->mini_own[l] : nullptr;
+    p.mini[1][l] = (dual && l < L) ? t->mini_other[l] : nullptr;
+    p.axH[l] = make_axis((h >> l) > 0 ? (h >> l) : 1), p.axW[l] = make_axis((w >> l) > 0 ? (w >> l) : 1);
+    if (l < L) {
+      PF_REQUIRE((h >> l) >= 1 && (w >> l) >= 1, "pf_lookup_onthefly_tc: level %d is empty", l);
+      PF_REQUIRE(p.f2[0][l] && p.mini[0][l] && t->f2_hi_own[l] && t->f2_lo_own[l], "pf_lookup_onthefly_tc: own level %d: null pointer", l);
+      PF_REQUIRE(!dual || (p.f2[1][l] && p.mini[1][l] && t->f2_hi_other[l] && t->f2_lo_other[l]), "pf_lookup_onthefly_tc: other level %d: null pointer", l);
+    }
+  }
+  p.ax_gw = make_axis(w), p.ax_gh = make_axis(h);
+  p.grid_w2c = a->grid_w2c, p.grid_bs = a->grid_batch_stride;
+  p.scale = 1.0f / sqrtf((float)C);
+  p.box_lo = t->box_lo, p.box_hi = t->box_hi;
+  p.amax[0] = reinterpret_cast<const uint32_t *>(t->amax_own), p.amax[1] = reinterpret_cast<const uint32_t *>(t->amax_other);
+  p.out_own = a->out_own, p.out_raw = a->scratch;
+  const size_t table = (size_t)views * L * B * tiles * 4 * sizeof(int);
+  if (cudaMemsetAsync(t->box_lo, 0x7f, table, st) != cudaSuccess || cudaMemsetAsync(t->box_hi, 0x80, table, st) != cudaSuccess)
+    return check_launch("pf_lookup_onthefly_tc(memset)");
+  const dim3 qgrid(ceil_div(N, kBlendQueries), L * views, B);
+  otf_box_kernel<<<qgrid, kBlendThreads, 0, st>>>(p);
+  if (int e = check_launch("pf_lookup_onthefly_tc(box)")) return e;
+  cudaFuncSetAttribute(otf_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OT_SMEM);
+  for (int v = 0; v < views; ++v) {
+    OtfMaps m;
+    const void *f1_hi = v ? t->f1_hi_other : t->f1_hi_own, *f1_lo = v ? t->f1_lo_other : t->f1_lo_own;
+    PF_REQUIRE(f1_hi && f1_lo, "pf_lookup_onthefly_tc: f1 planes missing");
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+      cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)w * C * 2, (cuuint64_t)h * w * C * 2};
+      cuuint32_t box[4] = {OT_BK, OT_TW, OT_TH, 1};
+      if (int e = encode(&m.f1_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(f1_hi), dims, strides, box, "otf f1.hi")) return e;
+      if (int e = encode(&m.f1_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(f1_lo), dims, strides, box, "otf f1.lo")) return e;
+    }
+    for (int l = 0; l < PF_MAX_LEVELS; ++l) {
+      const int ll = l < L ? l : 0;
+      const int Hl = h >> ll, Wl = w >> ll;
+      const void *hi = v ? t->f2_hi_other[ll] : t->f2_hi_own[ll], *lo = v ? t->f2_lo_other[ll] : t->f2_lo_own[ll];
+      float *mini = v ? t->mini_other[ll] : t->mini_own[ll];
+      for (int wide = 0; wide < 2; ++wide) {
+        const int pitch = wide ? 64 : 32;
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)(2 * Wl), (cuuint64_t)Hl, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)2 * Wl * C * 2, (cuuint64_t)Hl * 2 * Wl * C * 2};
+        cuuint32_t box[4] = {OT_BK, (cuuint32_t)pitch, (cuuint32_t)(256 / pitch), 1};
+        if (int e = encode(&m.f2_hi[wide][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(hi), dims, strides, box, "otf f2.hi")) return e;
+        if (int e = encode(&m.f2_lo[wide][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(lo), dims, strides, box, "otf f2.lo")) return e;
+        cuuint64_t od[5] = {(cuuint64_t)pitch, (cuuint64_t)(OT_PLANE / pitch), (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+        cuuint64_t os[4] = {(cuuint64_t)pitch * 4, (cuuint64_t)OT_PLANE * 4, (cuuint64_t)w * OT_PLANE * 4, (cuuint64_t)h * w * OT_PLANE * 4};
+        cuuint32_t ob[5] = {32, 1, OT_TW, OT_TH, 1};
+        if (int e = encode(&m.out[wide][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, mini, od, os, ob, "otf mini")) return e;
+      }
+    }
+    otf_dots_kernel<<<dim3(tiles, L, B), OT_THREADS, OT_SMEM, st>>>(m, p, v);
+    if (int e = check_launch("pf_lookup_onthefly_tc(dots)")) return e;
+  }
+  otf_blend_kernel<<<qgrid, kBlendThreads, 0, st>>>(p);
+  if (int e = check_launch("pf_lookup_onthefly_tc(blend)")) return e;
+  if (dual)
+    return rotate_forward(B, h, w, L, a->radius, a->div_mode, a->grid_c2w, a->grid_batch_stride, a->scratch, a->out_other, 0, 0, st, nullptr);
+  return 0;
+}

@@ -388,11 +388,53 @@ def channels_last_pyramid(fmap: torch.Tensor, num_levels: int) -> List[torch.Ten
     return levels
 
 
+class OnTheFlyPlanes:
+    """Tensor-core operands of one view for pf_lookup_onthefly_tc: fp16 hi/lo planes of the channels-last query features and
+    of every level of the pooled target pyramid (one shared split scale per tensor family), plus the view's per-query
+    local-plane scratch (2048 floats per query and level; O(N), allocated on first use and reused by every lookup).  The
+    target planes hold every image row twice side by side ([B, Hl, 2 Wl, C]) so that windows across the ERP seam are one box."""
+    TILE_H, TILE_W, BOX = 8, 16, 2048
+
+    def __init__(self, f1: torch.Tensor, f2: Sequence[torch.Tensor]):
+        lib = _lib.load()
+        f1, f2 = f1.detach(), [t.detach() for t in f2]
+        dev = f1.device
+        with torch.cuda.device(dev):
+            self.amax = torch.zeros(2, device=dev, dtype=torch.int32)
+            st = _stream()
+            a0, a1 = self.amax.data_ptr(), self.amax.data_ptr() + 4
+            _lib.check(lib.pf_onthefly_absmax(f1.data_ptr(), f1.numel(), a0, st), "pf_onthefly_absmax")
+            _lib.check(lib.pf_onthefly_absmax(f2[0].data_ptr(), f2[0].numel(), a1, st), "pf_onthefly_absmax")
+            self.f1_hi, self.f1_lo = torch.empty_like(f1, dtype=torch.float16), torch.empty_like(f1, dtype=torch.float16)
+            _lib.check(lib.pf_onthefly_split(f1.data_ptr(), f1.numel(), a0, self.f1_hi.data_ptr(), self.f1_lo.data_ptr(), 0, st), "pf_onthefly_split")
+            self.f2_hi, self.f2_lo = [], []
+            for t in f2:
+                Bt, Hl, Wl, Ct = t.shape
+                hi, lo = (torch.empty((Bt, Hl, 2 * Wl, Ct), device=dev, dtype=torch.float16) for _ in range(2))
+                _lib.check(lib.pf_onthefly_split(t.data_ptr(), t.numel(), a1, hi.data_ptr(), lo.data_ptr(), Wl * Ct, st), "pf_onthefly_split")
+                self.f2_hi.append(hi), self.f2_lo.append(lo)
+            _count(3 + len(f2))
+        self.shape, self.levels, self._mini = tuple(f1.shape), len(f2), None
+
+    @staticmethod
+    def supported(f1: torch.Tensor, radius: int = 4) -> bool:
+        B, h, w, Cn = f1.shape
+        return radius == 4 and h % OnTheFlyPlanes.TILE_H == 0 and w % OnTheFlyPlanes.TILE_W == 0 and Cn % 128 == 0 and Cn <= 512
+
+    def mini(self):
+        if self._mini is None:
+            B, h, w, _ = self.shape
+            self._mini = [torch.empty((B, h, w, self.BOX), device=self.f1_hi.device, dtype=torch.float32) for _ in range(self.levels)]
+        return self._mini
+
+
 def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence[torch.Tensor],
                     f1_other: Optional[torch.Tensor] = None, f2_other: Optional[Sequence[torch.Tensor]] = None,
                     grid_w2c: Optional[torch.Tensor] = None, grid_c2w: Optional[torch.Tensor] = None,
-                    radius: int = 4, cyclic: bool = True):
-    """Volume-free lookup.  f1_* are channels-last [B,h,w,C]; f2_* are channels_last_pyramid() lists."""
+                    radius: int = 4, cyclic: bool = True, planes_own: Optional["OnTheFlyPlanes"] = None,
+                    planes_other: Optional["OnTheFlyPlanes"] = None):
+    """Volume-free lookup.  f1_* are channels-last [B,h,w,C]; f2_* are channels_last_pyramid() lists.  With `planes_*`
+    (OnTheFlyPlanes of the same operands) the dot products run on tensor cores (pf_lookup_onthefly_tc)."""
     lib = _lib.load()
     _chk(coords, "coords", 4)
     coords = coords.contiguous()
@@ -426,8 +468,25 @@ def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence
             a.fmap1_other, a.fmap2_other = f1_other.data_ptr(), _lib.level_ptrs(list(f2_other))
             a.grid_w2c, a.grid_c2w, a.grid_batch_stride = gw.data_ptr(), gc.data_ptr(), bs_w
             a.out_other, a.scratch = out_other.data_ptr(), scratch.data_ptr()
-        _lib.check(lib.pf_lookup_onthefly(C.byref(a), _stream()), "pf_lookup_onthefly")
-        _count(2 if dual else 1)
+        if planes_own is not None and cyclic and radius == 4 and (not dual or planes_other is not None):
+            t = _lib.OnTheFlyTcArgs()
+            t.base = a
+            t.f1_hi_own, t.f1_lo_own = planes_own.f1_hi.data_ptr(), planes_own.f1_lo.data_ptr()
+            t.f2_hi_own, t.f2_lo_own = _lib.level_ptrs(planes_own.f2_hi), _lib.level_ptrs(planes_own.f2_lo)
+            t.amax_own, t.mini_own = planes_own.amax.data_ptr(), _lib.level_ptrs(planes_own.mini())
+            if dual:
+                t.f1_hi_other, t.f1_lo_other = planes_other.f1_hi.data_ptr(), planes_other.f1_lo.data_ptr()
+                t.f2_hi_other, t.f2_lo_other = _lib.level_ptrs(planes_other.f2_hi), _lib.level_ptrs(planes_other.f2_lo)
+                t.amax_other, t.mini_other = planes_other.amax.data_ptr(), _lib.level_ptrs(planes_other.mini())
+            tiles = (h // OnTheFlyPlanes.TILE_H) * (w // OnTheFlyPlanes.TILE_W)
+            box = torch.empty((2, (2 if dual else 1) * L * B * tiles * 4), device=dev, dtype=torch.int32)
+            t.box_lo, t.box_hi = box[0].data_ptr(), box[1].data_ptr()
+            _lib.check(lib.pf_lookup_onthefly_tc(C.byref(t), _stream()), "pf_lookup_onthefly_tc")
+            _state["otf_boxes"] = box.view(2, 2 if dual else 1, L, B, tiles, 4)      # diagnostics: scripts/probe/otf_tiles.py
+            _count(6 if dual else 3)
+        else:
+            _lib.check(lib.pf_lookup_onthefly(C.byref(a), _stream()), "pf_lookup_onthefly")
+            _count(2 if dual else 1)
     return (out_own, out_other) if dual else out_own
 
 
@@ -528,11 +587,12 @@ def _is_seed(t: torch.Tensor) -> bool:
 
 class _OnTheFlyLookupFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, coords, grid_w2c, grid_c2w, radius, tape, own_id, other_id, f1_own, f1_other, *f2):
+    def forward(ctx, coords, grid_w2c, grid_c2w, radius, tape, own_id, other_id, planes_own, planes_other, f1_own, f1_other, *f2):
         L = len(f2) // 2
         ctx.save_for_backward(coords, grid_w2c, grid_c2w)
         ctx.meta = (tape, own_id, other_id, tuple(f1_own.shape))
-        return lookup_onthefly(coords, f1_own, list(f2[:L]), f1_other, list(f2[L:]), grid_w2c, grid_c2w, radius, cyclic=True)
+        return lookup_onthefly(coords, f1_own, list(f2[:L]), f1_other, list(f2[L:]), grid_w2c, grid_c2w, radius, cyclic=True,
+                               planes_own=planes_own, planes_other=planes_other)
 
     @staticmethod
     def backward(ctx, g_own, g_other):
@@ -543,20 +603,20 @@ class _OnTheFlyLookupFn(torch.autograd.Function):
         if g_other is None:
             g_other = torch.zeros_like(g_own)
         tape.record(own_id, other_id, coords, gw, gc, g_own.contiguous(), g_other.contiguous())
-        n_f2 = len(ctx.needs_input_grad) - 9
+        n_f2 = len(ctx.needs_input_grad) - 11
         seed = None
         if not tape.seeded:        # one real (zero) gradient per pass makes sure autograd visits the pyramid nodes of BOTH views
             tape.seeded = True
             seed = (torch.zeros(f1_shape, device=coords.device), torch.zeros(f1_shape, device=coords.device))
             _SEEDS.clear()
             _SEEDS.update(t.data_ptr() for t in seed)
-        return (None, None, None, None, None, None, None, seed[0] if seed else None, seed[1] if seed else None, *([None] * n_f2))
+        return (None, None, None, None, None, None, None, None, None, seed[0] if seed else None, seed[1] if seed else None, *([None] * n_f2))
 
 
 def lookup_onthefly_autograd(coords, pyr_own, pyr_other, grid_w2c, grid_c2w, radius=4):
     """DCCL lookup straight from the features with gradients to the feature maps (pyr_*: corr.FeaturePyramid built under autograd)."""
     return _OnTheFlyLookupFn.apply(coords.detach(), grid_w2c.detach(), grid_c2w.detach(), radius, pyr_own.tape, pyr_own.view_id,
-                                   pyr_other.view_id, pyr_own.f1, pyr_other.f1, *pyr_own.f2, *pyr_other.f2)
+                                   pyr_other.view_id, pyr_own.planes, pyr_other.planes, pyr_own.f1, pyr_other.f1, *pyr_own.f2, *pyr_other.f2)
 
 
 # ------------------------------------------------------------------------------------------ (f2) / (f4)

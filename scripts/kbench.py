@@ -185,6 +185,12 @@ def main():
     cl = lambda t: t.permute(0, 2, 3, 1).contiguous()
     f1a, f2a, f1b, f2b = cl(fm[0]), ops.channels_last_pyramid(fm[1], 4), cl(fm[2]), ops.channels_last_pyramid(fm[3], 4)
     rec("lookup_onthefly", lambda: ops.lookup_onthefly(coords, f1a, f2a, f1b, f2b, gw, gc, 4))
+    pla, plb = ops.OnTheFlyPlanes(f1a, f2a), ops.OnTheFlyPlanes(f1b, f2b)
+    rec("lookup_onthefly[tcgen05 dots, smooth flow]", lambda: ops.lookup_onthefly(coords, f1a, f2a, f1b, f2b, gw, gc, 4, planes_own=pla, planes_other=plb))
+    noisy = TO.coords_grid(B, h, w, "cuda") + torch.randn(B, 2, h, w, device="cuda", generator=g) * 5.0
+    rec("lookup_onthefly[CUDA cores, iid sigma-5 flow]", lambda: ops.lookup_onthefly(noisy, f1a, f2a, f1b, f2b, gw, gc, 4))
+    rec("lookup_onthefly[tcgen05 dots, iid sigma-5 flow]", lambda: ops.lookup_onthefly(noisy, f1a, f2a, f1b, f2b, gw, gc, 4, planes_own=pla, planes_other=plb))
+    rec("onthefly_planes[absmax + split, one view]", lambda: ops.OnTheFlyPlanes(f1a, f2a))
     if a.out:
         os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
         with open(a.out, "w") as fh:

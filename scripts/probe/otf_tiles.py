@@ -1,0 +1,47 @@
+"""Which query tiles of the tensor-core on-the-fly lookup take the tcgen05 path (tile box <= 32 x 64 or 64 x 32 target pixels), per view
+and level, for a smooth flow, for i.i.d. noise and for the flow a random-init model predicts.  Prints the fractions."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle import torch_oracle as TO  # noqa: E402
+from prior_flow_b200 import ops  # noqa: E402
+
+
+def report(tag, coords, f1a, f2a, f1b, f2b, gw, gc, pla, plb):
+    ops.lookup_onthefly(coords, f1a, f2a, f1b, f2b, gw, gc, 4, planes_own=pla, planes_other=plb)
+    box = ops._state["otf_boxes"]
+    lo, hi = box[0].long(), box[1].long()
+    bw = torch.minimum(hi[..., 0] - lo[..., 0], hi[..., 1] - lo[..., 1]) + 1      # the narrower of the two column numberings
+    bh = hi[..., 2] - lo[..., 2] + 1
+    for v in range(box.shape[1]):
+        for l in range(box.shape[2]):
+            w_, h_ = bw[v, l].flatten(), bh[v, l].flatten()
+            valid = (w_ > 0) & (h_ > 0) & (w_ < 10000)
+            fit = valid & (((w_ <= 32) & (h_ <= 64)) | ((w_ <= 64) & (h_ <= 32)))
+            print(f"[{tag}] view {v} level {l}: tiles {w_.numel()}, on tensor cores {float(fit.float().mean()):.2f}; median box {int(w_[valid].median())} x {int(h_[valid].median())}, "
+                  f"p90 {int(w_[valid].float().quantile(0.9))} x {int(h_[valid].float().quantile(0.9))}")
+
+
+def main():
+    B, h, w, C = 1, 64, 128, 256
+    g = torch.Generator(device="cuda").manual_seed(0)
+    fm = [torch.randn(B, C, h, w, device="cuda", generator=g) * 1.45 for _ in range(4)]
+    Ra, Rb = TO.rotation_matrix([0., 0., -np.pi / 2], device="cuda"), TO.rotation_matrix([0., 0., np.pi / 2], device="cuda")
+    gw, gc = TO.generate_samplegrid((B, 3, h, w), Ra.T.contiguous()), TO.generate_samplegrid((B, 3, h, w), Rb)
+    cl = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    f1a, f2a, f1b, f2b = cl(fm[0]), ops.channels_last_pyramid(fm[1], 4), cl(fm[2]), ops.channels_last_pyramid(fm[3], 4)
+    pla, plb = ops.OnTheFlyPlanes(f1a, f2a), ops.OnTheFlyPlanes(f1b, f2b)
+    grid = TO.coords_grid(B, h, w, "cuda")
+    report("zero flow", grid, f1a, f2a, f1b, f2b, gw, gc, pla, plb)
+    low = torch.randn(B, 2, h // 8, w // 8, device="cuda", generator=g) * 5
+    report("smooth 5px/8", grid + torch.nn.functional.interpolate(low, size=(h, w), mode="bicubic", align_corners=True), f1a, f2a, f1b, f2b, gw, gc, pla, plb)
+    low = torch.randn(B, 2, h // 16, w // 16, device="cuda", generator=g) * 3
+    report("smooth 3px/16", grid + torch.nn.functional.interpolate(low, size=(h, w), mode="bicubic", align_corners=True), f1a, f2a, f1b, f2b, gw, gc, pla, plb)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,7 +39,7 @@ def test_struct_layouts_match_header(tmp_path):
     import ctypes as C
     import subprocess
     structs = {"pf_volume_args": _lib.VolumeArgs, "pf_lookup_args": _lib.LookupArgs, "pf_onthefly_args": _lib.OnTheFlyArgs,
-               "pf_remap_args": _lib.RemapArgs, "pf_lookup_bwd_args": _lib.LookupBwdArgs}
+               "pf_remap_args": _lib.RemapArgs, "pf_lookup_bwd_args": _lib.LookupBwdArgs, "pf_onthefly_tc_args": _lib.OnTheFlyTcArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "priorcorr.h"', 'int main(void) {']
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
