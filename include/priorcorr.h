@@ -158,14 +158,15 @@ typedef struct pf_onthefly_args {
 int pf_lookup_onthefly(const pf_onthefly_args *args, void *stream);
 /*
  * (c') The same lookup with the dot products on tcgen05 tensor cores (pf_onthefly_tc.cu).  Per tile of 8 x 16 queries the
- * bounding box of all taps is found first; tiles whose box fits 32 columns x 64 rows or 64 columns x 32 rows of target pixels
- * get a dense [128 x box] contraction of pre-split fp16 hi/lo planes (three products, fp32 accumulation: the volume kernel's
- * numerics) written to a per-query "local plane" of 2048 floats (O(N) scratch: 8 KiB per query, level and view), other tiles
- * keep the CUDA-core path.  Windows across the ERP seam stay on the tensor-core path: the target planes are stored twice side
+ * bounding box of all taps is found first; tiles whose box fits the level's "local plane" (PF_OTF_PLANE(l) target pixels at a
+ * pitch of 32, 64 or 128 columns) get a dense [128 x box] contraction of pre-split fp16 hi/lo planes (three products, fp32
+ * accumulation: the volume kernel's numerics) written to per-query planes (O(N) scratch: 32 KiB per query and view over four
+ * levels), other tiles keep the CUDA-core path.  Windows across the ERP seam stay on the tensor-core path: the target planes are stored twice side
  * by side.  Restrictions: radius 4, cyclic, h % 8 == 0, w % 16 == 0, channels % 128 == 0.  Prepare the planes once per pyramid:
  *   zero the view's two `amax` words; pf_onthefly_absmax(fmap1, .., amax); pf_onthefly_absmax(fmap2 level 0, .., amax + 1);
  *   pf_onthefly_split(fmap1, .., amax, hi, lo, 0); pf_onthefly_split(fmap2 level l, .., amax + 1, hi_l, lo_l, (w>>l) * C).
  */
+#define PF_OTF_PLANE(l) ((l) == 0 ? 4096 : ((l) == 1 ? 2048 : 1024))
 typedef struct pf_onthefly_tc_args {
   pf_onthefly_args base;                      /* fp32 operands and outputs exactly as for pf_lookup_onthefly       */
   const void *f1_hi_own, *f1_lo_own;          /* [B, h, w, C] fp16 planes of fmap1_own                             */
@@ -173,9 +174,10 @@ typedef struct pf_onthefly_tc_args {
   const void *f1_hi_other, *f1_lo_other;
   const void *f2_hi_other[PF_MAX_LEVELS], *f2_lo_other[PF_MAX_LEVELS];
   const void *amax_own, *amax_other;          /* uint32[2] per view: absmax bits of {fmap1, fmap2 level 0}          */
-  float *mini_own[PF_MAX_LEVELS];             /* scratch [B, h, w, 2048] fp32 per level                            */
+  float *mini_own[PF_MAX_LEVELS];             /* scratch [B, h, w, PF_OTF_PLANE(l)] fp32 per level                 */
   float *mini_other[PF_MAX_LEVELS];
   int *box_lo, *box_hi;                       /* scratch int[views * L * B * (h/8) * (w/16) * 4] each, 16-B aligned */
+  int *worklist;                              /* scratch int[4 + views * L * B * (h/8) * (w/16)]                   */
 } pf_onthefly_tc_args;
 int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *args, void *stream);
 int pf_onthefly_absmax(const float *x, long long count, void *amax_word, void *stream);

@@ -6,11 +6,11 @@
 // dense contraction per TILE of queries:
 //   otf_box_kernel    per query: the sampler's coordinate chain (bit-exact, shared with the blend below) and the integer
 //                     bounding box of its taps; atomically merged into the box of its 8 x 16 query tile
-//   otf_dots_kernel   per tile whose box fits (<= 32 columns x 64 rows, or <= 64 columns x 32 rows of target pixels):
+//   otf_dots_kernel   per tile whose box fits the level's local plane at a pitch of 32, 64 or 128 columns (level 0: 4096 pixels):
 //                     D[128 queries, box] = F1[tile] . F2_l[box]^T on tcgen05 — both operands are TMA boxes of pre-split fp16
 //                     hi/lo K-major planes ([B, h, w, C], the channels-last convention of `alt_cuda_corr`), three products into
-//                     fp32 TMEM like the volume kernel, written to a per-query local plane of 2048 floats ("mini volume": O(N)
-//                     memory) with TMA stores
+//                     fp32 TMEM like the volume kernel, written to a per-query local plane ("mini volume": 32 KiB per query and
+//                     view over the four levels, O(N) memory), one full 128-byte line per thread and box row segment
 //   otf_blend_kernel  per query: the taps blend from its slice of the local plane in ATen's order; tiles whose box does not fit
 //                     (poles of the rotation map, wild flow) keep the r01 CUDA-core path, query by query, inside the same kernel
 // The ERP seam: the sampler wraps x, so a window across the seam touches columns at both ends of the plane.  Boxes are therefore
@@ -27,20 +27,19 @@
 namespace pf {
 
 constexpr int OT_TH = 8, OT_TW = 16;                 // query tile: 8 rows x 16 columns = 128 queries = TMEM lanes
-constexpr int OT_PLANE = 2048;                       // local plane per query: 64 rows x 32 columns or 32 rows x 64 columns
-constexpr int OT_MAXCHUNKS = 8;                      // MMA passes per tile: 256 accumulator columns (8 x 32 or 4 x 64 box pixels) each
+// local plane per query and level (floats), see PF_OTF_PLANE in priorcorr.h: level 0 holds 32 x 128, 64 x 64 or 128 x 32 box pixels
+__host__ __device__ constexpr int ot_plane(int lvl) { return PF_OTF_PLANE(lvl); }
 constexpr int OT_BK = 64;
 constexpr int OT_APLANE = 128 * OT_BK * 2;           // 16 KiB
 constexpr int OT_BPLANE = 256 * OT_BK * 2;           // 32 KiB
 constexpr int OT_STAGE = 2 * (OT_APLANE + OT_BPLANE);   // hi + lo: 96 KiB
 constexpr int OT_STAGES = 2;
-constexpr int OT_OUT = 128 * 32 * 4;                 // 16 KiB staging for one box row of all queries
 constexpr int OT_THREADS = 192;                      // TMA warp, MMA warp, 4 epilogue warps
-constexpr int OT_SMEM = OT_STAGES * OT_STAGE + OT_OUT + 256 + 1024;
-constexpr uint32_t OT_IDESC = umma_idesc_f16(128, 256);
+constexpr int OT_OUT = 128 * 32 * 4;                 // 16 KiB staging for one box-row segment of all queries, two of them
+constexpr int OT_SMEM = OT_STAGES * OT_STAGE + 2 * OT_OUT + 256 + 1024;
 
-constexpr int kBlendThreads = 128;
-constexpr int kBlendQueries = 8;
+constexpr int kBlendThreads = 256;
+constexpr int kBlendQueries = 16;    // one row of a query tile
 constexpr int kBoxDots = 324;    // per-query boxes up to 4 dots per tap are evaluated as a plane, larger ones tap by tap
 constexpr int kMaxBox = kBoxDots;
 constexpr int kMaxTaps = 81;
@@ -56,7 +55,8 @@ struct OtfTcParams {
   long long grid_bs;
   float scale;                             // 1 / sqrt(C)
   int *box_lo, *box_hi;                    // [2 views][L][B][tiles][4]: (u0, u1, y, -) min / max of the tile's taps
-  float *mini[2][PF_MAX_LEVELS];           // [B, h, w, 2048] local planes
+  int *work;                               // [0] count, [1] cursor, [4 ...] tiles for the CUDA-core path: ((view * L + lvl) * B + b) * tiles + tile
+  float *mini[2][PF_MAX_LEVELS];           // [B, h, w, ot_plane(l)] local planes
   const uint32_t *amax[2];                 // per view: absmax bits of {f1, f2} (split scales of the fp16 planes)
   float *out_own, *out_raw;
 };
@@ -75,22 +75,41 @@ __device__ __forceinline__ float ot_split_scale(uint32_t amax_bits) {
   return __uint_as_float((uint32_t)(se + 127) << 23);
 }
 
-// The sampler's coordinates of tap t of query n (identical to pf_onthefly.cu / lookup_kernel): returns (ix, iy).
-__device__ __forceinline__ void otf_tap_coords(const OtfTcParams &p, int branch, int lvl, float cx, float cy, int t, const float *gridx,
-                                               const float *gridy, const Axis axW, const Axis axH, const Axis ax_gw, const Axis ax_gh,
-                                               float &ix, float &iy) {
-  const int aa = t / 9, bb = t - aa * 9;
-  const float px = __fadd_rn(cx, (float)(aa - 4)), py = __fadd_rn(cy, (float)(bb - 4));
-  float sx = px, sy = py;
-  if (branch) {
-    const float gx = to_sample_coord(remainder_pos(px, ax_gw.size), ax_gw, p.div_mode);
-    const float gy = to_sample_coord(py, ax_gh, p.div_mode);
-    const Taps tg = make_taps(gx, gy);
-    sx = blend_zeros(gridx, p.h, p.w, tg);
-    sy = blend_zeros(gridy, p.h, p.w, tg);
+// The sampler's coordinates (ix, iy) of all 81 taps of the CTA's 8 queries, same arithmetic as pf_onthefly.cu / lookup_kernel.  The
+// chains separate by axis — x depends on the tap's column offset only, y on its row offset — so step 1 evaluates 18 chains per
+// query (own view: the final coordinates; other view: the coordinates into the rotation grid) and step 2 visits the 81 taps
+// (other view: the two grid samples and the final chains).  `use(q, t, ix, iy)` consumes a tap.  Contains one __syncthreads.
+template <class F>
+__device__ __forceinline__ void cta_tap_coords(const OtfTcParams &p, int branch, int lvl, int b, int n0, float *s_axis /*[8][18]*/, F use) {
+  const Axis axW = p.axW[lvl], axH = p.axH[lvl], ax_gw = p.ax_gw, ax_gh = p.ax_gh;
+  const float inv_scale = 1.0f / (float)(1 << lvl);
+  for (int i = threadIdx.x; i < kBlendQueries * 18; i += kBlendThreads) {
+    const int q = i / 18, j = i - q * 18, n = n0 + q;
+    if (n >= p.N) continue;
+    const bool xaxis = j < 9;
+    const float c = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + (xaxis ? 0 : 1)) * p.N + n), inv_scale);
+    const float pv = __fadd_rn(c, (float)((xaxis ? j : j - 9) - 4));
+    float v;
+    if (branch)
+      v = xaxis ? to_sample_coord(remainder_pos(pv, ax_gw.size), ax_gw, p.div_mode) : to_sample_coord(pv, ax_gh, p.div_mode);
+    else
+      v = xaxis ? to_sample_coord(remainder_pos(pv, axW.size), axW, p.div_mode) : to_sample_coord(pv, axH, p.div_mode);
+    s_axis[i] = v;
   }
-  ix = to_sample_coord(remainder_pos(sx, axW.size), axW, p.div_mode);
-  iy = to_sample_coord(sy, axH, p.div_mode);
+  __syncthreads();
+  const float *gridx = p.grid_w2c ? p.grid_w2c + (long long)b * p.grid_bs : nullptr, *gridy = gridx ? gridx + p.N : nullptr;
+  for (int i = threadIdx.x; i < kBlendQueries * kMaxTaps; i += kBlendThreads) {
+    const int q = i / kMaxTaps, t = i - q * kMaxTaps, aa = t / 9, bb = t - aa * 9;
+    if (n0 + q >= p.N) continue;
+    float ix = s_axis[q * 18 + aa], iy = s_axis[q * 18 + 9 + bb];
+    if (branch) {
+      const Taps tg = make_taps(ix, iy);
+      const float sx = blend_zeros(gridx, p.h, p.w, tg), sy = blend_zeros(gridy, p.h, p.w, tg);
+      ix = to_sample_coord(remainder_pos(sx, axW.size), axW, p.div_mode);
+      iy = to_sample_coord(sy, axH, p.div_mode);
+    }
+    use(q, t, ix, iy);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ boxes
@@ -112,27 +131,32 @@ __device__ __forceinline__ void box_add_tap(int *s_box, int x0, int y0, int Wl, 
     atomicMax(&s_box[5], min(y0 + 1, Hl - 1));
   }
 }
+// The same for a whole (converged or not) warp into ONE box: reduce across the active lanes first, one lane does the atomics.
+__device__ __forceinline__ void box_add_tap_warp(int *s_box, int x0, int y0, int Wl, int Hl) {
+  const unsigned active = __activemask();
+  int v[6] = {INT_MAX, INT_MIN, INT_MAX, INT_MIN, INT_MAX, INT_MIN};
+  if (x0 + 1 >= 0 && x0 < Wl && y0 + 1 >= 0 && y0 < Hl) {
+    const int xa = max(x0, 0), xb = min(x0 + 1, Wl - 1);
+    const int ua = unwrap1(xa, Wl), ub = unwrap1(xb, Wl);
+    v[0] = xa, v[1] = xb, v[2] = min(ua, ub), v[3] = max(ua, ub), v[4] = max(y0, 0), v[5] = min(y0 + 1, Hl - 1);
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i += 2) v[i] = __reduce_min_sync(active, v[i]), v[i + 1] = __reduce_max_sync(active, v[i + 1]);
+  if ((threadIdx.x & 31) == (__ffs(active) - 1) && v[4] <= v[5]) {
+#pragma unroll
+    for (int i = 0; i < 6; i += 2) atomicMin(&s_box[i], v[i]), atomicMax(&s_box[i + 1], v[i + 1]);
+  }
+}
 
 __global__ void __launch_bounds__(kBlendThreads) otf_box_kernel(const OtfTcParams p) {
   __shared__ int s_box[6];
+  __shared__ float s_axis[kBlendQueries * 18];
   const int lvl = blockIdx.y % p.L, branch = blockIdx.y / p.L, b = blockIdx.z;
   const int Hl = p.h >> lvl, Wl = p.w >> lvl;
-  const Axis axW = p.axW[lvl], axH = p.axH[lvl], ax_gw = p.ax_gw, ax_gh = p.ax_gh;
-  const float inv_scale = 1.0f / (float)(1 << lvl);
-  const float *gridx = p.grid_w2c ? p.grid_w2c + (long long)b * p.grid_bs : nullptr, *gridy = gridx ? gridx + p.N : nullptr;
   const int n0 = blockIdx.x * kBlendQueries;
   // the 8 queries of a CTA are consecutive in a row and 8 | 16: they share the tile
   if (threadIdx.x == 0) box_reset(s_box);
-  __syncthreads();
-  for (int i = threadIdx.x; i < kBlendQueries * kMaxTaps; i += kBlendThreads) {
-    const int q = i / kMaxTaps, t = i - q * kMaxTaps, n = n0 + q;
-    if (n >= p.N) break;
-    const float cx = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + 0) * p.N + n), inv_scale);
-    const float cy = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + 1) * p.N + n), inv_scale);
-    float ix, iy;
-    otf_tap_coords(p, branch, lvl, cx, cy, t, gridx, gridy, axW, axH, ax_gw, ax_gh, ix, iy);
-    box_add_tap(s_box, (int)floorf(ix), (int)floorf(iy), Wl, Hl);
-  }
+  cta_tap_coords(p, branch, lvl, b, n0, s_axis, [&](int, int, float ix, float iy) { box_add_tap_warp(s_box, (int)floorf(ix), (int)floorf(iy), Wl, Hl); });
   __syncthreads();
   if (threadIdx.x < 3 && s_box[4] <= s_box[5]) {
     int tiles_x;
@@ -144,22 +168,24 @@ __global__ void __launch_bounds__(kBlendThreads) otf_box_kernel(const OtfTcParam
   }
 }
 
-// The tile's box: which numbering (mode), origin, rows, and the local-plane pitch (32 or 64 columns).
+// The tile's box: which numbering (mode), origin, rows, and the local-plane pitch (32, 64 or 128 columns).
 struct TileBox {
   int mode, X0, Y0, rows, pitch;
+  bool empty;      // no tap of the tile touches the plane: the outputs are zero
 };
 __device__ __forceinline__ bool tile_box(const OtfTcParams &p, int branch, int lvl, int b, int tile, int tiles, TileBox &tb) {
   const long long e = ((((long long)branch * p.L + lvl) * p.B + b) * tiles + tile) * 4;
   const int4 lo = *reinterpret_cast<const int4 *>(p.box_lo + e), hi = *reinterpret_cast<const int4 *>(p.box_hi + e);
-  if (lo.z > hi.z || lo.x > hi.x) return false;
+  tb.empty = lo.z > hi.z || lo.x > hi.x;
+  if (tb.empty) return false;
   const int w0 = hi.x - lo.x + 1, w1 = hi.y - lo.y + 1;
   tb.mode = w1 < w0 ? 1 : 0;
   const int bw = tb.mode ? w1 : w0;
   tb.X0 = tb.mode ? lo.y : lo.x;
   tb.Y0 = lo.z;
   tb.rows = hi.z - lo.z + 1;
-  tb.pitch = bw <= 32 ? 32 : 64;
-  return bw <= 64 && tb.rows * tb.pitch <= OT_PLANE;
+  tb.pitch = bw <= 32 ? 32 : (bw <= 64 ? 64 : 128);
+  return bw <= 128 && tb.rows * tb.pitch <= ot_plane(lvl);
 }
 
 // ------------------------------------------------------------------------------------------------ dots (tcgen05)
@@ -169,25 +195,34 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, uint32_t sr
                : "memory");
 }
 
-struct OtfMaps {
+struct OtfViewMaps {
   CUtensorMap f1_hi, f1_lo;                                    // [C, w, h, B] fp16, box {64, 16, 8, 1}
-  CUtensorMap f2_hi[2][PF_MAX_LEVELS], f2_lo[2][PF_MAX_LEVELS];   // [C, 2 Wl, Hl, B] fp16, box {64, 32, 8, 1} / {64, 64, 4, 1}
-  CUtensorMap out[2][PF_MAX_LEVELS];                           // [32, 64, w, h, B] / [64, 32, w, h, B] fp32, box {32, 1, 16, 8, 1}
+  CUtensorMap f2_hi[3][PF_MAX_LEVELS], f2_lo[3][PF_MAX_LEVELS];   // [C, 2 Wl, Hl, B] fp16, box {64, pitch, 256 / pitch, 1}, pitch 32 / 64 / 128
+  CUtensorMap out[3][PF_MAX_LEVELS];                           // [pitch, plane / pitch, w, h, B] fp32, box {32, 1, 16, 8, 1}
+};
+struct OtfMaps {
+  OtfViewMaps view[2];     // ~10 KiB of kernel parameters (CUDA 12.1+: up to 32 KiB)
 };
 
-__global__ void __launch_bounds__(OT_THREADS, 1) otf_dots_kernel(const __grid_constant__ OtfMaps maps, const OtfTcParams p, const int branch) {
-  const int tile = blockIdx.x, lvl = blockIdx.y, b = blockIdx.z;
+__global__ void __launch_bounds__(OT_THREADS, 1) otf_dots_kernel(const __grid_constant__ OtfMaps all_maps, const OtfTcParams p) {
+  // the other view first (its boxes are the large ones), fine levels first
+  const int tile = blockIdx.x, lvl = blockIdx.y % p.L, branch = (gridDim.y / p.L) - 1 - blockIdx.y / p.L, b = blockIdx.z;
+  const OtfViewMaps &maps = all_maps.view[branch];
   const int tiles_x = p.w / OT_TW, tiles = tiles_x * (p.h / OT_TH);
   TileBox tb;
-  if (!tile_box(p, branch, lvl, b, tile, tiles, tb)) return;      // uniform: the blend kernel takes the CUDA-core path for this tile
-  const int wide = tb.pitch == 64, rpc = 256 / tb.pitch;          // box rows per MMA pass
+  if (!tile_box(p, branch, lvl, b, tile, tiles, tb)) {             // uniform
+    // boxes that do not fit a local plane go on the work list of otf_fallback_kernel (CUDA cores)
+    if (!tb.empty && threadIdx.x == 0) p.work[4 + atomicAdd(p.work, 1)] = ((branch * p.L + lvl) * p.B + b) * tiles + tile;
+    return;
+  }
+  const int wide = tb.pitch >> 6, rpc = 256 / tb.pitch;           // pitch 32 / 64 / 128 -> map 0 / 1 / 2; box rows per MMA pass
   const int nchunks = (tb.rows + rpc - 1) / rpc, X0 = tb.X0, Y0 = tb.Y0;
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *out_stage = smem + OT_STAGES * OT_STAGE;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(out_stage + OT_OUT);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(out_stage + 2 * OT_OUT);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + OT_STAGES);
   const uint32_t bar_tfull = smem_u32(bars + 2 * OT_STAGES), bar_tempty = smem_u32(bars + 2 * OT_STAGES + 2);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * OT_STAGES + 4);
@@ -234,6 +269,8 @@ __global__ void __launch_bounds__(OT_THREADS, 1) otf_dots_kernel(const __grid_co
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * 256;
+        const int ncols = min(256, (tb.rows - c * rpc) * tb.pitch);       // the last pass needs only the box rows that are left
+        const uint32_t idesc = umma_idesc_f16(128, ncols);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
@@ -241,11 +278,11 @@ __global__ void __launch_bounds__(OT_THREADS, 1) otf_dots_kernel(const __grid_co
           const uint64_t a_hi = make_smem_desc(sbase), b_hi = make_smem_desc(sbase + OT_APLANE);
           const uint64_t a_lo = make_smem_desc(sbase + OT_APLANE + OT_BPLANE), b_lo = make_smem_desc(sbase + 2 * OT_APLANE + OT_BPLANE);
 #pragma unroll
-          for (int k = 0; k < OT_BK / 16; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, OT_IDESC, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < OT_BK / 16; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, (kb | k) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < OT_BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, OT_IDESC, 1u);
+          for (int k = 0; k < OT_BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
 #pragma unroll
-          for (int k = 0; k < OT_BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, OT_IDESC, 1u);
+          for (int k = 0; k < OT_BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
           umma_commit(bar_empty + 8 * stage);
           if (++stage == OT_STAGES) stage = 0, phase ^= 1;
         }
@@ -255,12 +292,13 @@ __global__ void __launch_bounds__(OT_THREADS, 1) otf_dots_kernel(const __grid_co
     }
   } else {
     // epilogue: 4 warps, TMEM lane = query of the tile (rx fastest), columns = box pixels of the pass in segments of 32:
-    // segment g = box row g / (pitch / 32), columns 32 (g % (pitch / 32)) ...; one TMA store per segment into the local planes
+    // segment g = box row g / (pitch / 32), columns 32 (g % (pitch / 32)) ...; one TMA store per segment scatters the 128 rows of
+    // the staging buffer into the 128 local planes (two staging buffers: a store drains while the next segment is staged)
     const int quarter = warp & 3, row = quarter * 32 + lane;
     const bool leader = threadIdx.x == 64;
     const float scale = p.scale / (ot_split_scale(p.amax[branch][0]) * ot_split_scale(p.amax[branch][1]));
     const int spr = tb.pitch >> 5;   // segments per box row
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, buf = 0;
     for (int c = 0; c < nchunks; ++c) {
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
@@ -281,10 +319,11 @@ __global__ void __launch_bounds__(OT_THREADS, 1) otf_dots_kernel(const __grid_co
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         }
-        if (leader) tma_store_wait_read0();
+        if (leader) tma_store_wait_read1();      // the store issued from this buffer two segments ago has read it
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint8_t *stage = out_stage + buf * OT_OUT;
         {
-          uint8_t *r0 = out_stage + row * 128;
+          uint8_t *r0 = stage + row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4 *>(r0 + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -292,9 +331,10 @@ __global__ void __launch_bounds__(OT_THREADS, 1) otf_dots_kernel(const __grid_co
         fence_async_smem();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (leader) {
-          tma_store_5d(&maps.out[wide][lvl], smem_u32(out_stage), (g % spr) * 32, c * rpc + g / spr, tx * OT_TW, ty * OT_TH, b);
+          tma_store_5d(&maps.out[wide][lvl], smem_u32(stage), (g % spr) * 32, c * rpc + g / spr, tx * OT_TW, ty * OT_TH, b);
           tma_store_commit();
         }
+        buf ^= 1;
       }
       if ((acc ^= 1) == 0) acc_phase ^= 1;
     }
@@ -346,128 +386,10 @@ __device__ __forceinline__ float ot_dot4(const float *const (&ptr)[4], const flo
   return r;
 }
 
-__global__ void __launch_bounds__(kBlendThreads) otf_blend_kernel(const OtfTcParams p) {
-  __shared__ float s_ix[kMaxTaps], s_iy[kMaxTaps];
-  __shared__ float s_dots[kMaxBox];
-  __shared__ float s_out[kMaxTaps][kBlendQueries + 1];
-  __shared__ int s_box[6];
+// s_out [tap][query] -> own view: [K2][8 queries] = 32-byte row segments of the [B, L*K2, N] output; other view: channels-last
+// [B, N, L*K2] pre-rotation map (contiguous per query), see pf_lookup.cu
+__device__ __forceinline__ void write_taps(const OtfTcParams &p, const float (*s_out)[kBlendQueries + 1], int branch, int lvl, int b, int n0) {
   constexpr int K2 = kMaxTaps;
-  // the other view first: its CUDA-core tiles (poles of the rotation map) are the long CTAs and must not start last
-  const int by = gridDim.y - 1 - blockIdx.y;
-  const int lvl = by % p.L, branch = by / p.L, b = blockIdx.z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int Hl = p.h >> lvl, Wl = p.w >> lvl;
-  const Axis axW = p.axW[lvl], axH = p.axH[lvl], ax_gw = p.ax_gw, ax_gh = p.ax_gh;
-  const float inv_scale = 1.0f / (float)(1 << lvl);
-  const float *gridx = p.grid_w2c ? p.grid_w2c + (long long)b * p.grid_bs : nullptr, *gridy = gridx ? gridx + p.N : nullptr;
-  const float *f2 = p.f2[branch][lvl] + (long long)b * Hl * Wl * p.C;
-  const float *mini = p.mini[branch][lvl] + (long long)b * p.N * OT_PLANE;
-  const int nvec = p.C / 128;
-  const int n0 = blockIdx.x * kBlendQueries;
-  int tiles_x;
-  const int tile = tile_of(n0, p.w, tiles_x);          // the CTA's 8 queries share the tile
-  TileBox tb;
-  const bool tile_tc = tile_box(p, branch, lvl, b, tile, tiles_x * (p.h / OT_TH), tb);
-
-  for (int q = 0; q < kBlendQueries; ++q) {
-    const int n = n0 + q;
-    if (n >= p.N) break;
-    if (threadIdx.x == 0) box_reset(s_box);
-    __syncthreads();
-    const float cx = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + 0) * p.N + n), inv_scale);
-    const float cy = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + 1) * p.N + n), inv_scale);
-    for (int t = threadIdx.x; t < K2; t += kBlendThreads) {
-      float ix, iy;
-      otf_tap_coords(p, branch, lvl, cx, cy, t, gridx, gridy, axW, axH, ax_gw, ax_gh, ix, iy);
-      s_ix[t] = ix, s_iy[t] = iy;
-      box_add_tap(s_box, (int)floorf(ix), (int)floorf(iy), Wl, Hl);
-    }
-    __syncthreads();
-    const bool empty = s_box[4] > s_box[5];
-    const bool tc = tile_tc && !empty;                                        // block-uniform
-    const int mode = tc ? tb.mode : 0;
-    const int x_lo = s_box[0], x_hi = s_box[1], y_lo = s_box[4], y_hi = s_box[5];      // the CUDA-core path works in plain columns
-    const int bw = empty ? 0 : x_hi - x_lo + 1, bh = empty ? 0 : y_hi - y_lo + 1;
-    const int area = bw * bh;
-    if (tc) {
-      // the tile's dots are in this query's local plane (otf_dots_kernel); a tap reads its four corners from it
-      const float *m = mini + (long long)n * OT_PLANE;
-      for (int t = threadIdx.x; t < K2; t += kBlendThreads) {
-        const Taps tp = make_taps(s_ix[t], s_iy[t]);
-        const bool xin0 = (unsigned)tp.x0 < (unsigned)Wl, xin1 = (unsigned)(tp.x0 + 1) < (unsigned)Wl;
-        const bool yin0 = (unsigned)tp.y0 < (unsigned)Hl, yin1 = (unsigned)(tp.y0 + 1) < (unsigned)Hl;
-        // column of the west corner in the box's numbering (mode 1: unwrapped); the east corner is the next column — a tap
-        // whose corners straddle the numbering's cut would have made the box as wide as the plane, and then mode 0 is chosen
-        const int ux = (mode && xin0) ? unwrap1(tp.x0, Wl) : ((mode && xin1) ? unwrap1(tp.x0 + 1, Wl) - 1 : tp.x0);
-        const float *c0 = m + (tp.y0 - tb.Y0) * tb.pitch + (ux - tb.X0);
-        const float v_nw = (yin0 && xin0) ? __ldg(c0) : 0.f;
-        const float v_ne = (yin0 && xin1) ? __ldg(c0 + 1) : 0.f;
-        const float v_sw = (yin1 && xin0) ? __ldg(c0 + tb.pitch) : 0.f;
-        const float v_se = (yin1 && xin1) ? __ldg(c0 + tb.pitch + 1) : 0.f;
-        float acc = __fmul_rn(v_nw, tp.nw);
-        acc = __fmaf_rn(v_ne, tp.ne, acc);
-        acc = __fmaf_rn(v_sw, tp.sw, acc);
-        acc = __fmaf_rn(v_se, tp.se, acc);
-        s_out[t][q] = acc;
-      }
-    } else {
-      float4 qv[kMaxVec];
-      const float4 *f1v = reinterpret_cast<const float4 *>(p.f1[branch] + ((long long)b * p.N + n) * p.C);
-#pragma unroll
-      for (int j = 0; j < kMaxVec; ++j) qv[j] = (j < nvec) ? __ldg(f1v + j * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (area <= kBoxDots) {
-        // the plane on the query's own box (fewer dot products than four per tap), four pixels per warp step
-        for (int pix = warp * 4; pix < area; pix += kBlendThreads / 8) {
-          const float *ptr[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int pc = pix + c, yy = pc / bw, xx = pc - yy * bw;
-            ptr[c] = pc < area ? f2 + ((long long)(y_lo + yy) * Wl + (x_lo + xx)) * p.C : nullptr;
-          }
-          const float d = ot_dot4(ptr, qv, nvec, lane);
-          if ((lane & 7) == 0 && pix + (lane >> 3) < area) s_dots[pix + (lane >> 3)] = d * p.scale;
-        }
-        __syncthreads();
-        for (int t = threadIdx.x; t < K2; t += kBlendThreads) {
-          const Taps tp = make_taps(s_ix[t], s_iy[t]);
-          const bool xin0 = (unsigned)tp.x0 < (unsigned)Wl, xin1 = (unsigned)(tp.x0 + 1) < (unsigned)Wl;
-          const bool yin0 = (unsigned)tp.y0 < (unsigned)Hl, yin1 = (unsigned)(tp.y0 + 1) < (unsigned)Hl;
-          const int base = (tp.y0 - y_lo) * bw + (tp.x0 - x_lo);
-          const float v_nw = (yin0 && xin0) ? s_dots[base] : 0.f;
-          const float v_ne = (yin0 && xin1) ? s_dots[base + 1] : 0.f;
-          const float v_sw = (yin1 && xin0) ? s_dots[base + bw] : 0.f;
-          const float v_se = (yin1 && xin1) ? s_dots[base + bw + 1] : 0.f;
-          float acc = __fmul_rn(v_nw, tp.nw);
-          acc = __fmaf_rn(v_ne, tp.ne, acc);
-          acc = __fmaf_rn(v_sw, tp.sw, acc);
-          acc = __fmaf_rn(v_se, tp.se, acc);
-          s_out[t][q] = acc;
-        }
-      } else {
-        // large boxes (poles of the rotation map, windows across the seam): a warp per tap, its four corners in one step
-        for (int t = warp; t < K2; t += kBlendThreads / 32) {
-          const Taps tp = make_taps(s_ix[t], s_iy[t]);
-          const float *ptr[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int xx = tp.x0 + (c & 1), yy = tp.y0 + (c >> 1);
-            const bool in = (unsigned)xx < (unsigned)Wl && (unsigned)yy < (unsigned)Hl;
-            ptr[c] = in ? f2 + ((long long)yy * Wl + xx) * p.C : nullptr;
-          }
-          const float d = ot_dot4(ptr, qv, nvec, lane) * p.scale;
-          const float v1 = __shfl_sync(0xffffffffu, d, 8), v2 = __shfl_sync(0xffffffffu, d, 16), v3 = __shfl_sync(0xffffffffu, d, 24);
-          if (lane == 0) {
-            float acc = __fmul_rn(d, tp.nw);
-            acc = __fmaf_rn(v1, tp.ne, acc);
-            acc = __fmaf_rn(v2, tp.sw, acc);
-            acc = __fmaf_rn(v3, tp.se, acc);
-            s_out[t][q] = acc;
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
   if (branch == 0) {
     float *out = p.out_own + ((long long)b * p.L + lvl) * K2 * (long long)p.N + n0;
     for (int i = threadIdx.x; i < K2 * kBlendQueries; i += kBlendThreads) {
@@ -479,6 +401,169 @@ __global__ void __launch_bounds__(kBlendThreads) otf_blend_kernel(const OtfTcPar
       const int q = i / K2, ch = i - q * K2;
       if (n0 + q < p.N) p.out_raw[(((long long)b * p.N + n0 + q) * p.L + lvl) * K2 + ch] = s_out[ch][q];
     }
+  }
+}
+
+struct BlendCta {
+  int lvl, branch, b, n0, Hl, Wl;
+  TileBox tb;
+  bool tc;
+};
+__device__ __forceinline__ BlendCta blend_cta(const OtfTcParams &p) {
+  BlendCta c;
+  const int by = blockIdx.y;
+  c.lvl = by % p.L, c.branch = by / p.L, c.b = blockIdx.z;
+  c.Hl = p.h >> c.lvl, c.Wl = p.w >> c.lvl;
+  c.n0 = blockIdx.x * kBlendQueries;
+  int tiles_x;
+  const int tile = tile_of(c.n0, p.w, tiles_x);          // the CTA's 16 queries are one row of a tile
+  c.tc = tile_box(p, c.branch, c.lvl, c.b, tile, tiles_x * (p.h / OT_TH), c.tb);      // block-uniform
+  return c;
+}
+
+// Tiles on the tensor-core path: the tile's dots are in the queries' local planes (otf_dots_kernel); every tap reads its four
+// corners from there.  All 648 taps of the CTA are in flight together.
+__global__ void __launch_bounds__(kBlendThreads) otf_blend_kernel(const OtfTcParams p) {
+  __shared__ float s_axis[kBlendQueries * 18];
+  __shared__ float s_out[kMaxTaps][kBlendQueries + 1];
+  const BlendCta c = blend_cta(p);
+  if (!c.tc && !c.tb.empty) return;       // otf_fallback_kernel's
+  const int lvl = c.lvl, branch = c.branch, b = c.b, n0 = c.n0, Hl = c.Hl, Wl = c.Wl;
+  const TileBox tb = c.tb;
+  if (tb.empty) {
+    for (int i = threadIdx.x; i < kMaxTaps * (kBlendQueries + 1); i += kBlendThreads) (&s_out[0][0])[i] = 0.f;
+    __syncthreads();
+    write_taps(p, s_out, branch, lvl, b, n0);
+    return;
+  }
+  // the tile's dots are in the queries' local planes (otf_dots_kernel): every tap reads its four corners from there
+  const int plane = ot_plane(lvl);
+  const float *mini = p.mini[branch][lvl] + ((long long)b * p.N + n0) * plane;
+  cta_tap_coords(p, branch, lvl, b, n0, s_axis, [&](int q, int t, float ix, float iy) {
+    const Taps tp = make_taps(ix, iy);
+    const bool xin0 = (unsigned)tp.x0 < (unsigned)Wl, xin1 = (unsigned)(tp.x0 + 1) < (unsigned)Wl;
+    const bool yin0 = (unsigned)tp.y0 < (unsigned)Hl, yin1 = (unsigned)(tp.y0 + 1) < (unsigned)Hl;
+    // column of the west corner in the box's numbering (mode 1: unwrapped); the east corner is the next column — a tap
+    // whose corners straddle the numbering's cut would have made the box as wide as the plane, and then mode 0 is chosen
+    const int ux = (tb.mode && xin0) ? unwrap1(tp.x0, Wl) : ((tb.mode && xin1) ? unwrap1(tp.x0 + 1, Wl) - 1 : tp.x0);
+    const float *c0 = mini + (long long)q * plane + (tp.y0 - tb.Y0) * tb.pitch + (ux - tb.X0);
+    const float v_nw = (yin0 && xin0) ? __ldg(c0) : 0.f;
+    const float v_ne = (yin0 && xin1) ? __ldg(c0 + 1) : 0.f;
+    const float v_sw = (yin1 && xin0) ? __ldg(c0 + tb.pitch) : 0.f;
+    const float v_se = (yin1 && xin1) ? __ldg(c0 + tb.pitch + 1) : 0.f;
+    float acc = __fmul_rn(v_nw, tp.nw);
+    acc = __fmaf_rn(v_ne, tp.ne, acc);
+    acc = __fmaf_rn(v_sw, tp.sw, acc);
+    acc = __fmaf_rn(v_se, tp.se, acc);
+    s_out[t][q] = acc;
+  });
+  __syncthreads();
+  write_taps(p, s_out, branch, lvl, b, n0);
+}
+
+// Tiles whose box does not fit a local plane (the work list otf_dots_kernel wrote): the CUDA-core path of the r01 kernel, query
+// by query — the plane on the query's own box if that is fewer dot products than four per tap, else tap by tap.  Persistent: a
+// CTA takes (tile, row of 16 queries) items off the list until it is empty; these are the long items of the call.
+__global__ void __launch_bounds__(kBlendThreads) otf_fallback_kernel(const OtfTcParams p) {
+  __shared__ float s_ix[kBlendQueries * kMaxTaps], s_iy[kBlendQueries * kMaxTaps];
+  __shared__ float s_axis[kBlendQueries * 18];
+  __shared__ float s_dots[kMaxBox];
+  __shared__ float s_out[kMaxTaps][kBlendQueries + 1];
+  __shared__ int s_box[kBlendQueries][6];
+  __shared__ int s_item;
+  constexpr int K2 = kMaxTaps;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_x = p.w / OT_TW, tiles = tiles_x * (p.h / OT_TH);
+  const int items = p.work[0] * OT_TH;
+  for (;;) {
+  __syncthreads();
+  if (threadIdx.x == 0) s_item = atomicAdd(p.work + 1, 1);
+  __syncthreads();
+  const int item = s_item;
+  if (item >= items) return;
+  int e = p.work[4 + item / OT_TH];
+  const int tile = e % tiles;
+  e /= tiles;
+  const int b = e % p.B;
+  e /= p.B;
+  const int lvl = e % p.L, branch = e / p.L;
+  const int Hl = p.h >> lvl, Wl = p.w >> lvl;
+  const int n0 = ((tile / tiles_x) * OT_TH + item % OT_TH) * p.w + (tile % tiles_x) * OT_TW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CUDA-core path (the r01 kernel's): per query, the plane on its own box if that is fewer dot products than four per tap
+  if (threadIdx.x < kBlendQueries) box_reset(s_box[threadIdx.x]);
+  __syncthreads();       // (cta_tap_coords syncs once more before any tap is consumed)
+  cta_tap_coords(p, branch, lvl, b, n0, s_axis, [&](int q, int t, float ix, float iy) {
+    s_ix[q * K2 + t] = ix, s_iy[q * K2 + t] = iy;
+    box_add_tap(s_box[q], (int)floorf(ix), (int)floorf(iy), Wl, Hl);
+  });
+  __syncthreads();
+  const float *f2 = p.f2[branch][lvl] + (long long)b * Hl * Wl * p.C;
+  const int nvec = p.C / 128;
+  for (int q = 0; q < kBlendQueries; ++q) {
+    const int n = n0 + q;
+    if (n >= p.N) break;
+    const float *q_ix = s_ix + q * K2, *q_iy = s_iy + q * K2;
+    const int x_lo = s_box[q][0], x_hi = s_box[q][1], y_lo = s_box[q][4], y_hi = s_box[q][5];      // plain columns
+    const bool empty = y_lo > y_hi;
+    const int bw = empty ? 0 : x_hi - x_lo + 1, bh = empty ? 0 : y_hi - y_lo + 1;
+    const int area = bw * bh;
+    float4 qv[kMaxVec];
+    const float4 *f1v = reinterpret_cast<const float4 *>(p.f1[branch] + ((long long)b * p.N + n) * p.C);
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) qv[j] = (j < nvec) ? __ldg(f1v + j * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (area <= kBoxDots) {
+      for (int pix = warp * 4; pix < area; pix += kBlendThreads / 8) {       // four pixels per warp step
+        const float *ptr[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int pc = pix + c, yy = pc / bw, xx = pc - yy * bw;
+          ptr[c] = pc < area ? f2 + ((long long)(y_lo + yy) * Wl + (x_lo + xx)) * p.C : nullptr;
+        }
+        const float d = ot_dot4(ptr, qv, nvec, lane);
+        if ((lane & 7) == 0 && pix + (lane >> 3) < area) s_dots[pix + (lane >> 3)] = d * p.scale;
+      }
+      __syncthreads();
+      for (int t = threadIdx.x; t < K2; t += kBlendThreads) {
+        const Taps tp = make_taps(q_ix[t], q_iy[t]);
+        const bool xin0 = (unsigned)tp.x0 < (unsigned)Wl, xin1 = (unsigned)(tp.x0 + 1) < (unsigned)Wl;
+        const bool yin0 = (unsigned)tp.y0 < (unsigned)Hl, yin1 = (unsigned)(tp.y0 + 1) < (unsigned)Hl;
+        const int base = (tp.y0 - y_lo) * bw + (tp.x0 - x_lo);
+        const float v_nw = (yin0 && xin0) ? s_dots[base] : 0.f;
+        const float v_ne = (yin0 && xin1) ? s_dots[base + 1] : 0.f;
+        const float v_sw = (yin1 && xin0) ? s_dots[base + bw] : 0.f;
+        const float v_se = (yin1 && xin1) ? s_dots[base + bw + 1] : 0.f;
+        float acc = __fmul_rn(v_nw, tp.nw);
+        acc = __fmaf_rn(v_ne, tp.ne, acc);
+        acc = __fmaf_rn(v_sw, tp.sw, acc);
+        acc = __fmaf_rn(v_se, tp.se, acc);
+        s_out[t][q] = acc;
+      }
+    } else {
+      // large boxes (poles of the rotation map): a warp per tap, its four corners in one step
+      for (int t = warp; t < K2; t += kBlendThreads / 32) {
+        const Taps tp = make_taps(q_ix[t], q_iy[t]);
+        const float *ptr[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int xx = tp.x0 + (c & 1), yy = tp.y0 + (c >> 1);
+          const bool in = (unsigned)xx < (unsigned)Wl && (unsigned)yy < (unsigned)Hl;
+          ptr[c] = in ? f2 + ((long long)yy * Wl + xx) * p.C : nullptr;
+        }
+        const float d = ot_dot4(ptr, qv, nvec, lane) * p.scale;
+        const float v1 = __shfl_sync(0xffffffffu, d, 8), v2 = __shfl_sync(0xffffffffu, d, 16), v3 = __shfl_sync(0xffffffffu, d, 24);
+        if (lane == 0) {
+          float acc = __fmul_rn(d, tp.nw);
+          acc = __fmaf_rn(v1, tp.ne, acc);
+          acc = __fmaf_rn(v2, tp.sw, acc);
+          acc = __fmaf_rn(v3, tp.se, acc);
+          s_out[t][q] = acc;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  write_taps(p, s_out, branch, lvl, b, n0);
   }
 }
 
@@ -535,7 +620,7 @@ extern "C" int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *t, void *stream)
   PF_REQUIRE(a->channels % 128 == 0 && a->channels <= 512 && a->channels % OT_BK == 0, "pf_lookup_onthefly_tc: channels must be a multiple of 128, <= 512");
   PF_REQUIRE(a->h % OT_TH == 0 && a->w % OT_TW == 0, "pf_lookup_onthefly_tc: the query grid must tile by %dx%d (got %dx%d)", OT_TH, OT_TW, a->h, a->w);
   PF_REQUIRE(a->num_levels >= 1 && a->num_levels <= PF_MAX_LEVELS, "pf_lookup_onthefly_tc: num_levels must be 1..%d", PF_MAX_LEVELS);
-  PF_REQUIRE(a->coords && a->fmap1_own && a->out_own && t->box_lo && t->box_hi && t->amax_own, "pf_lookup_onthefly_tc: null pointer");
+  PF_REQUIRE(a->coords && a->fmap1_own && a->out_own && t->box_lo && t->box_hi && t->worklist && t->amax_own, "pf_lookup_onthefly_tc: null pointer");
   const bool dual = a->fmap1_other != nullptr;
   PF_REQUIRE(!dual || (a->grid_w2c && a->grid_c2w && a->out_other && a->scratch && t->amax_other), "pf_lookup_onthefly_tc: dual lookup needs grids, out_other, scratch");
   cudaStream_t st = (cudaStream_t)stream;
@@ -560,19 +645,22 @@ extern "C" int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *t, void *stream)
   p.ax_gw = make_axis(w), p.ax_gh = make_axis(h);
   p.grid_w2c = a->grid_w2c, p.grid_bs = a->grid_batch_stride;
   p.scale = 1.0f / sqrtf((float)C);
-  p.box_lo = t->box_lo, p.box_hi = t->box_hi;
+  p.box_lo = t->box_lo, p.box_hi = t->box_hi, p.work = t->worklist;
   p.amax[0] = reinterpret_cast<const uint32_t *>(t->amax_own), p.amax[1] = reinterpret_cast<const uint32_t *>(t->amax_other);
   p.out_own = a->out_own, p.out_raw = a->scratch;
   const size_t table = (size_t)views * L * B * tiles * 4 * sizeof(int);
-  if (cudaMemsetAsync(t->box_lo, 0x7f, table, st) != cudaSuccess || cudaMemsetAsync(t->box_hi, 0x80, table, st) != cudaSuccess)
+  if (cudaMemsetAsync(t->box_lo, 0x7f, table, st) != cudaSuccess || cudaMemsetAsync(t->box_hi, 0x80, table, st) != cudaSuccess ||
+      cudaMemsetAsync(t->worklist, 0, 4 * sizeof(int), st) != cudaSuccess)
     return check_launch("pf_lookup_onthefly_tc(memset)");
   const dim3 qgrid(ceil_div(N, kBlendQueries), L * views, B);
   otf_box_kernel<<<qgrid, kBlendThreads, 0, st>>>(p);
   if (int e = check_launch("pf_lookup_onthefly_tc(box)")) return e;
   cudaFuncSetAttribute(otf_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OT_SMEM);
-  for (int v = 0; v < views; ++v) {
-    OtfMaps m;
-    const void *f1_hi = v ? t->f1_hi_other : t->f1_hi_own, *f1_lo = v ? t->f1_lo_other : t->f1_lo_own;
+  OtfMaps maps;
+  for (int v = 0; v < 2; ++v) {
+    const int vv = v < views ? v : 0;     // single view: the unused half repeats view 0
+    OtfViewMaps &m = maps.view[v];
+    const void *f1_hi = vv ? t->f1_hi_other : t->f1_hi_own, *f1_lo = vv ? t->f1_lo_other : t->f1_lo_own;
     PF_REQUIRE(f1_hi && f1_lo, "pf_lookup_onthefly_tc: f1 planes missing");
     {
       cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
@@ -584,24 +672,27 @@ extern "C" int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *t, void *stream)
     for (int l = 0; l < PF_MAX_LEVELS; ++l) {
       const int ll = l < L ? l : 0;
       const int Hl = h >> ll, Wl = w >> ll;
-      const void *hi = v ? t->f2_hi_other[ll] : t->f2_hi_own[ll], *lo = v ? t->f2_lo_other[ll] : t->f2_lo_own[ll];
-      float *mini = v ? t->mini_other[ll] : t->mini_own[ll];
-      for (int wide = 0; wide < 2; ++wide) {
-        const int pitch = wide ? 64 : 32;
+      const void *hi = vv ? t->f2_hi_other[ll] : t->f2_hi_own[ll], *lo = vv ? t->f2_lo_other[ll] : t->f2_lo_own[ll];
+      for (int wi = 0; wi < 3; ++wi) {
+        const int pitch = 32 << wi;
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)(2 * Wl), (cuuint64_t)Hl, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)2 * Wl * C * 2, (cuuint64_t)Hl * 2 * Wl * C * 2};
         cuuint32_t box[4] = {OT_BK, (cuuint32_t)pitch, (cuuint32_t)(256 / pitch), 1};
-        if (int e = encode(&m.f2_hi[wide][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(hi), dims, strides, box, "otf f2.hi")) return e;
-        if (int e = encode(&m.f2_lo[wide][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(lo), dims, strides, box, "otf f2.lo")) return e;
-        cuuint64_t od[5] = {(cuuint64_t)pitch, (cuuint64_t)(OT_PLANE / pitch), (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
-        cuuint64_t os[4] = {(cuuint64_t)pitch * 4, (cuuint64_t)OT_PLANE * 4, (cuuint64_t)w * OT_PLANE * 4, (cuuint64_t)h * w * OT_PLANE * 4};
+        if (int e = encode(&m.f2_hi[wi][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(hi), dims, strides, box, "otf f2.hi")) return e;
+        if (int e = encode(&m.f2_lo[wi][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(lo), dims, strides, box, "otf f2.lo")) return e;
+        const int plane = ot_plane(ll);
+        float *mini = vv ? t->mini_other[ll] : t->mini_own[ll];
+        cuuint64_t od[5] = {(cuuint64_t)pitch, (cuuint64_t)(plane / pitch), (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+        cuuint64_t os[4] = {(cuuint64_t)pitch * 4, (cuuint64_t)plane * 4, (cuuint64_t)w * plane * 4, (cuuint64_t)h * w * plane * 4};
         cuuint32_t ob[5] = {32, 1, OT_TW, OT_TH, 1};
-        if (int e = encode(&m.out[wide][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, mini, od, os, ob, "otf mini")) return e;
+        if (int e = encode(&m.out[wi][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, mini, od, os, ob, "otf mini")) return e;
       }
     }
-    otf_dots_kernel<<<dim3(tiles, L, B), OT_THREADS, OT_SMEM, st>>>(m, p, v);
-    if (int e = check_launch("pf_lookup_onthefly_tc(dots)")) return e;
   }
+  otf_dots_kernel<<<dim3(tiles, L * views, B), OT_THREADS, OT_SMEM, st>>>(maps, p);
+  if (int e = check_launch("pf_lookup_onthefly_tc(dots)")) return e;
+  otf_fallback_kernel<<<2 * 148, kBlendThreads, 0, st>>>(p);
+  if (int e = check_launch("pf_lookup_onthefly_tc(fallback)")) return e;
   otf_blend_kernel<<<qgrid, kBlendThreads, 0, st>>>(p);
   if (int e = check_launch("pf_lookup_onthefly_tc(blend)")) return e;
   if (dual)

@@ -391,9 +391,10 @@ def channels_last_pyramid(fmap: torch.Tensor, num_levels: int) -> List[torch.Ten
 class OnTheFlyPlanes:
     """Tensor-core operands of one view for pf_lookup_onthefly_tc: fp16 hi/lo planes of the channels-last query features and
     of every level of the pooled target pyramid (one shared split scale per tensor family), plus the view's per-query
-    local-plane scratch (2048 floats per query and level; O(N), allocated on first use and reused by every lookup).  The
+    local-plane scratch (PF_OTF_PLANE(l) floats per query and level, 32 KiB per query over four levels; O(N), allocated on
+    first use and reused by every lookup).  The
     target planes hold every image row twice side by side ([B, Hl, 2 Wl, C]) so that windows across the ERP seam are one box."""
-    TILE_H, TILE_W, BOX = 8, 16, 2048
+    TILE_H, TILE_W, PLANE = 8, 16, (4096, 2048, 1024, 1024)      # PF_OTF_PLANE in include/priorcorr.h
 
     def __init__(self, f1: torch.Tensor, f2: Sequence[torch.Tensor]):
         lib = _lib.load()
@@ -424,7 +425,7 @@ class OnTheFlyPlanes:
     def mini(self):
         if self._mini is None:
             B, h, w, _ = self.shape
-            self._mini = [torch.empty((B, h, w, self.BOX), device=self.f1_hi.device, dtype=torch.float32) for _ in range(self.levels)]
+            self._mini = [torch.empty((B, h, w, self.PLANE[min(l, 3)]), device=self.f1_hi.device, dtype=torch.float32) for l in range(self.levels)]
         return self._mini
 
 
@@ -481,9 +482,11 @@ def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence
             tiles = (h // OnTheFlyPlanes.TILE_H) * (w // OnTheFlyPlanes.TILE_W)
             box = torch.empty((2, (2 if dual else 1) * L * B * tiles * 4), device=dev, dtype=torch.int32)
             t.box_lo, t.box_hi = box[0].data_ptr(), box[1].data_ptr()
+            work = torch.empty(4 + box.shape[1] // 4, device=dev, dtype=torch.int32)
+            t.worklist = work.data_ptr()
             _lib.check(lib.pf_lookup_onthefly_tc(C.byref(t), _stream()), "pf_lookup_onthefly_tc")
             _state["otf_boxes"] = box.view(2, 2 if dual else 1, L, B, tiles, 4)      # diagnostics: scripts/probe/otf_tiles.py
-            _count(6 if dual else 3)
+            _count(5 if dual else 4)
         else:
             _lib.check(lib.pf_lookup_onthefly(C.byref(a), _stream()), "pf_lookup_onthefly")
             _count(2 if dual else 1)

@@ -1,4 +1,4 @@
-"""Which query tiles of the tensor-core on-the-fly lookup take the tcgen05 path (tile box <= 32 x 64 or 64 x 32 target pixels), per view
+"""Which query tiles of the tensor-core on-the-fly lookup take the tcgen05 path (tile box fits the level's local plane), per view
 and level, for a smooth flow, for i.i.d. noise and for the flow a random-init model predicts.  Prints the fractions."""
 import os
 import sys
@@ -21,8 +21,11 @@ def report(tag, coords, f1a, f2a, f1b, f2b, gw, gc, pla, plb):
         for l in range(box.shape[2]):
             w_, h_ = bw[v, l].flatten(), bh[v, l].flatten()
             valid = (w_ > 0) & (h_ > 0) & (w_ < 10000)
-            fit = valid & (((w_ <= 32) & (h_ <= 64)) | ((w_ <= 64) & (h_ <= 32)))
-            print(f"[{tag}] view {v} level {l}: tiles {w_.numel()}, on tensor cores {float(fit.float().mean()):.2f}; median box {int(w_[valid].median())} x {int(h_[valid].median())}, "
+            plane = (4096, 2048, 1024, 1024)[l]
+            pitch = torch.where(w_ <= 32, 32, torch.where(w_ <= 64, 64, 128))
+            fit = valid & (w_ <= 128) & (h_ * pitch <= plane)
+            print(f"[{tag}] view {v} level {l}: tiles {w_.numel()}, with taps {int(valid.sum())}, of those on tensor cores "
+                  f"{float(fit.sum()) / max(int(valid.sum()), 1):.2f}; median box {int(w_[valid].median())} x {int(h_[valid].median())}, "
                   f"p90 {int(w_[valid].float().quantile(0.9))} x {int(h_[valid].float().quantile(0.9))}")
 
 
