@@ -158,15 +158,19 @@ typedef struct pf_onthefly_args {
 int pf_lookup_onthefly(const pf_onthefly_args *args, void *stream);
 /*
  * (c') The same lookup with the dot products on tcgen05 tensor cores (pf_onthefly_tc.cu).  Per tile of 8 x 16 queries the
- * bounding box of all taps is found first; tiles whose box fits the level's "local plane" (PF_OTF_PLANE(l) target pixels at a
- * pitch of 32, 64 or 128 columns) get a dense [128 x box] contraction of pre-split fp16 hi/lo planes (three products, fp32
- * accumulation: the volume kernel's numerics) written to per-query planes (O(N) scratch: 32 KiB per query and view over four
- * levels), other tiles keep the CUDA-core path.  Windows across the ERP seam stay on the tensor-core path: the target planes are stored twice side
- * by side.  Restrictions: radius 4, cyclic, h % 8 == 0, w % 16 == 0, channels % 128 == 0.  Prepare the planes once per pyramid:
+ * bounding box of all taps is found first; every box up to 256 target columns wide gets a dense [128 queries x box]
+ * contraction of pre-split fp16 hi/lo planes (three products, fp32 accumulation: the volume kernel's numerics) written to
+ * "local planes" in a pool of 16 KiB segments (128 queries x 32 box pixels); boxes beyond the pool's end or wider than 256
+ * columns take the CUDA-core path.  The pool is the O(N) scratch that replaces the O(N^2) volume: 2 segments per query and
+ * view (32 KiB) hold the boxes of a smooth flow field several times over.  Windows across the ERP seam stay on the
+ * tensor-core path: the target planes are stored twice side by side.  Restrictions: radius 4, cyclic, h % 8 == 0,
+ * w % 16 == 0, channels % 128 == 0.  Prepare the planes once per pyramid:
  *   zero the view's two `amax` words; pf_onthefly_absmax(fmap1, .., amax); pf_onthefly_absmax(fmap2 level 0, .., amax + 1);
  *   pf_onthefly_split(fmap1, .., amax, hi, lo, 0); pf_onthefly_split(fmap2 level l, .., amax + 1, hi_l, lo_l, (w>>l) * C).
  */
-#define PF_OTF_PLANE(l) ((l) == 0 ? 4096 : ((l) == 1 ? 2048 : 1024))
+/* ints of `worklist` for T = views * num_levels * batch * (h/8) * (w/16) query tiles and a pool of `segs` segments */
+#define PF_OTF_WORK_INTS(T, segs) (16 + 10 * (long long)(T) + 2 + 2 * ((long long)(segs) / 8 + (long long)(T)))
+#define PF_OTF_SEGMENT_BYTES 16384
 typedef struct pf_onthefly_tc_args {
   pf_onthefly_args base;                      /* fp32 operands and outputs exactly as for pf_lookup_onthefly       */
   const void *f1_hi_own, *f1_lo_own;          /* [B, h, w, C] fp16 planes of fmap1_own                             */
@@ -174,10 +178,9 @@ typedef struct pf_onthefly_tc_args {
   const void *f1_hi_other, *f1_lo_other;
   const void *f2_hi_other[PF_MAX_LEVELS], *f2_lo_other[PF_MAX_LEVELS];
   const void *amax_own, *amax_other;          /* uint32[2] per view: absmax bits of {fmap1, fmap2 level 0}          */
-  float *mini_own[PF_MAX_LEVELS];             /* scratch [B, h, w, PF_OTF_PLANE(l)] fp32 per level                 */
-  float *mini_other[PF_MAX_LEVELS];
-  int *box_lo, *box_hi;                       /* scratch int[views * L * B * (h/8) * (w/16) * 4] each, 16-B aligned */
-  int *worklist;                              /* scratch int[4 + views * L * B * (h/8) * (w/16)]                   */
+  float *pool;                                /* scratch: pool_segments * PF_OTF_SEGMENT_BYTES bytes, 128-B aligned */
+  long long pool_segments;
+  int *worklist;                              /* scratch: PF_OTF_WORK_INTS(T, pool_segments) ints, 16-B aligned     */
 } pf_onthefly_tc_args;
 int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *args, void *stream);
 int pf_onthefly_absmax(const float *x, long long count, void *amax_word, void *stream);

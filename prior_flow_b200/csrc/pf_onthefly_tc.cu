@@ -6,13 +6,16 @@
 // dense contraction per TILE of queries:
 //   otf_box_kernel    per query: the sampler's coordinate chain (bit-exact, shared with the blend below) and the integer
 //                     bounding box of its taps; atomically merged into the box of its 8 x 16 query tile
-//   otf_dots_kernel   per tile whose box fits the level's local plane at a pitch of 32, 64 or 128 columns (level 0: 4096 pixels):
-//                     D[128 queries, box] = F1[tile] . F2_l[box]^T on tcgen05 — both operands are TMA boxes of pre-split fp16
-//                     hi/lo K-major planes ([B, h, w, C], the channels-last convention of `alt_cuda_corr`), three products into
-//                     fp32 TMEM like the volume kernel, written to a per-query local plane ("mini volume": 32 KiB per query and
-//                     view over the four levels, O(N) memory), one full 128-byte line per thread and box row segment
-//   otf_blend_kernel  per query: the taps blend from its slice of the local plane in ATen's order; tiles whose box does not fit
-//                     (poles of the rotation map, wild flow) keep the r01 CUDA-core path, query by query, inside the same kernel
+//   otf_alloc_kernel  one CTA: a prefix sum over the tiles gives every box its place in a pool of "local planes" (128 queries x box
+//                     pixels of fp32, in segments of 128 queries x 32 pixels = 16 KiB; the pool is O(N): 32 KiB per query and
+//                     view by default) and cuts the boxes into work items of up to four MMA passes; boxes wider than 256
+//                     columns or beyond the pool go on the work list of the CUDA-core kernel
+//   otf_dots_kernel   persistent, one CTA per SM over the work items: D[128 queries, 256 box pixels] = F1[tile] . F2_l[box]^T on
+//                     tcgen05 — both operands are TMA boxes of pre-split fp16 hi/lo K-major planes ([B, h, w, C], the
+//                     channels-last convention of `alt_cuda_corr`), three products into fp32 TMEM like the volume kernel,
+//                     written to the tile's local planes with one 16 KiB bulk store per segment
+//   otf_blend_kernel  per query: the taps blend from the local planes in ATen's order (zeros for tiles no tap touches)
+//   otf_fallback_kernel  persistent over its work list: the r01 CUDA-core path, query by query
 // The ERP seam: the sampler wraps x, so a window across the seam touches columns at both ends of the plane.  Boxes are therefore
 // kept in two "unwrapped" column numberings — u0(x) = x and u1(x) = x + W for x < W/2 — a window narrower than W/2 is contiguous
 // in at least one of them, and the target planes are stored twice side by side ([B, Hl, 2 Wl, C]) so that a box in either
@@ -27,8 +30,8 @@
 namespace pf {
 
 constexpr int OT_TH = 8, OT_TW = 16;                 // query tile: 8 rows x 16 columns = 128 queries = TMEM lanes
-// local plane per query and level (floats), see PF_OTF_PLANE in priorcorr.h: level 0 holds 32 x 128, 64 x 64 or 128 x 32 box pixels
-__host__ __device__ constexpr int ot_plane(int lvl) { return PF_OTF_PLANE(lvl); }
+constexpr int OT_SEG = 128 * 32;                     // floats of a pool segment: 128 queries x 32 box pixels
+constexpr int OT_ITEM_CHUNKS = 4;                    // MMA passes (256 box pixels each) per work item
 constexpr int OT_BK = 64;
 constexpr int OT_APLANE = 128 * OT_BK * 2;           // 16 KiB
 constexpr int OT_BPLANE = 256 * OT_BK * 2;           // 32 KiB
@@ -54,17 +57,37 @@ struct OtfTcParams {
   const float *grid_w2c;
   long long grid_bs;
   float scale;                             // 1 / sqrt(C)
-  int *box_lo, *box_hi;                    // [2 views][L][B][tiles][4]: (u0, u1, y, -) min / max of the tile's taps
-  int *work;                               // [0] count, [1] cursor, [4 ...] tiles for the CUDA-core path: ((view * L + lvl) * B + b) * tiles + tile
-  float *mini[2][PF_MAX_LEVELS];           // [B, h, w, ot_plane(l)] local planes
+  int tiles_x, tiles, T;                   // query tiles per row / per image; T = views * L * B * tiles entries e = ((view * L + lvl) * B + b) * tiles + tile
+  int *box_lo, *box_hi;                    // [T][4]: (u0, u1, y, -) min / max of the tile's taps
+  int *ctr;                                // [0] CUDA-core tiles, [1] their cursor, [2] work items of the dots kernel, [3] pool segments in use
+  int *alloc;                              // [T] first pool segment of the tile's local planes; -1: CUDA-core path, -2: no tap touches the plane
+  int *fb_list;                            // [T] entries of the CUDA-core path
+  int2 *items;                             // [max_items] (entry, first MMA pass)
+  float *pool;                             // [pool_segs][128][32]: row r of a segment is query r of the tile, 16-byte groups XOR-swizzled by r & 7
+  int pool_segs, max_items;
   const uint32_t *amax[2];                 // per view: absmax bits of {f1, f2} (split scales of the fp16 planes)
   float *out_own, *out_raw;
 };
 
-__device__ __forceinline__ int tile_of(int n, int w, int &tiles_x) {
-  tiles_x = w / OT_TW;
-  const int y = n / w, x = n - y * w;
-  return (y / OT_TH) * tiles_x + x / OT_TW;
+__device__ __forceinline__ int tile_of(const OtfTcParams &p, int n) {
+  const int y = n / p.w, x = n - y * p.w;
+  return (y / OT_TH) * p.tiles_x + x / OT_TW;
+}
+__device__ __forceinline__ int entry_of(const OtfTcParams &p, int branch, int lvl, int b, int tile) {
+  return ((branch * p.L + lvl) * p.B + b) * p.tiles + tile;
+}
+struct Entry {
+  int branch, lvl, b, tile;
+};
+__device__ __forceinline__ Entry decode_entry(const OtfTcParams &p, int e) {
+  Entry r;
+  r.tile = e % p.tiles;
+  e /= p.tiles;
+  r.b = e % p.B;
+  e /= p.B;
+  r.lvl = e % p.L;
+  r.branch = e / p.L;
+  return r;
 }
 
 __device__ __forceinline__ float ot_split_scale(uint32_t amax_bits) {
@@ -154,28 +177,29 @@ __global__ void __launch_bounds__(kBlendThreads) otf_box_kernel(const OtfTcParam
   const int lvl = blockIdx.y % p.L, branch = blockIdx.y / p.L, b = blockIdx.z;
   const int Hl = p.h >> lvl, Wl = p.w >> lvl;
   const int n0 = blockIdx.x * kBlendQueries;
-  // the 8 queries of a CTA are consecutive in a row and 8 | 16: they share the tile
+  // the 16 queries of a CTA are one row of a query tile
   if (threadIdx.x == 0) box_reset(s_box);
   cta_tap_coords(p, branch, lvl, b, n0, s_axis, [&](int, int, float ix, float iy) { box_add_tap_warp(s_box, (int)floorf(ix), (int)floorf(iy), Wl, Hl); });
   __syncthreads();
   if (threadIdx.x < 3 && s_box[4] <= s_box[5]) {
-    int tiles_x;
-    const int tile = tile_of(n0, p.w, tiles_x);
-    const int tiles = tiles_x * (p.h / OT_TH);
-    const long long e = ((((long long)branch * p.L + lvl) * p.B + b) * tiles + tile) * 4 + threadIdx.x;
+    const long long e = (long long)entry_of(p, branch, lvl, b, tile_of(p, n0)) * 4 + threadIdx.x;
     atomicMin(p.box_lo + e, s_box[2 * threadIdx.x]);
     atomicMax(p.box_hi + e, s_box[2 * threadIdx.x + 1]);
   }
 }
 
-// The tile's box: which numbering (mode), origin, rows, and the local-plane pitch (32, 64 or 128 columns).
+// The tile's box: which numbering (mode), origin, rows, and the pitch of its local planes (32 ... 256 columns, 1 ... 8 segments).
 struct TileBox {
   int mode, X0, Y0, rows, pitch;
   bool empty;      // no tap of the tile touches the plane: the outputs are zero
+  __device__ __forceinline__ int spr() const { return pitch >> 5; }                 // segments per box row
+  __device__ __forceinline__ int rpc() const { return 256 / pitch; }                // box rows per MMA pass
+  __device__ __forceinline__ int nseg() const { return rows * (pitch >> 5); }
+  __device__ __forceinline__ int nchunks() const { return (rows + rpc() - 1) / rpc(); }
 };
-__device__ __forceinline__ bool tile_box(const OtfTcParams &p, int branch, int lvl, int b, int tile, int tiles, TileBox &tb) {
-  const long long e = ((((long long)branch * p.L + lvl) * p.B + b) * tiles + tile) * 4;
-  const int4 lo = *reinterpret_cast<const int4 *>(p.box_lo + e), hi = *reinterpret_cast<const int4 *>(p.box_hi + e);
+// false: empty, or wider than one MMA pass (256 columns)
+__device__ __forceinline__ bool read_box(const OtfTcParams &p, int e, TileBox &tb) {
+  const int4 lo = *reinterpret_cast<const int4 *>(p.box_lo + 4ll * e), hi = *reinterpret_cast<const int4 *>(p.box_hi + 4ll * e);
   tb.empty = lo.z > hi.z || lo.x > hi.x;
   if (tb.empty) return false;
   const int w0 = hi.x - lo.x + 1, w1 = hi.y - lo.y + 1;
@@ -184,40 +208,79 @@ __device__ __forceinline__ bool tile_box(const OtfTcParams &p, int branch, int l
   tb.X0 = tb.mode ? lo.y : lo.x;
   tb.Y0 = lo.z;
   tb.rows = hi.z - lo.z + 1;
-  tb.pitch = bw <= 32 ? 32 : (bw <= 64 ? 64 : 128);
-  return bw <= 128 && tb.rows * tb.pitch <= ot_plane(lvl);
+  tb.pitch = bw <= 32 ? 32 : (bw <= 64 ? 64 : (bw <= 128 ? 128 : 256));
+  return bw <= 256;
+}
+
+// ------------------------------------------------------------------------------------------------ pool allocation, work items
+__device__ __forceinline__ int block_exclusive_scan(int v, int *s_scan, int &total) {   // 1024 threads
+  const int t = threadIdx.x;
+  s_scan[t] = v;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int add = t >= o ? s_scan[t - o] : 0;
+    __syncthreads();
+    s_scan[t] += add;
+    __syncthreads();
+  }
+  total = s_scan[1023];
+  const int excl = s_scan[t] - v;
+  __syncthreads();
+  return excl;
+}
+
+__global__ void __launch_bounds__(1024) otf_alloc_kernel(const OtfTcParams p) {
+  __shared__ int s_scan[1024];
+  const int per = (p.T + 1023) / 1024, e0 = threadIdx.x * per, e1 = min(e0 + per, p.T);
+  // 1. pool segments of the boxes one MMA pass can cover; a box beyond the pool's end goes to the CUDA-core path
+  int segs = 0;
+  for (int e = e0; e < e1; ++e) {
+    TileBox tb;
+    if (read_box(p, e, tb)) segs += tb.nseg();
+  }
+  int total, total_segs;
+  int off = block_exclusive_scan(segs, s_scan, total_segs);
+  int items = 0;
+  for (int e = e0; e < e1; ++e) {
+    TileBox tb;
+    const bool shape_ok = read_box(p, e, tb);
+    int a = tb.empty ? -2 : -1;
+    if (shape_ok) {
+      if (off + tb.nseg() <= p.pool_segs) a = off, items += (tb.nchunks() + OT_ITEM_CHUNKS - 1) / OT_ITEM_CHUNKS;
+      off += tb.nseg();
+    }
+    p.alloc[e] = a;
+    if (a == -1) p.fb_list[atomicAdd(p.ctr, 1)] = e;
+  }
+  // 2. work items of the dots kernel
+  int it = block_exclusive_scan(items, s_scan, total);
+  if (threadIdx.x == 0) p.ctr[2] = min(total, p.max_items), p.ctr[3] = total_segs;      // [3]: what the boxes asked for (diagnostics)
+  for (int e = e0; e < e1; ++e) {
+    if (p.alloc[e] < 0) continue;
+    TileBox tb;
+    read_box(p, e, tb);
+    for (int c = 0; c < tb.nchunks(); c += OT_ITEM_CHUNKS, ++it)
+      if (it < p.max_items) p.items[it] = make_int2(e, c);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ dots (tcgen05)
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map), "r"(src), "r"(c0),
-               "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-               : "memory");
+__device__ __forceinline__ void bulk_store(void *dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 
 struct OtfViewMaps {
   CUtensorMap f1_hi, f1_lo;                                    // [C, w, h, B] fp16, box {64, 16, 8, 1}
-  CUtensorMap f2_hi[3][PF_MAX_LEVELS], f2_lo[3][PF_MAX_LEVELS];   // [C, 2 Wl, Hl, B] fp16, box {64, pitch, 256 / pitch, 1}, pitch 32 / 64 / 128
-  CUtensorMap out[3][PF_MAX_LEVELS];                           // [pitch, plane / pitch, w, h, B] fp32, box {32, 1, 16, 8, 1}
+  CUtensorMap f2_hi[4][PF_MAX_LEVELS], f2_lo[4][PF_MAX_LEVELS];   // [C, 2 Wl, Hl, B] fp16, box {64, pitch, 256 / pitch, 1}, pitch 32 ... 256
 };
 struct OtfMaps {
-  OtfViewMaps view[2];     // ~10 KiB of kernel parameters (CUDA 12.1+: up to 32 KiB)
+  OtfViewMaps view[2];     // ~8.5 KiB of kernel parameters (CUDA 12.1+: up to 32 KiB)
 };
+__device__ __forceinline__ int pitch_index(int pitch) { return pitch == 32 ? 0 : (pitch == 64 ? 1 : (pitch == 128 ? 2 : 3)); }
 
 __global__ void __launch_bounds__(OT_THREADS, 1) otf_dots_kernel(const __grid_constant__ OtfMaps all_maps, const OtfTcParams p) {
-  // the other view first (its boxes are the large ones), fine levels first
-  const int tile = blockIdx.x, lvl = blockIdx.y % p.L, branch = (gridDim.y / p.L) - 1 - blockIdx.y / p.L, b = blockIdx.z;
-  const OtfViewMaps &maps = all_maps.view[branch];
-  const int tiles_x = p.w / OT_TW, tiles = tiles_x * (p.h / OT_TH);
-  TileBox tb;
-  if (!tile_box(p, branch, lvl, b, tile, tiles, tb)) {             // uniform
-    // boxes that do not fit a local plane go on the work list of otf_fallback_kernel (CUDA cores)
-    if (!tb.empty && threadIdx.x == 0) p.work[4 + atomicAdd(p.work, 1)] = ((branch * p.L + lvl) * p.B + b) * tiles + tile;
-    return;
-  }
-  const int wide = tb.pitch >> 6, rpc = 256 / tb.pitch;           // pitch 32 / 64 / 128 -> map 0 / 1 / 2; box rows per MMA pass
-  const int nchunks = (tb.rows + rpc - 1) / rpc, X0 = tb.X0, Y0 = tb.Y0;
-  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  const int nitems = p.ctr[2];
+  if ((int)blockIdx.x >= nitems) return;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -243,100 +306,124 @@ __global__ void __launch_bounds__(OT_THREADS, 1) otf_dots_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // every role walks the same static item sequence; the smem / TMEM pipelines run on across items
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int c = 0; c < nchunks; ++c)
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          const uint32_t full = bar_full + 8 * stage;
-          mbar_arrive_expect_tx(full, (uint32_t)OT_STAGE);
-          const uint32_t sbase = smem_u32(smem + stage * OT_STAGE);
-          // layout of a stage: [A.hi 16K | B.hi 32K | A.lo 16K | B.lo 32K]
-          tma_load_4d(sbase, &maps.f1_hi, full, kb * OT_BK, tx * OT_TW, ty * OT_TH, b);
-          tma_load_4d(sbase + OT_APLANE, &maps.f2_hi[wide][lvl], full, kb * OT_BK, X0, Y0 + c * rpc, b);
-          tma_load_4d(sbase + OT_APLANE + OT_BPLANE, &maps.f1_lo, full, kb * OT_BK, tx * OT_TW, ty * OT_TH, b);
-          tma_load_4d(sbase + 2 * OT_APLANE + OT_BPLANE, &maps.f2_lo[wide][lvl], full, kb * OT_BK, X0, Y0 + c * rpc, b);
-          if (++stage == OT_STAGES) stage = 0, phase ^= 1;
-        }
+      for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const int2 item = p.items[it];
+        const Entry en = decode_entry(p, item.x);
+        TileBox tb;
+        read_box(p, item.x, tb);
+        const OtfViewMaps &maps = all_maps.view[en.branch];
+        const int pi = pitch_index(tb.pitch), rpc = tb.rpc(), c1 = min(item.y + OT_ITEM_CHUNKS, tb.nchunks());
+        const int ty = en.tile / p.tiles_x, tx = en.tile - ty * p.tiles_x;
+        for (int c = item.y; c < c1; ++c)
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t full = bar_full + 8 * stage;
+            mbar_arrive_expect_tx(full, (uint32_t)OT_STAGE);
+            const uint32_t sbase = smem_u32(smem + stage * OT_STAGE);
+            // layout of a stage: [A.hi 16K | B.hi 32K | A.lo 16K | B.lo 32K]
+            tma_load_4d(sbase, &maps.f1_hi, full, kb * OT_BK, tx * OT_TW, ty * OT_TH, en.b);
+            tma_load_4d(sbase + OT_APLANE, &maps.f2_hi[pi][en.lvl], full, kb * OT_BK, tb.X0, tb.Y0 + c * rpc, en.b);
+            tma_load_4d(sbase + OT_APLANE + OT_BPLANE, &maps.f1_lo, full, kb * OT_BK, tx * OT_TW, ty * OT_TH, en.b);
+            tma_load_4d(sbase + 2 * OT_APLANE + OT_BPLANE, &maps.f2_lo[pi][en.lvl], full, kb * OT_BK, tb.X0, tb.Y0 + c * rpc, en.b);
+            if (++stage == OT_STAGES) stage = 0, phase ^= 1;
+          }
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0;
-      for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * 256;
-        const int ncols = min(256, (tb.rows - c * rpc) * tb.pitch);       // the last pass needs only the box rows that are left
-        const uint32_t idesc = umma_idesc_f16(128, ncols);
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
+      for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const int2 item = p.items[it];
+        TileBox tb;
+        read_box(p, item.x, tb);
+        const int rpc = tb.rpc(), c1 = min(item.y + OT_ITEM_CHUNKS, tb.nchunks());
+        for (int c = item.y; c < c1; ++c) {
+          mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t sbase = smem_u32(smem + stage * OT_STAGE);
-          const uint64_t a_hi = make_smem_desc(sbase), b_hi = make_smem_desc(sbase + OT_APLANE);
-          const uint64_t a_lo = make_smem_desc(sbase + OT_APLANE + OT_BPLANE), b_lo = make_smem_desc(sbase + 2 * OT_APLANE + OT_BPLANE);
+          const uint32_t tmem_d = tmem_base + acc * 256;
+          const int ncols = min(256, (tb.rows - c * rpc) * tb.pitch);       // the last pass needs only the box rows that are left
+          const uint32_t idesc = umma_idesc_f16(128, ncols);
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t sbase = smem_u32(smem + stage * OT_STAGE);
+            const uint64_t a_hi = make_smem_desc(sbase), b_hi = make_smem_desc(sbase + OT_APLANE);
+            const uint64_t a_lo = make_smem_desc(sbase + OT_APLANE + OT_BPLANE), b_lo = make_smem_desc(sbase + 2 * OT_APLANE + OT_BPLANE);
 #pragma unroll
-          for (int k = 0; k < OT_BK / 16; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < OT_BK / 16; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, (kb | k) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < OT_BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+            for (int k = 0; k < OT_BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
 #pragma unroll
-          for (int k = 0; k < OT_BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
-          umma_commit(bar_empty + 8 * stage);
-          if (++stage == OT_STAGES) stage = 0, phase ^= 1;
+            for (int k = 0; k < OT_BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+            umma_commit(bar_empty + 8 * stage);
+            if (++stage == OT_STAGES) stage = 0, phase ^= 1;
+          }
+          umma_commit(bar_tfull + 8 * acc);
+          if ((acc ^= 1) == 0) acc_phase ^= 1;
         }
-        umma_commit(bar_tfull + 8 * acc);
-        if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
     }
   } else {
-    // epilogue: 4 warps, TMEM lane = query of the tile (rx fastest), columns = box pixels of the pass in segments of 32:
-    // segment g = box row g / (pitch / 32), columns 32 (g % (pitch / 32)) ...; one TMA store per segment scatters the 128 rows of
-    // the staging buffer into the 128 local planes (two staging buffers: a store drains while the next segment is staged)
+    // epilogue: 4 warps, TMEM lane = query of the tile (rx fastest), columns = box pixels of the pass in segments of 32.  Segment g
+    // of pass c is pool segment 8 c + g of the tile (box row (8 c + g) / spr, columns 32 ((8 c + g) % spr) ...): staged as
+    // [128 queries][32 floats] with the 16-byte groups XOR-swizzled (conflict-free float4 writes; the blend un-swizzles) and
+    // written with one 16 KiB bulk store; two staging buffers, a store drains while the next segment is staged
     const int quarter = warp & 3, row = quarter * 32 + lane;
     const bool leader = threadIdx.x == 64;
-    const float scale = p.scale / (ot_split_scale(p.amax[branch][0]) * ot_split_scale(p.amax[branch][1]));
-    const int spr = tb.pitch >> 5;   // segments per box row
     uint32_t acc = 0, acc_phase = 0, buf = 0;
-    for (int c = 0; c < nchunks; ++c) {
-      mbar_wait(bar_tfull + 8 * acc, acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
-      const int nseg = min(8, (tb.rows - c * rpc) * spr);      // segments of this pass that hold box rows
-      uint32_t un[32];
-      tmem_ld32(taddr, un);
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+      const int2 item = p.items[it];
+      const Entry en = decode_entry(p, item.x);
+      TileBox tb;
+      read_box(p, item.x, tb);
+      const int rpc = tb.rpc(), spr = tb.spr(), c1 = min(item.y + OT_ITEM_CHUNKS, tb.nchunks());
+      const float scale = p.scale / (ot_split_scale(p.amax[en.branch][0]) * ot_split_scale(p.amax[en.branch][1]));
+      float *planes = p.pool + (long long)p.alloc[item.x] * OT_SEG;
+      for (int c = item.y; c < c1; ++c) {
+        mbar_wait(bar_tfull + 8 * acc, acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
+        const int nseg = min(8, (tb.rows - c * rpc) * spr);      // segments of this pass that hold box rows
+        uint32_t un[32];
+        tmem_ld32(taddr, un);
 #pragma unroll 1
-      for (int g = 0; g < nseg; ++g) {
-        tmem_ld_wait();
-        float v[32];
+        for (int g = 0; g < nseg; ++g) {
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(un[j]) * scale;
-        if (g + 1 < nseg) {
-          tmem_ld32(taddr + (g + 1) * 32, un);
-        } else {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-        }
-        if (leader) tma_store_wait_read1();      // the store issued from this buffer two segments ago has read it
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        uint8_t *stage = out_stage + buf * OT_OUT;
-        {
-          uint8_t *r0 = stage + row * 128;
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(un[j]) * scale;
+          if (g + 1 < nseg) {
+            tmem_ld32(taddr + (g + 1) * 32, un);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+          }
+          if (leader) tma_store_wait_read1();      // the store issued from this buffer two segments ago has read it
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          uint8_t *stage = out_stage + buf * OT_OUT;
+          {
+            uint8_t *r0 = stage + row * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4 *>(r0 + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4 *>(r0 + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          fence_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (leader) {
+            bulk_store(planes + (long long)(8 * c + g) * OT_SEG, smem_u32(stage), OT_OUT);
+            tma_store_commit();
+          }
+          buf ^= 1;
         }
-        fence_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (leader) {
-          tma_store_5d(&maps.out[wide][lvl], smem_u32(stage), (g % spr) * 32, c * rpc + g / spr, tx * OT_TW, ty * OT_TH, b);
-          tma_store_commit();
-        }
-        buf ^= 1;
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
-      if ((acc ^= 1) == 0) acc_phase ^= 1;
     }
     if (leader) tma_store_wait_all();
   }
@@ -404,41 +491,28 @@ __device__ __forceinline__ void write_taps(const OtfTcParams &p, const float (*s
   }
 }
 
-struct BlendCta {
-  int lvl, branch, b, n0, Hl, Wl;
-  TileBox tb;
-  bool tc;
-};
-__device__ __forceinline__ BlendCta blend_cta(const OtfTcParams &p) {
-  BlendCta c;
-  const int by = blockIdx.y;
-  c.lvl = by % p.L, c.branch = by / p.L, c.b = blockIdx.z;
-  c.Hl = p.h >> c.lvl, c.Wl = p.w >> c.lvl;
-  c.n0 = blockIdx.x * kBlendQueries;
-  int tiles_x;
-  const int tile = tile_of(c.n0, p.w, tiles_x);          // the CTA's 16 queries are one row of a tile
-  c.tc = tile_box(p, c.branch, c.lvl, c.b, tile, tiles_x * (p.h / OT_TH), c.tb);      // block-uniform
-  return c;
-}
-
-// Tiles on the tensor-core path: the tile's dots are in the queries' local planes (otf_dots_kernel); every tap reads its four
-// corners from there.  All 648 taps of the CTA are in flight together.
+// Tiles on the tensor-core path: the tile's dots are in its local planes (otf_dots_kernel); every tap reads its four corners from
+// there.  All taps of the CTA's 16 queries are in flight together.  Tiles no tap touches: zeros.
 __global__ void __launch_bounds__(kBlendThreads) otf_blend_kernel(const OtfTcParams p) {
   __shared__ float s_axis[kBlendQueries * 18];
   __shared__ float s_out[kMaxTaps][kBlendQueries + 1];
-  const BlendCta c = blend_cta(p);
-  if (!c.tc && !c.tb.empty) return;       // otf_fallback_kernel's
-  const int lvl = c.lvl, branch = c.branch, b = c.b, n0 = c.n0, Hl = c.Hl, Wl = c.Wl;
-  const TileBox tb = c.tb;
-  if (tb.empty) {
+  const int lvl = blockIdx.y % p.L, branch = blockIdx.y / p.L, b = blockIdx.z;
+  const int Hl = p.h >> lvl, Wl = p.w >> lvl;
+  const int n0 = blockIdx.x * kBlendQueries;
+  const int e = entry_of(p, branch, lvl, b, tile_of(p, n0));
+  const int first = p.alloc[e];                       // block-uniform
+  if (first == -1) return;                            // otf_fallback_kernel's
+  if (first == -2) {
     for (int i = threadIdx.x; i < kMaxTaps * (kBlendQueries + 1); i += kBlendThreads) (&s_out[0][0])[i] = 0.f;
     __syncthreads();
     write_taps(p, s_out, branch, lvl, b, n0);
     return;
   }
-  // the tile's dots are in the queries' local planes (otf_dots_kernel): every tap reads its four corners from there
-  const int plane = ot_plane(lvl);
-  const float *mini = p.mini[branch][lvl] + ((long long)b * p.N + n0) * plane;
+  TileBox tb;
+  read_box(p, e, tb);
+  const int spr = tb.spr();
+  const int qrow0 = ((n0 / p.w) % OT_TH) * OT_TW;     // row of query n0 in its tile's segments
+  const float *planes = p.pool + (long long)first * OT_SEG;
   cta_tap_coords(p, branch, lvl, b, n0, s_axis, [&](int q, int t, float ix, float iy) {
     const Taps tp = make_taps(ix, iy);
     const bool xin0 = (unsigned)tp.x0 < (unsigned)Wl, xin1 = (unsigned)(tp.x0 + 1) < (unsigned)Wl;
@@ -446,11 +520,17 @@ __global__ void __launch_bounds__(kBlendThreads) otf_blend_kernel(const OtfTcPar
     // column of the west corner in the box's numbering (mode 1: unwrapped); the east corner is the next column — a tap
     // whose corners straddle the numbering's cut would have made the box as wide as the plane, and then mode 0 is chosen
     const int ux = (tb.mode && xin0) ? unwrap1(tp.x0, Wl) : ((tb.mode && xin1) ? unwrap1(tp.x0 + 1, Wl) - 1 : tp.x0);
-    const float *c0 = mini + (long long)q * plane + (tp.y0 - tb.Y0) * tb.pitch + (ux - tb.X0);
-    const float v_nw = (yin0 && xin0) ? __ldg(c0) : 0.f;
-    const float v_ne = (yin0 && xin1) ? __ldg(c0 + 1) : 0.f;
-    const float v_sw = (yin1 && xin0) ? __ldg(c0 + tb.pitch) : 0.f;
-    const float v_se = (yin1 && xin1) ? __ldg(c0 + tb.pitch + 1) : 0.f;
+    const int r = qrow0 + q, sw = r & 7;
+    const int cw = ux - tb.X0, ce = cw + 1, yy = tp.y0 - tb.Y0;
+    // element (box row y, column c) of query r: segment y * spr + c / 32, float r * 32 + (((c % 32) / 4) ^ (r & 7)) * 4 + c % 4
+    const float *qn = planes + (long long)yy * spr * OT_SEG + r * 32;
+    const long long off_w = (long long)(cw >> 5) * OT_SEG + ((((cw & 31) >> 2) ^ sw) << 2) + (cw & 3);
+    const long long off_e = (long long)(ce >> 5) * OT_SEG + ((((ce & 31) >> 2) ^ sw) << 2) + (ce & 3);
+    const long long down = (long long)spr * OT_SEG;
+    const float v_nw = (yin0 && xin0) ? __ldg(qn + off_w) : 0.f;
+    const float v_ne = (yin0 && xin1) ? __ldg(qn + off_e) : 0.f;
+    const float v_sw = (yin1 && xin0) ? __ldg(qn + down + off_w) : 0.f;
+    const float v_se = (yin1 && xin1) ? __ldg(qn + down + off_e) : 0.f;
     float acc = __fmul_rn(v_nw, tp.nw);
     acc = __fmaf_rn(v_ne, tp.ne, acc);
     acc = __fmaf_rn(v_sw, tp.sw, acc);
@@ -461,7 +541,7 @@ __global__ void __launch_bounds__(kBlendThreads) otf_blend_kernel(const OtfTcPar
   write_taps(p, s_out, branch, lvl, b, n0);
 }
 
-// Tiles whose box does not fit a local plane (the work list otf_dots_kernel wrote): the CUDA-core path of the r01 kernel, query
+// Tiles whose box is too wide or beyond the pool (the work list otf_alloc_kernel wrote): the CUDA-core path of the r01 kernel, query
 // by query — the plane on the query's own box if that is fewer dot products than four per tap, else tap by tap.  Persistent: a
 // CTA takes (tile, row of 16 queries) items off the list until it is empty; these are the long items of the call.
 __global__ void __launch_bounds__(kBlendThreads) otf_fallback_kernel(const OtfTcParams p) {
@@ -473,22 +553,17 @@ __global__ void __launch_bounds__(kBlendThreads) otf_fallback_kernel(const OtfTc
   __shared__ int s_item;
   constexpr int K2 = kMaxTaps;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_x = p.w / OT_TW, tiles = tiles_x * (p.h / OT_TH);
-  const int items = p.work[0] * OT_TH;
+  const int items = p.ctr[0] * OT_TH;
   for (;;) {
   __syncthreads();
-  if (threadIdx.x == 0) s_item = atomicAdd(p.work + 1, 1);
+  if (threadIdx.x == 0) s_item = atomicAdd(p.ctr + 1, 1);
   __syncthreads();
   const int item = s_item;
   if (item >= items) return;
-  int e = p.work[4 + item / OT_TH];
-  const int tile = e % tiles;
-  e /= tiles;
-  const int b = e % p.B;
-  e /= p.B;
-  const int lvl = e % p.L, branch = e / p.L;
+  const Entry en = decode_entry(p, p.fb_list[item / OT_TH]);
+  const int tile = en.tile, b = en.b, lvl = en.lvl, branch = en.branch;
   const int Hl = p.h >> lvl, Wl = p.w >> lvl;
-  const int n0 = ((tile / tiles_x) * OT_TH + item % OT_TH) * p.w + (tile % tiles_x) * OT_TW;
+  const int n0 = ((tile / p.tiles_x) * OT_TH + item % OT_TH) * p.w + (tile % p.tiles_x) * OT_TW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // CUDA-core path (the r01 kernel's): per query, the plane on its own box if that is fewer dot products than four per tap
   if (threadIdx.x < kBlendQueries) box_reset(s_box[threadIdx.x]);
@@ -620,41 +695,47 @@ extern "C" int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *t, void *stream)
   PF_REQUIRE(a->channels % 128 == 0 && a->channels <= 512 && a->channels % OT_BK == 0, "pf_lookup_onthefly_tc: channels must be a multiple of 128, <= 512");
   PF_REQUIRE(a->h % OT_TH == 0 && a->w % OT_TW == 0, "pf_lookup_onthefly_tc: the query grid must tile by %dx%d (got %dx%d)", OT_TH, OT_TW, a->h, a->w);
   PF_REQUIRE(a->num_levels >= 1 && a->num_levels <= PF_MAX_LEVELS, "pf_lookup_onthefly_tc: num_levels must be 1..%d", PF_MAX_LEVELS);
-  PF_REQUIRE(a->coords && a->fmap1_own && a->out_own && t->box_lo && t->box_hi && t->worklist && t->amax_own, "pf_lookup_onthefly_tc: null pointer");
+  PF_REQUIRE(a->coords && a->fmap1_own && a->out_own && t->worklist && t->pool && t->amax_own, "pf_lookup_onthefly_tc: null pointer");
+  PF_REQUIRE(t->pool_segments >= 8 && t->pool_segments < (1ll << 30), "pf_lookup_onthefly_tc: pool_segments must be in [8, 2^30)");
   const bool dual = a->fmap1_other != nullptr;
   PF_REQUIRE(!dual || (a->grid_w2c && a->grid_c2w && a->out_other && a->scratch && t->amax_other), "pf_lookup_onthefly_tc: dual lookup needs grids, out_other, scratch");
   cudaStream_t st = (cudaStream_t)stream;
   const int views = dual ? 2 : 1, L = a->num_levels, B = a->batch, h = a->h, w = a->w, C = a->channels, N = h * w;
-  const int tiles = (h / OT_TH) * (w / OT_TW);
   OtfTcParams p;
   p.B = B, p.N = N, p.h = h, p.w = w, p.C = C, p.L = L, p.div_mode = a->div_mode;
+  p.tiles_x = w / OT_TW, p.tiles = p.tiles_x * (h / OT_TH), p.T = views * L * B * p.tiles;
   p.coords = a->coords;
   p.f1[0] = a->fmap1_own, p.f1[1] = a->fmap1_other;
   for (int l = 0; l < PF_MAX_LEVELS; ++l) {
     p.f2[0][l] = l < L ? a->fmap2_own[l] : nullptr;
     p.f2[1][l] = (dual && l < L) ? a->fmap2_other[l] : nullptr;
-    p.mini[0][l] = l < L ? t->mini_own[l] : nullptr;
-    p.mini[1][l] = (dual && l < L) ? t->mini_other[l] : nullptr;
     p.axH[l] = make_axis((h >> l) > 0 ? (h >> l) : 1), p.axW[l] = make_axis((w >> l) > 0 ? (w >> l) : 1);
     if (l < L) {
       PF_REQUIRE((h >> l) >= 1 && (w >> l) >= 1, "pf_lookup_onthefly_tc: level %d is empty", l);
-      PF_REQUIRE(p.f2[0][l] && p.mini[0][l] && t->f2_hi_own[l] && t->f2_lo_own[l], "pf_lookup_onthefly_tc: own level %d: null pointer", l);
-      PF_REQUIRE(!dual || (p.f2[1][l] && p.mini[1][l] && t->f2_hi_other[l] && t->f2_lo_other[l]), "pf_lookup_onthefly_tc: other level %d: null pointer", l);
+      PF_REQUIRE(p.f2[0][l] && t->f2_hi_own[l] && t->f2_lo_own[l], "pf_lookup_onthefly_tc: own level %d: null pointer", l);
+      PF_REQUIRE(!dual || (p.f2[1][l] && t->f2_hi_other[l] && t->f2_lo_other[l]), "pf_lookup_onthefly_tc: other level %d: null pointer", l);
     }
   }
   p.ax_gw = make_axis(w), p.ax_gh = make_axis(h);
   p.grid_w2c = a->grid_w2c, p.grid_bs = a->grid_batch_stride;
   p.scale = 1.0f / sqrtf((float)C);
-  p.box_lo = t->box_lo, p.box_hi = t->box_hi, p.work = t->worklist;
+  // the work buffer: PF_OTF_WORK_INTS(T, pool_segments) ints = [16 counters | box_lo 4T | box_hi 4T | alloc T | fb_list T | items 2 * max_items]
+  p.pool = t->pool, p.pool_segs = (int)t->pool_segments, p.max_items = (int)(t->pool_segments / 8) + p.T;
+  p.ctr = t->worklist;
+  p.box_lo = t->worklist + 16, p.box_hi = p.box_lo + 4 * p.T;
+  p.alloc = p.box_hi + 4 * p.T, p.fb_list = p.alloc + p.T;
+  p.items = reinterpret_cast<int2 *>(p.fb_list + p.T + (p.T & 1));
   p.amax[0] = reinterpret_cast<const uint32_t *>(t->amax_own), p.amax[1] = reinterpret_cast<const uint32_t *>(t->amax_other);
   p.out_own = a->out_own, p.out_raw = a->scratch;
-  const size_t table = (size_t)views * L * B * tiles * 4 * sizeof(int);
-  if (cudaMemsetAsync(t->box_lo, 0x7f, table, st) != cudaSuccess || cudaMemsetAsync(t->box_hi, 0x80, table, st) != cudaSuccess ||
-      cudaMemsetAsync(t->worklist, 0, 4 * sizeof(int), st) != cudaSuccess)
+  const size_t table = (size_t)p.T * 4 * sizeof(int);
+  if (cudaMemsetAsync(p.ctr, 0, 16 * sizeof(int), st) != cudaSuccess || cudaMemsetAsync(p.box_lo, 0x7f, table, st) != cudaSuccess ||
+      cudaMemsetAsync(p.box_hi, 0x80, table, st) != cudaSuccess)
     return check_launch("pf_lookup_onthefly_tc(memset)");
   const dim3 qgrid(ceil_div(N, kBlendQueries), L * views, B);
   otf_box_kernel<<<qgrid, kBlendThreads, 0, st>>>(p);
   if (int e = check_launch("pf_lookup_onthefly_tc(box)")) return e;
+  otf_alloc_kernel<<<1, 1024, 0, st>>>(p);
+  if (int e = check_launch("pf_lookup_onthefly_tc(alloc)")) return e;
   cudaFuncSetAttribute(otf_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OT_SMEM);
   OtfMaps maps;
   for (int v = 0; v < 2; ++v) {
@@ -673,25 +754,26 @@ extern "C" int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *t, void *stream)
       const int ll = l < L ? l : 0;
       const int Hl = h >> ll, Wl = w >> ll;
       const void *hi = vv ? t->f2_hi_other[ll] : t->f2_hi_own[ll], *lo = vv ? t->f2_lo_other[ll] : t->f2_lo_own[ll];
-      for (int wi = 0; wi < 3; ++wi) {
-        const int pitch = 32 << wi;
+      for (int pi = 0; pi < 4; ++pi) {
+        const int pitch = 32 << pi;
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)(2 * Wl), (cuuint64_t)Hl, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)2 * Wl * C * 2, (cuuint64_t)Hl * 2 * Wl * C * 2};
         cuuint32_t box[4] = {OT_BK, (cuuint32_t)pitch, (cuuint32_t)(256 / pitch), 1};
-        if (int e = encode(&m.f2_hi[wi][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(hi), dims, strides, box, "otf f2.hi")) return e;
-        if (int e = encode(&m.f2_lo[wi][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(lo), dims, strides, box, "otf f2.lo")) return e;
-        const int plane = ot_plane(ll);
-        float *mini = vv ? t->mini_other[ll] : t->mini_own[ll];
-        cuuint64_t od[5] = {(cuuint64_t)pitch, (cuuint64_t)(plane / pitch), (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
-        cuuint64_t os[4] = {(cuuint64_t)pitch * 4, (cuuint64_t)plane * 4, (cuuint64_t)w * plane * 4, (cuuint64_t)h * w * plane * 4};
-        cuuint32_t ob[5] = {32, 1, OT_TW, OT_TH, 1};
-        if (int e = encode(&m.out[wi][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, mini, od, os, ob, "otf mini")) return e;
+        if (int e = encode(&m.f2_hi[pi][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(hi), dims, strides, box, "otf f2.hi")) return e;
+        if (int e = encode(&m.f2_lo[pi][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(lo), dims, strides, box, "otf f2.lo")) return e;
       }
     }
   }
-  otf_dots_kernel<<<dim3(tiles, L * views, B), OT_THREADS, OT_SMEM, st>>>(maps, p);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  otf_dots_kernel<<<sms, OT_THREADS, OT_SMEM, st>>>(maps, p);
   if (int e = check_launch("pf_lookup_onthefly_tc(dots)")) return e;
-  otf_fallback_kernel<<<2 * 148, kBlendThreads, 0, st>>>(p);
+  otf_fallback_kernel<<<2 * sms, kBlendThreads, 0, st>>>(p);
   if (int e = check_launch("pf_lookup_onthefly_tc(fallback)")) return e;
   otf_blend_kernel<<<qgrid, kBlendThreads, 0, st>>>(p);
   if (int e = check_launch("pf_lookup_onthefly_tc(blend)")) return e;

@@ -390,11 +390,10 @@ def channels_last_pyramid(fmap: torch.Tensor, num_levels: int) -> List[torch.Ten
 
 class OnTheFlyPlanes:
     """Tensor-core operands of one view for pf_lookup_onthefly_tc: fp16 hi/lo planes of the channels-last query features and
-    of every level of the pooled target pyramid (one shared split scale per tensor family), plus the view's per-query
-    local-plane scratch (PF_OTF_PLANE(l) floats per query and level, 32 KiB per query over four levels; O(N), allocated on
-    first use and reused by every lookup).  The
-    target planes hold every image row twice side by side ([B, Hl, 2 Wl, C]) so that windows across the ERP seam are one box."""
-    TILE_H, TILE_W, PLANE = 8, 16, (4096, 2048, 1024, 1024)      # PF_OTF_PLANE in include/priorcorr.h
+    of every level of the pooled target pyramid (one shared split scale per tensor family).  The target planes hold every
+    image row twice side by side ([B, Hl, 2 Wl, C]) so that windows across the ERP seam are one box."""
+    TILE_H, TILE_W = 8, 16
+    POOL_SEGMENTS_PER_QUERY = 2          # 16 KiB segments of the local-plane pool per query and view (32 KiB): O(N) scratch
 
     def __init__(self, f1: torch.Tensor, f2: Sequence[torch.Tensor]):
         lib = _lib.load()
@@ -415,18 +414,30 @@ class OnTheFlyPlanes:
                 _lib.check(lib.pf_onthefly_split(t.data_ptr(), t.numel(), a1, hi.data_ptr(), lo.data_ptr(), Wl * Ct, st), "pf_onthefly_split")
                 self.f2_hi.append(hi), self.f2_lo.append(lo)
             _count(3 + len(f2))
-        self.shape, self.levels, self._mini = tuple(f1.shape), len(f2), None
+        self.shape, self.levels = tuple(f1.shape), len(f2)
 
     @staticmethod
     def supported(f1: torch.Tensor, radius: int = 4) -> bool:
         B, h, w, Cn = f1.shape
         return radius == 4 and h % OnTheFlyPlanes.TILE_H == 0 and w % OnTheFlyPlanes.TILE_W == 0 and Cn % 128 == 0 and Cn <= 512
 
-    def mini(self):
-        if self._mini is None:
-            B, h, w, _ = self.shape
-            self._mini = [torch.empty((B, h, w, self.PLANE[min(l, 3)]), device=self.f1_hi.device, dtype=torch.float32) for l in range(self.levels)]
-        return self._mini
+
+_OTF_SCRATCH = {}
+
+
+def _otf_scratch(dev, views: int, L: int, B: int, h: int, w: int):
+    """The local-plane pool and the work buffer of pf_lookup_onthefly_tc: per device and shape, reused by every call (calls are
+    stream-ordered; allocate outside CUDA-graph capture — PriOrRAFT.graphed() warms up eagerly first)."""
+    key = (dev.index, views, L, B, h, w, OnTheFlyPlanes.POOL_SEGMENTS_PER_QUERY)
+    got = _OTF_SCRATCH.get(key)
+    if got is None:
+        tiles = (h // OnTheFlyPlanes.TILE_H) * (w // OnTheFlyPlanes.TILE_W)
+        T = views * L * B * tiles
+        segs = views * B * h * w * OnTheFlyPlanes.POOL_SEGMENTS_PER_QUERY
+        pool = torch.empty((segs, 128, 32), device=dev, dtype=torch.float32)
+        work = torch.empty(16 + 10 * T + 2 + 2 * (segs // 8 + T), device=dev, dtype=torch.int32)      # PF_OTF_WORK_INTS
+        got = _OTF_SCRATCH[key] = (pool, work, T)
+    return got
 
 
 def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence[torch.Tensor],
@@ -474,19 +485,16 @@ def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence
             t.base = a
             t.f1_hi_own, t.f1_lo_own = planes_own.f1_hi.data_ptr(), planes_own.f1_lo.data_ptr()
             t.f2_hi_own, t.f2_lo_own = _lib.level_ptrs(planes_own.f2_hi), _lib.level_ptrs(planes_own.f2_lo)
-            t.amax_own, t.mini_own = planes_own.amax.data_ptr(), _lib.level_ptrs(planes_own.mini())
+            t.amax_own = planes_own.amax.data_ptr()
             if dual:
                 t.f1_hi_other, t.f1_lo_other = planes_other.f1_hi.data_ptr(), planes_other.f1_lo.data_ptr()
                 t.f2_hi_other, t.f2_lo_other = _lib.level_ptrs(planes_other.f2_hi), _lib.level_ptrs(planes_other.f2_lo)
-                t.amax_other, t.mini_other = planes_other.amax.data_ptr(), _lib.level_ptrs(planes_other.mini())
-            tiles = (h // OnTheFlyPlanes.TILE_H) * (w // OnTheFlyPlanes.TILE_W)
-            box = torch.empty((2, (2 if dual else 1) * L * B * tiles * 4), device=dev, dtype=torch.int32)
-            t.box_lo, t.box_hi = box[0].data_ptr(), box[1].data_ptr()
-            work = torch.empty(4 + box.shape[1] // 4, device=dev, dtype=torch.int32)
-            t.worklist = work.data_ptr()
+                t.amax_other = planes_other.amax.data_ptr()
+            pool, work, T = _otf_scratch(dev, 2 if dual else 1, L, B, h, w)
+            t.pool, t.pool_segments, t.worklist = pool.data_ptr(), pool.shape[0], work.data_ptr()
             _lib.check(lib.pf_lookup_onthefly_tc(C.byref(t), _stream()), "pf_lookup_onthefly_tc")
-            _state["otf_boxes"] = box.view(2, 2 if dual else 1, L, B, tiles, 4)      # diagnostics: scripts/probe/otf_tiles.py
-            _count(5 if dual else 4)
+            _state["otf_work"] = (work, T, 2 if dual else 1, L, B)      # diagnostics: scripts/probe/otf_tiles.py
+            _count(6 if dual else 5)
         else:
             _lib.check(lib.pf_lookup_onthefly(C.byref(a), _stream()), "pf_lookup_onthefly")
             _count(2 if dual else 1)

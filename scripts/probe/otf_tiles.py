@@ -13,20 +13,21 @@ from prior_flow_b200 import ops  # noqa: E402
 
 def report(tag, coords, f1a, f2a, f1b, f2b, gw, gc, pla, plb):
     ops.lookup_onthefly(coords, f1a, f2a, f1b, f2b, gw, gc, 4, planes_own=pla, planes_other=plb)
-    box = ops._state["otf_boxes"]
-    lo, hi = box[0].long(), box[1].long()
+    work, T, views, L, B = ops._state["otf_work"]
+    work = work.cpu().long()
+    ctr = work[:16]
+    lo, hi = work[16:16 + 4 * T].view(views, L, B, -1, 4), work[16 + 4 * T:16 + 8 * T].view(views, L, B, -1, 4)
+    alloc = work[16 + 8 * T:16 + 9 * T].view(views, L, B, -1)
     bw = torch.minimum(hi[..., 0] - lo[..., 0], hi[..., 1] - lo[..., 1]) + 1      # the narrower of the two column numberings
     bh = hi[..., 2] - lo[..., 2] + 1
-    for v in range(box.shape[1]):
-        for l in range(box.shape[2]):
-            w_, h_ = bw[v, l].flatten(), bh[v, l].flatten()
-            valid = (w_ > 0) & (h_ > 0) & (w_ < 10000)
-            plane = (4096, 2048, 1024, 1024)[l]
-            pitch = torch.where(w_ <= 32, 32, torch.where(w_ <= 64, 64, 128))
-            fit = valid & (w_ <= 128) & (h_ * pitch <= plane)
+    print(f"[{tag}] tiles on the CUDA-core path {int(ctr[0])}, work items of the dots kernel {int(ctr[2])}, pool segments asked for {int(ctr[3])}")
+    for v in range(views):
+        for l in range(L):
+            w_, h_, a_ = bw[v, l].flatten(), bh[v, l].flatten(), alloc[v, l].flatten()
+            valid = a_ != -2
             print(f"[{tag}] view {v} level {l}: tiles {w_.numel()}, with taps {int(valid.sum())}, of those on tensor cores "
-                  f"{float(fit.sum()) / max(int(valid.sum()), 1):.2f}; median box {int(w_[valid].median())} x {int(h_[valid].median())}, "
-                  f"p90 {int(w_[valid].float().quantile(0.9))} x {int(h_[valid].float().quantile(0.9))}")
+                  f"{float((a_ >= 0).sum()) / max(int(valid.sum()), 1):.2f}; median box {int(w_[valid].median())} x {int(h_[valid].median())}, "
+                  f"p90 {int(w_[valid].float().quantile(0.9))} x {int(h_[valid].float().quantile(0.9))}, max {int(w_[valid].max())} x {int(h_[valid].max())}")
 
 
 def main():
