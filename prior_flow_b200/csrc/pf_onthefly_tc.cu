@@ -102,22 +102,20 @@ __device__ __forceinline__ float ot_split_scale(uint32_t amax_bits) {
 // chains separate by axis — x depends on the tap's column offset only, y on its row offset — so step 1 evaluates 18 chains per
 // query (own view: the final coordinates; other view: the coordinates into the rotation grid) and step 2 visits the 81 taps
 // (other view: the two grid samples and the final chains).  `use(q, t, ix, iy)` consumes a tap.  Contains one __syncthreads.
+// step 1 for item i = 18 q + j of the CTA: j < 9 the x chain of column offset j - 4, else the y chain of row offset j - 13
+__device__ __forceinline__ float tap_axis_coord(const OtfTcParams &p, int branch, int lvl, int b, int n, int j) {
+  const bool xaxis = j < 9;
+  const float c = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + (xaxis ? 0 : 1)) * p.N + n), 1.0f / (float)(1 << lvl));
+  const float pv = __fadd_rn(c, (float)((xaxis ? j : j - 9) - 4));
+  if (branch) return xaxis ? to_sample_coord(remainder_pos(pv, p.ax_gw.size), p.ax_gw, p.div_mode) : to_sample_coord(pv, p.ax_gh, p.div_mode);
+  return xaxis ? to_sample_coord(remainder_pos(pv, p.axW[lvl].size), p.axW[lvl], p.div_mode) : to_sample_coord(pv, p.axH[lvl], p.div_mode);
+}
 template <class F>
-__device__ __forceinline__ void cta_tap_coords(const OtfTcParams &p, int branch, int lvl, int b, int n0, float *s_axis /*[8][18]*/, F use) {
-  const Axis axW = p.axW[lvl], axH = p.axH[lvl], ax_gw = p.ax_gw, ax_gh = p.ax_gh;
-  const float inv_scale = 1.0f / (float)(1 << lvl);
+__device__ __forceinline__ void cta_tap_coords(const OtfTcParams &p, int branch, int lvl, int b, int n0, float *s_axis /*[16][18]*/, F use) {
+  const Axis axW = p.axW[lvl], axH = p.axH[lvl];
   for (int i = threadIdx.x; i < kBlendQueries * 18; i += kBlendThreads) {
     const int q = i / 18, j = i - q * 18, n = n0 + q;
-    if (n >= p.N) continue;
-    const bool xaxis = j < 9;
-    const float c = __fmul_rn(__ldg(p.coords + ((long long)b * 2 + (xaxis ? 0 : 1)) * p.N + n), inv_scale);
-    const float pv = __fadd_rn(c, (float)((xaxis ? j : j - 9) - 4));
-    float v;
-    if (branch)
-      v = xaxis ? to_sample_coord(remainder_pos(pv, ax_gw.size), ax_gw, p.div_mode) : to_sample_coord(pv, ax_gh, p.div_mode);
-    else
-      v = xaxis ? to_sample_coord(remainder_pos(pv, axW.size), axW, p.div_mode) : to_sample_coord(pv, axH, p.div_mode);
-    s_axis[i] = v;
+    if (n < p.N) s_axis[i] = tap_axis_coord(p, branch, lvl, b, n, j);
   }
   __syncthreads();
   const float *gridx = p.grid_w2c ? p.grid_w2c + (long long)b * p.grid_bs : nullptr, *gridy = gridx ? gridx + p.N : nullptr;
@@ -179,8 +177,29 @@ __global__ void __launch_bounds__(kBlendThreads) otf_box_kernel(const OtfTcParam
   const int n0 = blockIdx.x * kBlendQueries;
   // the 16 queries of a CTA are one row of a query tile
   if (threadIdx.x == 0) box_reset(s_box);
-  cta_tap_coords(p, branch, lvl, b, n0, s_axis, [&](int, int, float ix, float iy) { box_add_tap_warp(s_box, (int)floorf(ix), (int)floorf(iy), Wl, Hl); });
-  __syncthreads();
+  if (branch == 0) {
+    // own view: the taps are a product of 9 columns and 9 rows, so the box is the columns any query touches x the rows any
+    // query touches (a superset of the taps' union when some query misses the plane in one axis only: harmless)
+    __syncthreads();
+    for (int i = threadIdx.x; i < kBlendQueries * 18; i += kBlendThreads) {
+      const int q = i / 18, j = i - q * 18, n = n0 + q;
+      if (n >= p.N) continue;
+      const int c0 = (int)floorf(tap_axis_coord(p, 0, lvl, b, n, j));
+      if (j < 9) {
+        if (c0 + 1 >= 0 && c0 < Wl) {
+          const int xa = max(c0, 0), xb = min(c0 + 1, Wl - 1), ua = unwrap1(xa, Wl), ub = unwrap1(xb, Wl);
+          atomicMin(&s_box[0], xa), atomicMax(&s_box[1], xb), atomicMin(&s_box[2], min(ua, ub)), atomicMax(&s_box[3], max(ua, ub));
+        }
+      } else if (c0 + 1 >= 0 && c0 < Hl) {
+        atomicMin(&s_box[4], max(c0, 0)), atomicMax(&s_box[5], min(c0 + 1, Hl - 1));
+      }
+    }
+    __syncthreads();
+    if (s_box[0] > s_box[1]) return;      // no column touched: leave the tile's box as it is (uniform)
+  } else {
+    cta_tap_coords(p, branch, lvl, b, n0, s_axis, [&](int, int, float ix, float iy) { box_add_tap_warp(s_box, (int)floorf(ix), (int)floorf(iy), Wl, Hl); });
+    __syncthreads();
+  }
   if (threadIdx.x < 3 && s_box[4] <= s_box[5]) {
     const long long e = (long long)entry_of(p, branch, lvl, b, tile_of(p, n0)) * 4 + threadIdx.x;
     atomicMin(p.box_lo + e, s_box[2 * threadIdx.x]);

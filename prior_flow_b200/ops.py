@@ -433,7 +433,7 @@ def _otf_scratch(dev, views: int, L: int, B: int, h: int, w: int):
     if got is None:
         tiles = (h // OnTheFlyPlanes.TILE_H) * (w // OnTheFlyPlanes.TILE_W)
         T = views * L * B * tiles
-        segs = views * B * h * w * OnTheFlyPlanes.POOL_SEGMENTS_PER_QUERY
+        segs = max(8, int(views * B * h * w * OnTheFlyPlanes.POOL_SEGMENTS_PER_QUERY))
         pool = torch.empty((segs, 128, 32), device=dev, dtype=torch.float32)
         work = torch.empty(16 + 10 * T + 2 + 2 * (segs // 8 + T), device=dev, dtype=torch.int32)      # PF_OTF_WORK_INTS
         got = _OTF_SCRATCH[key] = (pool, work, T)

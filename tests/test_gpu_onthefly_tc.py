@@ -50,13 +50,31 @@ def test_tensor_core_onthefly_matches_materialised(B, h, w, scene):
         assert e_tc < 1e-5
 
 
+def test_small_pool_sends_the_overflow_to_the_cuda_core_path(monkeypatch):
+    """A pool that holds only part of the boxes: the tiles past its end take otf_fallback_kernel; same results."""
+    from prior_flow_b200 import ops
+    B, h, w = 1, 64, 128
+    fm, noisy, gw, gc = make_scene(B, h, w, 21)
+    pyr_a, pyr_b = ops.volume_pyramid(fm[0], fm[1], 4, "fp32"), ops.volume_pyramid(fm[2], fm[3], 4, "fp32")
+    for coords in (smooth_coords(B, h, w, 5, 6.0), noisy):
+        want = ops.lookup(coords, pyr_a, pyr_b, gw, gc, 4)
+        for per_query in (0.3, 0.02):
+            monkeypatch.setattr(ops.OnTheFlyPlanes, "POOL_SEGMENTS_PER_QUERY", per_query)
+            tc, _ = run_both(ops, coords, fm, gw, gc)
+            work, T = ops._state["otf_work"][:2]
+            on_cuda_cores = int(work[0])
+            print(f"\n[onthefly tc pool {per_query} segments/query] tiles on the CUDA-core path: {on_cuda_cores} of {T}")
+            assert on_cuda_cores > 0
+            for got, ref in zip(tc, want):
+                assert rel(got, ref) < 1e-5
+
+
 def test_single_view_and_zero_features():
     from prior_flow_b200 import ops
     B, h, w = 1, 32, 64
     fm, _, gw, gc = make_scene(B, h, w, 5)
     coords = smooth_coords(B, h, w, 9, 4.0)
     (tc,), (cc,) = run_both(ops, coords, fm, gw, gc, dual=False)
-    want = ops.lookup(coords, ops.volume_pyramid(fm[0], fm[1], 4, "fp32"), radius=4) if False else None
     assert rel(tc, cc) < 1e-5
     zero = [torch.zeros_like(t) for t in fm]
     (tz, _), _ = run_both(ops, coords, zero, gw, gc)
