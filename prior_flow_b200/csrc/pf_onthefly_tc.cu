@@ -31,7 +31,6 @@ namespace pf {
 
 constexpr int OT_TH = 8, OT_TW = 16;                 // query tile: 8 rows x 16 columns = 128 queries = TMEM lanes
 constexpr int OT_SEG = 128 * 32;                     // floats of a pool segment: 128 queries x 32 box pixels
-constexpr int OT_ITEM_CHUNKS = 4;                    // MMA passes (256 box pixels each) per work item
 constexpr int OT_BK = 64;
 constexpr int OT_APLANE = 128 * OT_BK * 2;           // 16 KiB
 constexpr int OT_BPLANE = 256 * OT_BK * 2;           // 32 KiB
@@ -65,6 +64,7 @@ struct OtfTcParams {
   int2 *items;                             // [max_items] (entry, first MMA pass)
   float *pool;                             // [pool_segs][128][32]: row r of a segment is query r of the tile, 16-byte groups XOR-swizzled by r & 7
   int pool_segs, max_items;
+  int item_chunks;                         // MMA passes (256 box pixels each) per work item
   const uint32_t *amax[2];                 // per view: absmax bits of {f1, f2} (split scales of the fp16 planes)
   float *out_own, *out_raw;
 };
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(1024) otf_alloc_kernel(const OtfTcParams p) {
     const bool shape_ok = read_box(p, e, tb);
     int a = tb.empty ? -2 : -1;
     if (shape_ok) {
-      if (off + tb.nseg() <= p.pool_segs) a = off, items += (tb.nchunks() + OT_ITEM_CHUNKS - 1) / OT_ITEM_CHUNKS;
+      if (off + tb.nseg() <= p.pool_segs) a = off, items += (tb.nchunks() + p.item_chunks - 1) / p.item_chunks;
       off += tb.nseg();
     }
     p.alloc[e] = a;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(1024) otf_alloc_kernel(const OtfTcParams p) {
     if (p.alloc[e] < 0) continue;
     TileBox tb;
     read_box(p, e, tb);
-    for (int c = 0; c < tb.nchunks(); c += OT_ITEM_CHUNKS, ++it)
+    for (int c = 0; c < tb.nchunks(); c += p.item_chunks, ++it)
       if (it < p.max_items) p.items[it] = make_int2(e, c);
   }
 }
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(OT_THREADS, 1) otf_dots_kernel(const __grid_co
         TileBox tb;
         read_box(p, item.x, tb);
         const OtfViewMaps &maps = all_maps.view[en.branch];
-        const int pi = pitch_index(tb.pitch), rpc = tb.rpc(), c1 = min(item.y + OT_ITEM_CHUNKS, tb.nchunks());
+        const int pi = pitch_index(tb.pitch), rpc = tb.rpc(), c1 = min(item.y + p.item_chunks, tb.nchunks());
         const int ty = en.tile / p.tiles_x, tx = en.tile - ty * p.tiles_x;
         for (int c = item.y; c < c1; ++c)
           for (int kb = 0; kb < kblocks; ++kb) {
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(OT_THREADS, 1) otf_dots_kernel(const __grid_co
         const int2 item = p.items[it];
         TileBox tb;
         read_box(p, item.x, tb);
-        const int rpc = tb.rpc(), c1 = min(item.y + OT_ITEM_CHUNKS, tb.nchunks());
+        const int rpc = tb.rpc(), c1 = min(item.y + p.item_chunks, tb.nchunks());
         for (int c = item.y; c < c1; ++c) {
           mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
           tc_fence_after();
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(OT_THREADS, 1) otf_dots_kernel(const __grid_co
       const Entry en = decode_entry(p, item.x);
       TileBox tb;
       read_box(p, item.x, tb);
-      const int rpc = tb.rpc(), spr = tb.spr(), c1 = min(item.y + OT_ITEM_CHUNKS, tb.nchunks());
+      const int rpc = tb.rpc(), spr = tb.spr(), c1 = min(item.y + p.item_chunks, tb.nchunks());
       const float scale = p.scale / (ot_split_scale(p.amax[en.branch][0]) * ot_split_scale(p.amax[en.branch][1]));
       float *planes = p.pool + (long long)p.alloc[item.x] * OT_SEG;
       for (int c = item.y; c < c1; ++c) {
@@ -740,6 +740,12 @@ extern "C" int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *t, void *stream)
   p.scale = 1.0f / sqrtf((float)C);
   // the work buffer: PF_OTF_WORK_INTS(T, pool_segments) ints = [16 counters | box_lo 4T | box_hi 4T | alloc T | fb_list T | items 2 * max_items]
   p.pool = t->pool, p.pool_segs = (int)t->pool_segments, p.max_items = (int)(t->pool_segments / 8) + p.T;
+  static const int item_chunks = [] {
+    const char *e = getenv("PF_OTF_ITEM_CHUNKS");       // tuning knob: passes per work item (balance vs per-item latency)
+    const int v = e ? atoi(e) : 1;
+    return v >= 1 && v <= 64 ? v : 1;
+  }();
+  p.item_chunks = item_chunks;
   p.ctr = t->worklist;
   p.box_lo = t->worklist + 16, p.box_hi = p.box_lo + 4 * p.T;
   p.alloc = p.box_hi + 4 * p.T, p.fb_list = p.alloc + p.T;
