@@ -208,12 +208,10 @@ def lookup(coords: torch.Tensor, pyr_own: Sequence[torch.Tensor], pyr_other: Opt
 
 
 # ------------------------------------------------------------------------------------------ (f1)
-_conv_weight_cache = {}
-
-
 def prepare_conv_weight(weight: torch.Tensor) -> torch.Tensor:
-    """Conv2d(324, 256, 1) weight -> the K-major fp16 hi/lo planes pf_dccl_conv streams with TMA (cached per tensor
-    version: call again after an optimizer step)."""
+    """Conv2d(324, 256, 1) weight -> the K-major fp16 hi/lo planes pf_dccl_conv streams with TMA.  The planes are cached ON the
+    tensor object, keyed by its storage address and version counter (an optimizer step or load_state_dict bumps the version);
+    a cache keyed by address alone would hand a new layer the planes of a freed one whose memory it reuses."""
     lib = _lib.load()
     _chk(weight, "weight")
     if weight.dim() == 4:
@@ -222,9 +220,9 @@ def prepare_conv_weight(weight: torch.Tensor) -> torch.Tensor:
     elif weight.dim() != 2:
         raise ValueError("weight must be [256, 324] or [256, 324, 1, 1]")
     key = (weight.data_ptr(), weight._version, str(weight.device))
-    hit = _conv_weight_cache.get(key)
-    if hit is not None:
-        return hit
+    hit = getattr(weight, "_pf_conv_planes", None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
     w2 = weight.detach().reshape(weight.shape[0], weight.shape[1]).contiguous()
     with torch.cuda.device(weight.device):
         nbytes = lib.pf_dccl_conv_weight_bytes()
@@ -234,9 +232,10 @@ def prepare_conv_weight(weight: torch.Tensor) -> torch.Tensor:
         _lib.check(lib.pf_dccl_conv_prepare(w2.data_ptr(), w2.shape[0], w2.shape[1], prepared.data_ptr(), _stream()),
                    "pf_dccl_conv_prepare")
         _count(2)
-    if len(_conv_weight_cache) > 16:
-        _conv_weight_cache.clear()
-    _conv_weight_cache[key] = prepared
+    try:
+        weight._pf_conv_planes = (key, prepared)
+    except AttributeError:      # an object that takes no attributes: prepared again on the next call
+        pass
     return prepared
 
 

@@ -101,3 +101,22 @@ def test_model_with_fused_first_layer_matches_unfused():
         assert epe(a, b) < 1e-3 and epe(a, c) < 1e-3
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+def test_prepared_weight_planes_follow_the_tensor_not_its_address():
+    """r03z regression: the prepared planes were cached by (address, version counter); a new layer allocated where a freed one
+    had been (same address, version 0) got the old layer's planes.  They now live on the tensor object.  `.data` gives the
+    deterministic stand-in for that: a fresh tensor object at the same address with its own version counter at 0."""
+    from prior_flow_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    w1 = torch.randn(256, 324, 1, 1, device="cuda", generator=g)
+    p1 = ops.prepare_conv_weight(w1)
+    assert ops.prepare_conv_weight(w1) is p1                            # cached on the tensor
+    old_planes = p1.clone()
+    w1.data.copy_(torch.randn(256, 324, 1, 1, device="cuda", generator=g))      # new contents, w1's own counter untouched
+    w2 = w1.data
+    assert w2.data_ptr() == w1.data_ptr() and w2._version == w1._version == 0
+    assert not torch.equal(ops.prepare_conv_weight(w2), old_planes)     # an (address, version) cache would return old_planes
+    before = ops.prepare_conv_weight(w2).clone()
+    w2.mul_(1.5)                                                        # in-place update: version bump -> prepared again
+    assert not torch.equal(ops.prepare_conv_weight(w2), before)
