@@ -181,6 +181,8 @@ typedef struct pf_onthefly_tc_args {
   float *pool;                                /* scratch: pool_segments * PF_OTF_SEGMENT_BYTES bytes, 128-B aligned */
   long long pool_segments;
   int *worklist;                              /* scratch: PF_OTF_WORK_INTS(T, pool_segments) ints, 16-B aligned     */
+  int no_rotate;                              /* 1: stop before img_rotate and leave BOTH views channels-last — out_own and
+                                               * scratch as [B, h, w, L*81] — the inputs of pf_dccl_conv (own_cl, raw)   */
 } pf_onthefly_tc_args;
 int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *args, void *stream);
 int pf_onthefly_absmax(const float *x, long long count, void *amax_word, void *stream);

@@ -169,8 +169,16 @@ class DCCL:
     def summed_conv(self, coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x, conv,
                     channels_last: bool = False, fp32: bool = True):
         """`F.relu(conv(corr_own + corr_other))` for the motion encoder's first layer `conv` = Conv2d(324, 256, 1)
-        (core/update.py:168,184 / :85,92) without ever forming the [B,324,h,w] sum: inference only, materialised pyramids."""
-        if isinstance(corr_pyramid_A, FeaturePyramid) or torch.is_grad_enabled() and (conv.weight.requires_grad or corr_pyramid_A[0].requires_grad):
+        (core/update.py:168,184 / :85,92) without ever forming the [B,324,h,w] sum: inference only; materialised pyramids or
+        the tensor-core on-the-fly lookup."""
+        if isinstance(corr_pyramid_A, FeaturePyramid):
+            if corr_pyramid_A.planes is not None and corr_pyramid_B.planes is not None and not torch.is_grad_enabled():
+                return ops.lookup_onthefly_conv(coords.float(), corr_pyramid_A.f1, corr_pyramid_A.f2, corr_pyramid_B.f1, corr_pyramid_B.f2,
+                                                sample_grid_A2B_W2C_8x, sample_grid_B2A_8x, corr_pyramid_A.planes, corr_pyramid_B.planes,
+                                                conv.weight, conv.bias, channels_last=channels_last, fp32=fp32)
+            x = self.summed(coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x, channels_last)
+            return torch.relu(conv(x))
+        if torch.is_grad_enabled() and (conv.weight.requires_grad or corr_pyramid_A[0].requires_grad):
             x = self.summed(coords, corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x, channels_last)
             return torch.relu(conv(x))
         return ops.lookup_conv(coords.float(), corr_pyramid_A, corr_pyramid_B, sample_grid_A2B_W2C_8x, sample_grid_B2A_8x,

@@ -67,6 +67,7 @@ struct OtfTcParams {
   int item_chunks;                         // MMA passes (256 box pixels each) per work item
   const uint32_t *amax[2];                 // per view: absmax bits of {f1, f2} (split scales of the fp16 planes)
   float *out_own, *out_raw;
+  int own_cl;                              // own view channels-last [B, N, L*81] like out_raw (for pf_dccl_conv), no rotate pass
 };
 
 __device__ __forceinline__ int tile_of(const OtfTcParams &p, int n) {
@@ -496,7 +497,7 @@ __device__ __forceinline__ float ot_dot4(const float *const (&ptr)[4], const flo
 // [B, N, L*K2] pre-rotation map (contiguous per query), see pf_lookup.cu
 __device__ __forceinline__ void write_taps(const OtfTcParams &p, const float (*s_out)[kBlendQueries + 1], int branch, int lvl, int b, int n0) {
   constexpr int K2 = kMaxTaps;
-  if (branch == 0) {
+  if (branch == 0 && !p.own_cl) {
     float *out = p.out_own + ((long long)b * p.L + lvl) * K2 * (long long)p.N + n0;
     for (int i = threadIdx.x; i < K2 * kBlendQueries; i += kBlendThreads) {
       const int ch = i / kBlendQueries, q = i - ch * kBlendQueries;
@@ -505,7 +506,7 @@ __device__ __forceinline__ void write_taps(const OtfTcParams &p, const float (*s
   } else {
     for (int i = threadIdx.x; i < K2 * kBlendQueries; i += kBlendThreads) {
       const int q = i / K2, ch = i - q * K2;
-      if (n0 + q < p.N) p.out_raw[(((long long)b * p.N + n0 + q) * p.L + lvl) * K2 + ch] = s_out[ch][q];
+      if (n0 + q < p.N) (branch ? p.out_raw : p.out_own)[(((long long)b * p.N + n0 + q) * p.L + lvl) * K2 + ch] = s_out[ch][q];
     }
   }
 }
@@ -717,7 +718,8 @@ extern "C" int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *t, void *stream)
   PF_REQUIRE(a->coords && a->fmap1_own && a->out_own && t->worklist && t->pool && t->amax_own, "pf_lookup_onthefly_tc: null pointer");
   PF_REQUIRE(t->pool_segments >= 8 && t->pool_segments < (1ll << 30), "pf_lookup_onthefly_tc: pool_segments must be in [8, 2^30)");
   const bool dual = a->fmap1_other != nullptr;
-  PF_REQUIRE(!dual || (a->grid_w2c && a->grid_c2w && a->out_other && a->scratch && t->amax_other), "pf_lookup_onthefly_tc: dual lookup needs grids, out_other, scratch");
+  PF_REQUIRE(!dual || (a->grid_w2c && a->scratch && t->amax_other && (t->no_rotate || (a->grid_c2w && a->out_other))),
+             "pf_lookup_onthefly_tc: dual lookup needs grids, out_other, scratch");
   cudaStream_t st = (cudaStream_t)stream;
   const int views = dual ? 2 : 1, L = a->num_levels, B = a->batch, h = a->h, w = a->w, C = a->channels, N = h * w;
   OtfTcParams p;
@@ -751,7 +753,7 @@ extern "C" int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *t, void *stream)
   p.alloc = p.box_hi + 4 * p.T, p.fb_list = p.alloc + p.T;
   p.items = reinterpret_cast<int2 *>(p.fb_list + p.T + (p.T & 1));
   p.amax[0] = reinterpret_cast<const uint32_t *>(t->amax_own), p.amax[1] = reinterpret_cast<const uint32_t *>(t->amax_other);
-  p.out_own = a->out_own, p.out_raw = a->scratch;
+  p.out_own = a->out_own, p.out_raw = a->scratch, p.own_cl = t->no_rotate ? 1 : 0;
   const size_t table = (size_t)p.T * 4 * sizeof(int);
   if (cudaMemsetAsync(p.ctr, 0, 16 * sizeof(int), st) != cudaSuccess || cudaMemsetAsync(p.box_lo, 0x7f, table, st) != cudaSuccess ||
       cudaMemsetAsync(p.box_hi, 0x80, table, st) != cudaSuccess)
@@ -802,7 +804,7 @@ extern "C" int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *t, void *stream)
   if (int e = check_launch("pf_lookup_onthefly_tc(fallback)")) return e;
   otf_blend_kernel<<<qgrid, kBlendThreads, 0, st>>>(p);
   if (int e = check_launch("pf_lookup_onthefly_tc(blend)")) return e;
-  if (dual)
+  if (dual && !t->no_rotate)
     return rotate_forward(B, h, w, L, a->radius, a->div_mode, a->grid_c2w, a->grid_batch_stride, a->scratch, a->out_other, 0, 0, st, nullptr);
   return 0;
 }

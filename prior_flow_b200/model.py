@@ -338,7 +338,7 @@ class PriOrRAFT(nn.Module):
             with amp():
                 # corr_A + corr_B_A and corr_B + corr_A_B (prior_raft.py:185-188), the adds fused into the rotate kernel
                 fused1 = (self.fuse_conv1 and not torch.is_grad_enabled() and not self.args.mixed_precision
-                          and isinstance(pyr_A, list))
+                          and (isinstance(pyr_A, list) or getattr(pyr_A, "planes", None) is not None))
                 corr_A = corr_B = cor1_A = cor1_B = None
                 if fused1:
                     fp32 = not torch.backends.cudnn.allow_tf32     # the precision cuDNN would run this layer in

@@ -443,9 +443,11 @@ def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence
                     f1_other: Optional[torch.Tensor] = None, f2_other: Optional[Sequence[torch.Tensor]] = None,
                     grid_w2c: Optional[torch.Tensor] = None, grid_c2w: Optional[torch.Tensor] = None,
                     radius: int = 4, cyclic: bool = True, planes_own: Optional["OnTheFlyPlanes"] = None,
-                    planes_other: Optional["OnTheFlyPlanes"] = None):
+                    planes_other: Optional["OnTheFlyPlanes"] = None, _no_rotate: bool = False):
     """Volume-free lookup.  f1_* are channels-last [B,h,w,C]; f2_* are channels_last_pyramid() lists.  With `planes_*`
-    (OnTheFlyPlanes of the same operands) the dot products run on tensor cores (pf_lookup_onthefly_tc)."""
+    (OnTheFlyPlanes of the same operands) the dot products run on tensor cores (pf_lookup_onthefly_tc).
+    `_no_rotate` (tensor-core dual lookup only): returns (own, raw) channels-last [B,h,w,L*81] before img_rotate — the inputs
+    of pf_dccl_conv, see lookup_onthefly_conv."""
     lib = _lib.load()
     _chk(coords, "coords", 4)
     coords = coords.contiguous()
@@ -461,8 +463,11 @@ def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence
     dual = f1_other is not None
     K2 = (2 * radius + 1) ** 2
     dev = coords.device
+    tc = planes_own is not None and cyclic and radius == 4 and (not dual or planes_other is not None)
+    if _no_rotate and not (tc and dual):
+        raise ValueError("_no_rotate needs the tensor-core dual lookup")
     with torch.cuda.device(dev):
-        out_own = torch.empty((B, L * K2, h, w), device=dev, dtype=torch.float32)
+        out_own = torch.empty((B, h, w, L * K2) if _no_rotate else (B, L * K2, h, w), device=dev, dtype=torch.float32)
         a = _lib.OnTheFlyArgs()
         a.batch, a.channels, a.h, a.w = B, Cn, h, w
         a.radius, a.num_levels, a.cyclic, a.div_mode = radius, L, int(cyclic), _state["div_mode"]
@@ -475,13 +480,15 @@ def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence
             if bs_w != bs_c:
                 gw, gc = gw.expand(B, 2, h, w).contiguous(), gc.expand(B, 2, h, w).contiguous()
                 bs_w = gw.stride(0)
-            out_other, scratch = torch.empty_like(out_own), torch.empty_like(out_own)
+            scratch = torch.empty_like(out_own)
+            out_other = None if _no_rotate else torch.empty_like(out_own)
             a.fmap1_other, a.fmap2_other = f1_other.data_ptr(), _lib.level_ptrs(list(f2_other))
             a.grid_w2c, a.grid_c2w, a.grid_batch_stride = gw.data_ptr(), gc.data_ptr(), bs_w
-            a.out_other, a.scratch = out_other.data_ptr(), scratch.data_ptr()
-        if planes_own is not None and cyclic and radius == 4 and (not dual or planes_other is not None):
+            a.out_other, a.scratch = (out_other.data_ptr() if out_other is not None else None), scratch.data_ptr()
+        if tc:
             t = _lib.OnTheFlyTcArgs()
             t.base = a
+            t.no_rotate = int(_no_rotate)
             t.f1_hi_own, t.f1_lo_own = planes_own.f1_hi.data_ptr(), planes_own.f1_lo.data_ptr()
             t.f2_hi_own, t.f2_lo_own = _lib.level_ptrs(planes_own.f2_hi), _lib.level_ptrs(planes_own.f2_lo)
             t.amax_own = planes_own.amax.data_ptr()
@@ -493,11 +500,40 @@ def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence
             t.pool, t.pool_segments, t.worklist = pool.data_ptr(), pool.shape[0], work.data_ptr()
             _lib.check(lib.pf_lookup_onthefly_tc(C.byref(t), _stream()), "pf_lookup_onthefly_tc")
             _state["otf_work"] = (work, T, 2 if dual else 1, L, B)      # diagnostics: scripts/probe/otf_tiles.py
-            _count(6 if dual else 5)
+            _count((6 if dual else 5) - int(_no_rotate))
+            if _no_rotate:
+                return out_own, scratch, gc, bs_w
         else:
             _lib.check(lib.pf_lookup_onthefly(C.byref(a), _stream()), "pf_lookup_onthefly")
             _count(2 if dual else 1)
     return (out_own, out_other) if dual else out_own
+
+
+def lookup_onthefly_conv(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence[torch.Tensor], f1_other: torch.Tensor,
+                         f2_other: Sequence[torch.Tensor], grid_w2c: torch.Tensor, grid_c2w: torch.Tensor, planes_own: "OnTheFlyPlanes",
+                         planes_other: "OnTheFlyPlanes", weight: torch.Tensor, bias: torch.Tensor, channels_last: bool = False,
+                         fp32: bool = True) -> torch.Tensor:
+    """lookup_conv for the volume-free mode: relu(conv1x1(own + img_rotate(other))) with the tensor-core on-the-fly lookup
+    leaving both views channels-last and pf_dccl_conv rotating, summing and convolving (SURVEY §8 f1 behind kernel (c))."""
+    lib = _lib.load()
+    _chk(bias, "bias", 1)
+    prepared = prepare_conv_weight(weight)
+    own_cl, raw, gc, bs = lookup_onthefly(coords, f1_own, f2_own, f1_other, f2_other, grid_w2c, grid_c2w, 4, True, planes_own, planes_other,
+                                          _no_rotate=True)
+    B, h, w, K = own_cl.shape
+    if K != 324:
+        raise ValueError("lookup_onthefly_conv is built for the model's 4-level, radius-4 lookup")
+    dev = coords.device
+    with torch.cuda.device(dev):
+        out = torch.empty((B, h, w, 256) if channels_last else (B, 256, h, w), device=dev, dtype=torch.float32)
+        c = _lib.DcclConvArgs()
+        c.batch, c.h, c.w, c.in_channels, c.out_channels = B, h, w, 324, 256
+        c.div_mode, c.split, c.out_channels_last, c.after_lookup = _state["div_mode"], int(fp32), int(channels_last), 0
+        c.raw, c.own_cl, c.grid_c2w, c.grid_batch_stride = raw.data_ptr(), own_cl.data_ptr(), gc.data_ptr(), bs
+        c.prepared_weight, c.bias, c.out = prepared.data_ptr(), bias.contiguous().data_ptr(), out.data_ptr()
+        _lib.check(lib.pf_dccl_conv(C.byref(c), _stream()), "pf_dccl_conv")
+        _count(1)
+    return _as_nchw_view(out) if channels_last else out
 
 
 # ------------------------------------------------------------------------------------------ (c) backward

@@ -107,3 +107,29 @@ def test_model_onthefly_mode_uses_planes_and_matches(monkeypatch):
             outs[flag] = d(coords, pa, pb, gw, gc)
     for a, b in zip(outs["1"], outs["0"]):
         assert rel(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 64, 128), (2, 16, 32)])
+def test_onthefly_lookup_with_fused_first_conv(B, h, w):
+    """SURVEY §8 f1 behind the volume-free lookup: both views stay channels-last, pf_dccl_conv rotates, sums, convolves."""
+    from prior_flow_b200 import ops
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        fm, _, gw, gc = make_scene(B, h, w, 31 + h)
+        coords = smooth_coords(B, h, w, 17, 5.0)
+        conv = torch.nn.Conv2d(324, 256, 1).cuda()
+        cl = lambda t: t.permute(0, 2, 3, 1).contiguous()
+        f1a, f2a, f1b, f2b = cl(fm[0]), ops.channels_last_pyramid(fm[1], 4), cl(fm[2]), ops.channels_last_pyramid(fm[3], 4)
+        pa, pb = ops.OnTheFlyPlanes(f1a, f2a), ops.OnTheFlyPlanes(f1b, f2b)
+        with torch.no_grad():
+            own, other = ops.lookup_onthefly(coords, f1a, f2a, f1b, f2b, gw, gc, 4, planes_own=pa, planes_other=pb)
+            want = torch.relu(conv(own + other))
+            for chl in (False, True):
+                got = ops.lookup_onthefly_conv(coords, f1a, f2a, f1b, f2b, gw, gc, pa, pb, conv.weight, conv.bias, channels_last=chl, fp32=True)
+                assert got.shape == want.shape
+                e = rel(got, want)
+                print(f"\n[onthefly tc + conv1 B{B} {h}x{w} cl={chl}] vs cuDNN fp32 on the un-fused lookup: {e:.2e}")
+                assert e < 1e-5
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
