@@ -181,6 +181,7 @@ typedef struct pf_onthefly_tc_args {
   float *pool;                                /* scratch: pool_segments * PF_OTF_SEGMENT_BYTES bytes, 128-B aligned */
   long long pool_segments;
   int *worklist;                              /* scratch: PF_OTF_WORK_INTS(T, pool_segments) ints, 16-B aligned     */
+  float *tap_xy;                              /* scratch (dual lookups): L * B * h * w * 81 * 2 floats, 8-B aligned  */
   int no_rotate;                              /* 1: stop before img_rotate and leave BOTH views channels-last — out_own and
                                                * scratch as [B, h, w, L*81] — the inputs of pf_dccl_conv (own_cl, raw)   */
 } pf_onthefly_tc_args;

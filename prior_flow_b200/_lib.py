@@ -66,7 +66,7 @@ class OnTheFlyTcArgs(C.Structure):
     _fields_ = [("base", OnTheFlyArgs),
                 ("f1_hi_own", _fp), ("f1_lo_own", _fp), ("f2_hi_own", _LevelPtrs), ("f2_lo_own", _LevelPtrs),
                 ("f1_hi_other", _fp), ("f1_lo_other", _fp), ("f2_hi_other", _LevelPtrs), ("f2_lo_other", _LevelPtrs),
-                ("amax_own", _fp), ("amax_other", _fp), ("pool", _fp), ("pool_segments", C.c_longlong), ("worklist", _fp), ("no_rotate", C.c_int)]
+                ("amax_own", _fp), ("amax_other", _fp), ("pool", _fp), ("pool_segments", C.c_longlong), ("worklist", _fp), ("tap_xy", _fp), ("no_rotate", C.c_int)]
 
 
 class RemapArgs(C.Structure):

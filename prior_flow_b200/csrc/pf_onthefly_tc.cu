@@ -67,6 +67,8 @@ struct OtfTcParams {
   int item_chunks;                         // MMA passes (256 box pixels each) per work item
   const uint32_t *amax[2];                 // per view: absmax bits of {f1, f2} (split scales of the fp16 planes)
   float *out_own, *out_raw;
+  float2 *tapxy;                           // [L][B][N][81] sample coordinates of the other view's taps: written by the box kernel,
+                                           // read by the blend (the chain through the rotation grid is evaluated once)
   int own_cl;                              // own view channels-last [B, N, L*81] like out_raw (for pf_dccl_conv), no rotate pass
 };
 
@@ -198,7 +200,11 @@ __global__ void __launch_bounds__(kBlendThreads) otf_box_kernel(const OtfTcParam
     __syncthreads();
     if (s_box[0] > s_box[1]) return;      // no column touched: leave the tile's box as it is (uniform)
   } else {
-    cta_tap_coords(p, branch, lvl, b, n0, s_axis, [&](int, int, float ix, float iy) { box_add_tap_warp(s_box, (int)floorf(ix), (int)floorf(iy), Wl, Hl); });
+    float2 *xy = p.tapxy + (((long long)lvl * p.B + b) * p.N + n0) * kMaxTaps;
+    cta_tap_coords(p, branch, lvl, b, n0, s_axis, [&](int q, int t, float ix, float iy) {
+      xy[q * kMaxTaps + t] = make_float2(ix, iy);
+      box_add_tap_warp(s_box, (int)floorf(ix), (int)floorf(iy), Wl, Hl);
+    });
     __syncthreads();
   }
   if (threadIdx.x < 3 && s_box[4] <= s_box[5]) {
@@ -533,7 +539,7 @@ __global__ void __launch_bounds__(kBlendThreads) otf_blend_kernel(const OtfTcPar
   const int spr = tb.spr();
   const int qrow0 = ((n0 / p.w) % OT_TH) * OT_TW;     // row of query n0 in its tile's segments
   const float *planes = p.pool + (long long)first * OT_SEG;
-  cta_tap_coords(p, branch, lvl, b, n0, s_axis, [&](int q, int t, float ix, float iy) {
+  auto blend_tap = [&](int q, int t, float ix, float iy) {
     const Taps tp = make_taps(ix, iy);
     const bool xin0 = (unsigned)tp.x0 < (unsigned)Wl, xin1 = (unsigned)(tp.x0 + 1) < (unsigned)Wl;
     const bool yin0 = (unsigned)tp.y0 < (unsigned)Hl, yin1 = (unsigned)(tp.y0 + 1) < (unsigned)Hl;
@@ -556,7 +562,18 @@ __global__ void __launch_bounds__(kBlendThreads) otf_blend_kernel(const OtfTcPar
     acc = __fmaf_rn(v_sw, tp.sw, acc);
     acc = __fmaf_rn(v_se, tp.se, acc);
     s_out[t][q] = acc;
-  });
+  };
+  if (branch) {      // the other view's coordinates were stashed by otf_box_kernel
+    const float2 *xy = p.tapxy + (((long long)lvl * p.B + b) * p.N + n0) * kMaxTaps;
+    for (int i = threadIdx.x; i < kBlendQueries * kMaxTaps; i += kBlendThreads) {
+      const int q = i / kMaxTaps;
+      if (n0 + q >= p.N) break;
+      const float2 c = __ldg(xy + i);
+      blend_tap(q, i - q * kMaxTaps, c.x, c.y);
+    }
+  } else {
+    cta_tap_coords(p, branch, lvl, b, n0, s_axis, blend_tap);
+  }
   __syncthreads();
   write_taps(p, s_out, branch, lvl, b, n0);
 }
@@ -718,7 +735,7 @@ extern "C" int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *t, void *stream)
   PF_REQUIRE(a->coords && a->fmap1_own && a->out_own && t->worklist && t->pool && t->amax_own, "pf_lookup_onthefly_tc: null pointer");
   PF_REQUIRE(t->pool_segments >= 8 && t->pool_segments < (1ll << 30), "pf_lookup_onthefly_tc: pool_segments must be in [8, 2^30)");
   const bool dual = a->fmap1_other != nullptr;
-  PF_REQUIRE(!dual || (a->grid_w2c && a->scratch && t->amax_other && (t->no_rotate || (a->grid_c2w && a->out_other))),
+  PF_REQUIRE(!dual || (a->grid_w2c && a->scratch && t->amax_other && t->tap_xy && (t->no_rotate || (a->grid_c2w && a->out_other))),
              "pf_lookup_onthefly_tc: dual lookup needs grids, out_other, scratch");
   cudaStream_t st = (cudaStream_t)stream;
   const int views = dual ? 2 : 1, L = a->num_levels, B = a->batch, h = a->h, w = a->w, C = a->channels, N = h * w;
@@ -754,6 +771,7 @@ extern "C" int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *t, void *stream)
   p.items = reinterpret_cast<int2 *>(p.fb_list + p.T + (p.T & 1));
   p.amax[0] = reinterpret_cast<const uint32_t *>(t->amax_own), p.amax[1] = reinterpret_cast<const uint32_t *>(t->amax_other);
   p.out_own = a->out_own, p.out_raw = a->scratch, p.own_cl = t->no_rotate ? 1 : 0;
+  p.tapxy = reinterpret_cast<float2 *>(t->tap_xy);
   const size_t table = (size_t)p.T * 4 * sizeof(int);
   if (cudaMemsetAsync(p.ctr, 0, 16 * sizeof(int), st) != cudaSuccess || cudaMemsetAsync(p.box_lo, 0x7f, table, st) != cudaSuccess ||
       cudaMemsetAsync(p.box_hi, 0x80, table, st) != cudaSuccess)

@@ -435,7 +435,8 @@ def _otf_scratch(dev, views: int, L: int, B: int, h: int, w: int):
         segs = max(8, int(views * B * h * w * OnTheFlyPlanes.POOL_SEGMENTS_PER_QUERY))
         pool = torch.empty((segs, 128, 32), device=dev, dtype=torch.float32)
         work = torch.empty(16 + 10 * T + 2 + 2 * (segs // 8 + T), device=dev, dtype=torch.int32)      # PF_OTF_WORK_INTS
-        got = _OTF_SCRATCH[key] = (pool, work, T)
+        tap_xy = torch.empty((L, B, h * w, 81, 2), device=dev, dtype=torch.float32) if views == 2 else None
+        got = _OTF_SCRATCH[key] = (pool, work, T, tap_xy)
     return got
 
 
@@ -496,8 +497,9 @@ def lookup_onthefly(coords: torch.Tensor, f1_own: torch.Tensor, f2_own: Sequence
                 t.f1_hi_other, t.f1_lo_other = planes_other.f1_hi.data_ptr(), planes_other.f1_lo.data_ptr()
                 t.f2_hi_other, t.f2_lo_other = _lib.level_ptrs(planes_other.f2_hi), _lib.level_ptrs(planes_other.f2_lo)
                 t.amax_other = planes_other.amax.data_ptr()
-            pool, work, T = _otf_scratch(dev, 2 if dual else 1, L, B, h, w)
+            pool, work, T, tap_xy = _otf_scratch(dev, 2 if dual else 1, L, B, h, w)
             t.pool, t.pool_segments, t.worklist = pool.data_ptr(), pool.shape[0], work.data_ptr()
+            t.tap_xy = tap_xy.data_ptr() if tap_xy is not None else None
             _lib.check(lib.pf_lookup_onthefly_tc(C.byref(t), _stream()), "pf_lookup_onthefly_tc")
             _state["otf_work"] = (work, T, 2 if dual else 1, L, B)      # diagnostics: scripts/probe/otf_tiles.py
             _count((6 if dual else 5) - int(_no_rotate))
