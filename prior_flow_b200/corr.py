@@ -15,6 +15,7 @@ avg-pool kernel), and `CostVolume.materialize()` gives that tensor to callers th
 from __future__ import annotations
 
 import os
+import time
 from typing import List, Optional, Sequence
 
 import torch
@@ -27,16 +28,29 @@ from . import ops
 AUTO_MATERIALIZE_FRACTION = 0.4     # of the currently free device memory, for the two pyramids + split workspace
 
 
+DRIVER_FREE_TTL_S = 1.0             # how long a cudaMemGetInfo answer is reused (see available_device_memory)
+_driver_free = {}                   # str(device) -> (monotonic time, driver-free bytes, torch-reserved bytes at that moment)
+
+
 def available_device_memory(device) -> int:
     """Bytes a new allocation can use: what the driver reports free PLUS what PyTorch's caching allocator holds but has not
     handed out (reserved - allocated).  `mem_get_info` alone shrinks as a long-running process caches freed blocks, which would
-    silently push `mode="auto"` onto the slower volume-free path."""
-    free = torch.cuda.mem_get_info(device)[0]
+    silently push `mode="auto"` onto the slower volume-free path.
+    The driver query (cudaMemGetInfo) is reused for DRIVER_FREE_TTL_S: the reference builds a new DCCL per forward, so `auto`
+    asks per forward, and inside a process with CUDA graphs and gigabytes of cached blocks the call was measured at 2-17 ms
+    (r03z: it was the whole 5.6 ms of the drop-in's build_pyramid stage).  Between queries the estimate follows the caching
+    allocator's own counters, which are exact and cost microseconds."""
+    key = str(device)
     try:
-        free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+        reserved, allocated = torch.cuda.memory_reserved(device), torch.cuda.memory_allocated(device)
     except Exception:  # noqa: BLE001 - a mocked / uninitialised device
-        pass
-    return int(free)
+        reserved = allocated = 0
+    now = time.monotonic()
+    hit = _driver_free.get(key)
+    if hit is None or now - hit[0] > DRIVER_FREE_TTL_S:
+        hit = _driver_free[key] = (now, int(torch.cuda.mem_get_info(device)[0]), reserved)
+    driver_free = hit[1] - max(0, reserved - hit[2])          # what the allocator took from the driver since the query
+    return int(max(0, driver_free) + reserved - allocated)
 
 
 class CostVolume:

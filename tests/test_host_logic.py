@@ -96,6 +96,7 @@ def test_dccl_auto_mode_decides_by_free_memory_once(monkeypatch):
     fmap = SimpleNamespace(shape=(1, 256, 128, 256), device="cuda:0", is_cuda=True)     # 1024x2048 ERP: 2 x 5.7 GB
     free = {"bytes": 170 << 30}
     monkeypatch.setattr(torch.cuda, "mem_get_info", lambda dev=None: (free["bytes"], 180 << 30))
+    monkeypatch.setattr(pcorr, "DRIVER_FREE_TTL_S", -1.0)          # every instance asks the driver (no reuse of the last answer)
     big = pcorr.DCCL(4, 4, mode="auto")
     assert big._use_onthefly(fmap) is False              # fits on a 180 GB B200
     free["bytes"] = 1 << 30
@@ -104,3 +105,15 @@ def test_dccl_auto_mode_decides_by_free_memory_once(monkeypatch):
     assert small._use_onthefly(fmap) is True             # 1 GiB free: volume-free lookup
     assert pcorr.DCCL(4, 4, mode="onthefly")._use_onthefly(fmap) is True
     assert pcorr.DCCL(4, 4, mode="materialized")._use_onthefly(fmap) is False
+    # the driver's answer is reused for DRIVER_FREE_TTL_S: a new DCCL per forward (the reference's pattern) does not query per forward
+    calls = {"n": 0}
+
+    def counting(dev=None):
+        calls["n"] += 1
+        return (170 << 30, 180 << 30)
+    monkeypatch.setattr(torch.cuda, "mem_get_info", counting)
+    monkeypatch.setattr(pcorr, "DRIVER_FREE_TTL_S", 60.0)
+    pcorr._driver_free.clear()
+    for _ in range(5):
+        assert pcorr.DCCL(4, 4, mode="auto")._use_onthefly(fmap) is False
+    assert calls["n"] == 1
