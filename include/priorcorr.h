@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 4
+#define PF_ABI_VERSION 5   /* 5: pf_lookup_onthefly_tc, pf_onthefly_absmax, pf_onthefly_split */
 #define PF_MAX_LEVELS 4
 
 /* `tensor / python_scalar`: IEEE division on CPU, multiply by fp32 reciprocal in ATen's CUDA

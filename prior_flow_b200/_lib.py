@@ -11,7 +11,7 @@ import threading
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libpriorcorr.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_LEVELS = 4
 
 DIV_IEEE, DIV_ATEN_CUDA = 0, 1
