@@ -502,17 +502,19 @@ __device__ __forceinline__ float ot_dot4(const float *const (&ptr)[4], const flo
 // s_out [tap][query] -> own view: [K2][8 queries] = 32-byte row segments of the [B, L*K2, N] output; other view: channels-last
 // [B, N, L*K2] pre-rotation map (contiguous per query), see pf_lookup.cu
 __device__ __forceinline__ void write_taps(const OtfTcParams &p, const float (*s_out)[kBlendQueries + 1], int branch, int lvl, int b, int n0) {
-  constexpr int K2 = kMaxTaps;
+  constexpr int K2 = kMaxTaps;      // (N is a multiple of 16: every query of the CTA exists)
   if (branch == 0 && !p.own_cl) {
     float *out = p.out_own + ((long long)b * p.L + lvl) * K2 * (long long)p.N + n0;
     for (int i = threadIdx.x; i < K2 * kBlendQueries; i += kBlendThreads) {
       const int ch = i / kBlendQueries, q = i - ch * kBlendQueries;
-      if (n0 + q < p.N) out[(long long)ch * p.N + q] = s_out[ch][q];
+      out[(unsigned)ch * (unsigned)p.N + q] = s_out[ch][q];
     }
   } else {
+    float *out = (branch ? p.out_raw : p.out_own) + (((long long)b * p.N + n0) * p.L + lvl) * K2;
+    const int qstride = p.L * K2;
     for (int i = threadIdx.x; i < K2 * kBlendQueries; i += kBlendThreads) {
       const int q = i / K2, ch = i - q * K2;
-      if (n0 + q < p.N) (branch ? p.out_raw : p.out_own)[(((long long)b * p.N + n0 + q) * p.L + lvl) * K2 + ch] = s_out[ch][q];
+      out[q * qstride + ch] = s_out[ch][q];
     }
   }
 }
@@ -520,7 +522,6 @@ __device__ __forceinline__ void write_taps(const OtfTcParams &p, const float (*s
 // Tiles on the tensor-core path: the tile's dots are in its local planes (otf_dots_kernel); every tap reads its four corners from
 // there.  All taps of the CTA's 16 queries are in flight together.  Tiles no tap touches: zeros.
 __global__ void __launch_bounds__(kBlendThreads) otf_blend_kernel(const OtfTcParams p) {
-  __shared__ float s_axis[kBlendQueries * 18];
   __shared__ float s_out[kMaxTaps][kBlendQueries + 1];
   const int lvl = blockIdx.y % p.L, branch = blockIdx.y / p.L, b = blockIdx.z;
   const int Hl = p.h >> lvl, Wl = p.w >> lvl;
@@ -539,40 +540,74 @@ __global__ void __launch_bounds__(kBlendThreads) otf_blend_kernel(const OtfTcPar
   const int spr = tb.spr();
   const int qrow0 = ((n0 / p.w) % OT_TH) * OT_TW;     // row of query n0 in its tile's segments
   const float *planes = p.pool + (long long)first * OT_SEG;
-  auto blend_tap = [&](int q, int t, float ix, float iy) {
-    const Taps tp = make_taps(ix, iy);
-    const bool xin0 = (unsigned)tp.x0 < (unsigned)Wl, xin1 = (unsigned)(tp.x0 + 1) < (unsigned)Wl;
-    const bool yin0 = (unsigned)tp.y0 < (unsigned)Hl, yin1 = (unsigned)(tp.y0 + 1) < (unsigned)Hl;
-    // column of the west corner in the box's numbering (mode 1: unwrapped); the east corner is the next column — a tap
-    // whose corners straddle the numbering's cut would have made the box as wide as the plane, and then mode 0 is chosen
-    const int ux = (tb.mode && xin0) ? unwrap1(tp.x0, Wl) : ((tb.mode && xin1) ? unwrap1(tp.x0 + 1, Wl) - 1 : tp.x0);
-    const int r = qrow0 + q, sw = r & 7;
-    const int cw = ux - tb.X0, ce = cw + 1, yy = tp.y0 - tb.Y0;
-    // element (box row y, column c) of query r: segment y * spr + c / 32, float r * 32 + (((c % 32) / 4) ^ (r & 7)) * 4 + c % 4
-    const float *qn = planes + (long long)yy * spr * OT_SEG + r * 32;
-    const long long off_w = (long long)(cw >> 5) * OT_SEG + ((((cw & 31) >> 2) ^ sw) << 2) + (cw & 3);
-    const long long off_e = (long long)(ce >> 5) * OT_SEG + ((((ce & 31) >> 2) ^ sw) << 2) + (ce & 3);
-    const long long down = (long long)spr * OT_SEG;
-    const float v_nw = (yin0 && xin0) ? __ldg(qn + off_w) : 0.f;
-    const float v_ne = (yin0 && xin1) ? __ldg(qn + off_e) : 0.f;
-    const float v_sw = (yin1 && xin0) ? __ldg(qn + down + off_w) : 0.f;
-    const float v_se = (yin1 && xin1) ? __ldg(qn + down + off_e) : 0.f;
-    float acc = __fmul_rn(v_nw, tp.nw);
-    acc = __fmaf_rn(v_ne, tp.ne, acc);
-    acc = __fmaf_rn(v_sw, tp.sw, acc);
-    acc = __fmaf_rn(v_se, tp.se, acc);
-    s_out[t][q] = acc;
+  // element (box row y, column c) of query r (row of the tile's segments): segment y * spr + c / 32, float
+  // r * 32 + (((c % 32) / 4) ^ (r & 7)) * 4 + c % 4 of it.  Offsets inside a tile's planes fit an int.
+  const int down = spr * OT_SEG;
+  auto col_off = [&](int c, int r) { return (c >> 5) * OT_SEG + ((((c & 31) >> 2) ^ (r & 7)) << 2) + (c & 3); };
+  // column of the west corner in the box's numbering (mode 1: unwrapped); the east corner is the next column — a tap
+  // whose corners straddle the numbering's cut would have made the box as wide as the plane, and then mode 0 is chosen
+  auto west_col = [&](int x0, bool xin0, bool xin1) {
+    return ((tb.mode && xin0) ? unwrap1(x0, Wl) : ((tb.mode && xin1) ? unwrap1(x0 + 1, Wl) - 1 : x0)) - tb.X0;
   };
-  if (branch) {      // the other view's coordinates were stashed by otf_box_kernel
+  if (branch) {
+    // other view: the coordinates were stashed by otf_box_kernel (each tap went through the rotation grid)
     const float2 *xy = p.tapxy + (((long long)lvl * p.B + b) * p.N + n0) * kMaxTaps;
     for (int i = threadIdx.x; i < kBlendQueries * kMaxTaps; i += kBlendThreads) {
-      const int q = i / kMaxTaps;
-      if (n0 + q >= p.N) break;
+      const int q = i / kMaxTaps, t = i - q * kMaxTaps;
       const float2 c = __ldg(xy + i);
-      blend_tap(q, i - q * kMaxTaps, c.x, c.y);
+      const Taps tp = make_taps(c.x, c.y);
+      const bool xin0 = (unsigned)tp.x0 < (unsigned)Wl, xin1 = (unsigned)(tp.x0 + 1) < (unsigned)Wl;
+      const bool yin0 = (unsigned)tp.y0 < (unsigned)Hl, yin1 = (unsigned)(tp.y0 + 1) < (unsigned)Hl;
+      const int r = qrow0 + q, cw = west_col(tp.x0, xin0, xin1);
+      const float *qn = planes + (tp.y0 - tb.Y0) * down + r * 32;
+      const int off_w = col_off(cw, r), off_e = col_off(cw + 1, r);
+      const float v_nw = (yin0 && xin0) ? __ldg(qn + off_w) : 0.f;
+      const float v_ne = (yin0 && xin1) ? __ldg(qn + off_e) : 0.f;
+      const float v_sw = (yin1 && xin0) ? __ldg(qn + down + off_w) : 0.f;
+      const float v_se = (yin1 && xin1) ? __ldg(qn + down + off_e) : 0.f;
+      float acc = __fmul_rn(v_nw, tp.nw);
+      acc = __fmaf_rn(v_ne, tp.ne, acc);
+      acc = __fmaf_rn(v_sw, tp.sw, acc);
+      acc = __fmaf_rn(v_se, tp.se, acc);
+      s_out[t][q] = acc;
     }
   } else {
-    cta_tap_coords(p, branch, lvl, b, n0, s_axis, blend_tap);
+    // own view: the 81 taps of a query are 9 columns x 9 rows, so the column half (corner offsets, dx weights) and the row half of
+    // make_taps / the corner addresses are evaluated 9 + 9 times per query and the taps only combine them (same roundings:
+    // nw = dxe * dys, ne = dxw * dys, sw = dxe * dyn, se = dxw * dyn as in make_taps)
+    __shared__ int4 s_half[kBlendQueries * 18];      // (offset of corner 0 or -1, offset of corner 1 or -1, weight toward 0, toward 1)
+    for (int i = threadIdx.x; i < kBlendQueries * 18; i += kBlendThreads) {
+      const int q = i / 18, j = i - q * 18, r = qrow0 + q;
+      const float v = tap_axis_coord(p, 0, lvl, b, n0 + q, j);
+      const float f0 = floorf(v), f1 = __fadd_rn(f0, 1.f);
+      const float w0 = __fsub_rn(f1, v), w1 = __fsub_rn(v, f0);      // dxe / dys, dxw / dyn
+      const int i0 = (int)f0;
+      int o0, o1;
+      if (j < 9) {
+        const bool in0 = (unsigned)i0 < (unsigned)Wl, in1 = (unsigned)(i0 + 1) < (unsigned)Wl;
+        const int cw = west_col(i0, in0, in1);
+        o0 = in0 ? col_off(cw, r) + r * 32 : -1, o1 = in1 ? col_off(cw + 1, r) + r * 32 : -1;
+      } else {
+        const bool in0 = (unsigned)i0 < (unsigned)Hl, in1 = (unsigned)(i0 + 1) < (unsigned)Hl;
+        o0 = in0 ? (i0 - tb.Y0) * down : -1, o1 = in1 ? (i0 + 1 - tb.Y0) * down : -1;
+      }
+      s_half[i] = make_int4(o0, o1, __float_as_int(w0), __float_as_int(w1));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kBlendQueries * kMaxTaps; i += kBlendThreads) {
+      const int q = i / kMaxTaps, t = i - q * kMaxTaps, aa = t / 9, bb = t - aa * 9;
+      const int4 X = s_half[q * 18 + aa], Y = s_half[q * 18 + 9 + bb];
+      const float dxe = __int_as_float(X.z), dxw = __int_as_float(X.w), dys = __int_as_float(Y.z), dyn = __int_as_float(Y.w);
+      const float v_nw = (Y.x >= 0 && X.x >= 0) ? __ldg(planes + Y.x + X.x) : 0.f;
+      const float v_ne = (Y.x >= 0 && X.y >= 0) ? __ldg(planes + Y.x + X.y) : 0.f;
+      const float v_sw = (Y.y >= 0 && X.x >= 0) ? __ldg(planes + Y.y + X.x) : 0.f;
+      const float v_se = (Y.y >= 0 && X.y >= 0) ? __ldg(planes + Y.y + X.y) : 0.f;
+      float acc = __fmul_rn(v_nw, __fmul_rn(dxe, dys));
+      acc = __fmaf_rn(v_ne, __fmul_rn(dxw, dys), acc);
+      acc = __fmaf_rn(v_sw, __fmul_rn(dxe, dyn), acc);
+      acc = __fmaf_rn(v_se, __fmul_rn(dxw, dyn), acc);
+      s_out[t][q] = acc;
+    }
   }
   __syncthreads();
   write_taps(p, s_out, branch, lvl, b, n0);
