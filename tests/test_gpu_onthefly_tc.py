@@ -133,3 +133,23 @@ def test_onthefly_lookup_with_fused_first_conv(B, h, w):
                 assert e < 1e-5
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 8, 16), (3, 24, 48), (1, 40, 112)])
+def test_wild_and_non_finite_coordinates_match_the_cuda_core_path(B, h, w):
+    """Flows of hundreds of pixels (boxes as large as the plane: pool overflow, CUDA-core tiles), NaN / inf / 1e30 coordinates (the
+    sampler maps them to -100: no tap touches the plane), the smallest grid (one query tile), grids that are not powers of two."""
+    from prior_flow_b200 import ops
+    fm, _, gw, gc = make_scene(B, h, w, 900 + h)
+    g = torch.Generator(device="cuda").manual_seed(h)
+    coords = TO.coords_grid(B, h, w, "cuda") + torch.randn(B, 2, h, w, device="cuda", generator=g) * 60.0
+    flat = coords.view(-1)
+    idx = torch.randperm(flat.numel(), device="cuda", generator=g)[:max(8, flat.numel() // 50)]
+    flat[idx[0::4]] = float("nan")
+    flat[idx[1::4]] = float("inf")
+    flat[idx[2::4]] = -float("inf")
+    flat[idx[3::4]] = 1e30
+    tc, cc = run_both(ops, coords, fm, gw, gc)
+    for got, old in zip(tc, cc):
+        assert torch.isfinite(got).all()
+        assert rel(got, old) < 1e-5
