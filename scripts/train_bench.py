@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--iters", type=int, default=12)
     ap.add_argument("--memory-format", default="nchw", choices=["nchw", "channels_last"])
+    ap.add_argument("--corr-mode", default="auto", choices=["auto", "materialized", "onthefly"],
+                    help="onthefly: volume-free forward (tensor-core lookup) and backward (ops.OnTheFlyTape)")
     ap.add_argument("--ddp", default="ddp", choices=["ddp", "static", "nobroadcast", "none"],
                     help="ddp: DistributedDataParallel defaults; static: static_graph=True; nobroadcast: broadcast_buffers=False (BN is frozen); "
                          "none: independent replicas, no gradient all-reduce (isolates host contention from DDP's cost)")
@@ -35,7 +37,7 @@ def main():
     ctx = pfd.init_from_env("nccl")
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(0)
-    model = PriOrRAFT().to(ctx.device)
+    model = PriOrRAFT(corr_mode=a.corr_mode).to(ctx.device)
     if a.memory_format == "channels_last":
         model = model.to_channels_last()
     model.train()
@@ -69,7 +71,8 @@ def main():
     if ctx.rank == 0:
         print(json.dumps({"what": "train step (config 5)", "n_gpus": ctx.world, "global_batch": B * ctx.world, "ms_per_step": round(ms, 2),
                           "pairs_per_s": round(B * ctx.world / ms * 1e3, 2), "losses": [round(x, 4) for x in losses],
-                          "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2), "shape": [H, W], "iters": a.iters, "ddp": a.ddp if ctx.world > 1 else "n/a", "memory_format": a.memory_format}), flush=True)
+                          "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2), "shape": [H, W], "iters": a.iters, "ddp": a.ddp if ctx.world > 1 else "n/a", "memory_format": a.memory_format,
+                          "corr_mode": a.corr_mode}), flush=True)
     if ctx.world > 1:
         torch.distributed.destroy_process_group()
 
