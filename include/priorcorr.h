@@ -284,6 +284,10 @@ int pf_warp_groupcorr_bwd(const float *fmap1, const float *fmap2, const float *c
  * channel = k*64 + di*8 + dj) -> out [B,2,8h,8w] = sum_k softmax_k(mask) * 8 * flow[3x3 neighbour k], zero padded. */
 int pf_convex_upsample(const float *flow, const float *mask, float *out, int batch, int h, int w, int mask_channels_last,
                        void *stream);
+/* Its adjoint: dflow [B,2,h,w] (zeroed here, accumulated with atomics: float sums in arbitrary order) and dmask in the mask's
+ * layout, from grad_out [B,2,8h,8w]; the softmax is recomputed from `mask`. */
+int pf_convex_upsample_bwd(const float *flow, const float *mask, const float *grad_out, float *dflow, float *dmask, int batch, int h, int w,
+                           int mask_channels_last, void *stream);
 /* One term of uniform_loss (train_flow.py:55-79): *acc += term_weight * sum(ok * lat[y] * |pred - gt|_1), with ok [B,H,W] the
  * 0/1 validity mask, lat [H] the normalised cos-latitude weights (core/utils/spherical.py:11-17); and its gradient
  * dpred = *upstream * term_weight * ok * lat[y] * sign(pred - gt). */

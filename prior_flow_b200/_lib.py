@@ -111,6 +111,7 @@ SIGNATURES = {
     "pf_volume_bwd_workspace_bytes": (C.c_longlong, [C.c_int] * 4),
     "pf_volume_bwd": (C.c_int, [C.POINTER(VolumeBwdArgs), _fp]),
     "pf_convex_upsample": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    "pf_convex_upsample_bwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     "pf_uniform_loss_fwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_float, C.c_int, C.c_int, C.c_int, _fp]),
     "pf_uniform_loss_bwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_float, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     "pf_great_circle": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, _fp]),

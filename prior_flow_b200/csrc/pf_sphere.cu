@@ -51,6 +51,61 @@ __global__ void __launch_bounds__(256) convex_upsample_kernel(const float *__res
   o[HW] = v;
 }
 
+// Adjoint of convex_upsample_kernel, same thread mapping (the softmax is recomputed, nothing is saved):
+//   dmask[k*64+d] = w_k (dw_k - sum_m w_m dw_m),  dw_k = 8 (g_u flow_u[nbr_k] + g_v flow_v[nbr_k])      (0 outside the image)
+//   dflow_c[nbr_k] += 8 sum_d w_k g_c          — reduced over the 64 sub-pixels of the coarse pixel first, then 18 atomics
+__global__ void __launch_bounds__(256) convex_upsample_bwd_kernel(const float *__restrict__ flow, const float *__restrict__ mask,
+                                                                  const float *__restrict__ gout, float *__restrict__ dflow,
+                                                                  float *__restrict__ dmask, int h, int w, long long m_bs,
+                                                                  long long m_cs, long long m_ps) {
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * 4 + (threadIdx.x >> 6);       // 4 coarse pixels per CTA, 2 warps each
+  if (pix >= h * w) return;                                  // (warp-uniform: 64 threads per pixel)
+  const int d = threadIdx.x & 63, di = d >> 3, dj = d & 7, lane = threadIdx.x & 31;
+  const int i = pix / w, j = pix - i * w;
+  const long long moff = (long long)b * m_bs + (long long)pix * m_ps + (long long)d * m_cs;
+  float wk[9], mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    wk[k] = __ldg(mask + moff + (long long)(k * 64) * m_cs);
+    mx = fmaxf(mx, wk[k]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    wk[k] = expf(wk[k] - mx);
+    s += wk[k];
+  }
+  const float inv = 1.0f / s;
+  const long long HW = 64LL * h * w;
+  const float *g = gout + (long long)b * 2 * HW + (long long)(8 * i + di) * (8 * w) + 8 * j + dj;
+  const float gu = 8.f * __ldg(g), gv = 8.f * __ldg(g + HW);
+  const float *f = flow + (long long)b * 2 * h * w;
+  float *df = dflow + (long long)b * 2 * h * w;
+  float dw[9], dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int y = i + k / 3 - 1, x = j + k % 3 - 1;
+    const bool in = (unsigned)y < (unsigned)h && (unsigned)x < (unsigned)w;
+    wk[k] *= inv;
+    dw[k] = in ? fmaf(gu, __ldg(f + y * w + x), gv * __ldg(f + h * w + y * w + x)) : 0.f;
+    dot = fmaf(wk[k], dw[k], dot);
+    // flow gradient: reduce w_k g over the warp's 32 sub-pixels, one atomic per warp, component and neighbour
+    float cu = in ? wk[k] * gu : 0.f, cv = in ? wk[k] * gv : 0.f;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      cu += __shfl_xor_sync(0xffffffffu, cu, o);
+      cv += __shfl_xor_sync(0xffffffffu, cv, o);
+    }
+    if (lane == 0 && in) {
+      atomicAdd(df + y * w + x, cu);
+      atomicAdd(df + h * w + y * w + x, cv);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) dmask[moff + (long long)(k * 64) * m_cs] = wk[k] * (dw[k] - dot);
+}
+
 // one loss term: acc += term_weight * sum(ok * lat[y] * (|pu - gu| + |pv - gv|))
 __global__ void __launch_bounds__(256) uniform_loss_fwd_kernel(const float *__restrict__ pred, const float *__restrict__ gt,
                                                                const float *__restrict__ ok, const float *__restrict__ lat, float *acc,
@@ -127,6 +182,17 @@ extern "C" int pf_convex_upsample(const float *flow, const float *mask, float *o
   const long long m_bs = 576 * N, m_cs = mask_channels_last ? 1 : N, m_ps = mask_channels_last ? 576 : 1;
   convex_upsample_kernel<<<dim3(ceil_div(N, 4), batch), 256, 0, (cudaStream_t)stream>>>(flow, mask, out, h, w, m_bs, m_cs, m_ps);
   return check_launch("pf_convex_upsample");
+}
+
+extern "C" int pf_convex_upsample_bwd(const float *flow, const float *mask, const float *grad_out, float *dflow, float *dmask, int batch,
+                                      int h, int w, int mask_channels_last, void *stream) {
+  using namespace pf;
+  PF_REQUIRE(flow && mask && grad_out && dflow && dmask && batch > 0 && h > 0 && w > 0, "pf_convex_upsample_bwd: bad arguments");
+  const long long N = (long long)h * w;
+  const long long m_bs = 576 * N, m_cs = mask_channels_last ? 1 : N, m_ps = mask_channels_last ? 576 : 1;
+  if (cudaMemsetAsync(dflow, 0, sizeof(float) * 2 * N * batch, (cudaStream_t)stream) != cudaSuccess) return check_launch("pf_convex_upsample_bwd(memset)");
+  convex_upsample_bwd_kernel<<<dim3(ceil_div(N, 4), batch), 256, 0, (cudaStream_t)stream>>>(flow, mask, grad_out, dflow, dmask, h, w, m_bs, m_cs, m_ps);
+  return check_launch("pf_convex_upsample_bwd");
 }
 
 extern "C" int pf_uniform_loss_fwd(const float *pred, const float *gt, const float *ok, const float *lat, float *acc, float term_weight,

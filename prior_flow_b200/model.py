@@ -232,9 +232,8 @@ class DualUpdateBlock(_UpdateBase):      # BasicMultiUpdateBlock ("ODDC"), core/
 def convex_upsample(flow: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """core/prior_raft.py:58-67 — [B,2,h,w] -> [B,2,8h,8w] as a convex combination of the 3x3 neighbourhood."""
     B, _, h, w = flow.shape
-    if flow.is_cuda and flow.dtype == torch.float32 and mask.dtype == torch.float32 and not (
-            torch.is_grad_enabled() and (flow.requires_grad or mask.requires_grad)):
-        return ops.convex_upsample(flow, mask)       # one launch (SURVEY §8 f2); the eager chain below carries the gradients
+    if flow.is_cuda and flow.dtype == torch.float32 and mask.dtype == torch.float32 and os.environ.get("PF_UPSAMPLE_KERNEL", "1") != "0":
+        return ops.convex_upsample(flow, mask)       # one launch forward, one backward (SURVEY §8 f2); eager chain below otherwise
     mask = torch.softmax(mask.view(B, 1, 9, 8, 8, h, w), dim=2)
     nb = F.unfold(8 * flow, [3, 3], padding=1).view(B, 2, 9, 1, 1, h, w)
     up = torch.sum(mask * nb, dim=2).permute(0, 1, 4, 2, 5, 3)

@@ -668,10 +668,7 @@ def lookup_onthefly_autograd(coords, pyr_own, pyr_other, grid_w2c, grid_c2w, rad
 
 
 # ------------------------------------------------------------------------------------------ (f2) / (f4)
-def convex_upsample(flow: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
-    """PriOr_RAFT.upsample_flow (core/prior_raft.py:58-67) in one launch: flow [B,2,h,w], mask [B,576,h,w] (NCHW or
-    torch.channels_last) -> [B,2,8h,8w].  Forward only."""
-    lib = _lib.load()
+def _convex_upsample_args(flow, mask):
     _chk(flow, "flow", 4), _chk(mask, "mask", 4)
     B, two, h, w = flow.shape
     if two != 2 or tuple(mask.shape) != (B, 576, h, w):
@@ -680,12 +677,48 @@ def convex_upsample(flow: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     cl = mask.is_contiguous(memory_format=torch.channels_last) and not mask.is_contiguous()
     if not cl:
         mask = mask.contiguous()
+    return flow, mask, cl, B, h, w
+
+
+def _convex_upsample_fwd(flow, mask):
+    lib = _lib.load()
+    flow, mask, cl, B, h, w = _convex_upsample_args(flow, mask)
     with torch.cuda.device(flow.device):
         out = torch.empty((B, 2, 8 * h, 8 * w), device=flow.device, dtype=torch.float32)
         _lib.check(lib.pf_convex_upsample(flow.data_ptr(), mask.data_ptr(), out.data_ptr(), B, h, w, int(cl), _stream()),
                    "pf_convex_upsample")
         _count(1)
     return out
+
+
+class _ConvexUpsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow, mask):
+        ctx.save_for_backward(flow, mask)
+        return _convex_upsample_fwd(flow, mask)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        flow, mask = ctx.saved_tensors
+        flow, mask, cl, B, h, w = _convex_upsample_args(flow, mask)
+        g = g.contiguous().float()
+        with torch.cuda.device(flow.device):
+            dflow = torch.empty_like(flow)
+            dmask = torch.empty_like(mask)          # same memory format as the mask
+            _lib.check(lib.pf_convex_upsample_bwd(flow.data_ptr(), mask.data_ptr(), g.data_ptr(), dflow.data_ptr(), dmask.data_ptr(),
+                                                  B, h, w, int(cl), _stream()), "pf_convex_upsample_bwd")
+            _count(1)
+        return dflow, dmask
+
+
+def convex_upsample(flow: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """PriOr_RAFT.upsample_flow (core/prior_raft.py:58-67) in one launch: flow [B,2,h,w], mask [B,576,h,w] (NCHW or
+    torch.channels_last) -> [B,2,8h,8w].  Under autograd the adjoint is one launch too (pf_convex_upsample_bwd: softmax
+    recomputed, nothing but the two inputs is kept for backward — the eager chain keeps five 576-channel tensors per call)."""
+    if torch.is_grad_enabled() and (flow.requires_grad or mask.requires_grad):
+        return _ConvexUpsampleFn.apply(flow, mask)
+    return _convex_upsample_fwd(flow, mask)
 
 
 class _UniformLossTermFn(torch.autograd.Function):

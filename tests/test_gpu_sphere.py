@@ -37,6 +37,32 @@ def test_convex_upsample(B, h, w):
         assert rel(ops.convex_upsample(flow, mask), model.upsample_flow(flow, mask)) < 1e-5
 
 
+@pytest.mark.parametrize("B,h,w", [(1, 64, 128), (2, 16, 32), (1, 5, 7)])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_convex_upsample_gradients(B, h, w, channels_last):
+    """pf_convex_upsample_bwd against autograd of the eager softmax / unfold / mul / sum chain (core/prior_raft.py:58-67)."""
+    from prior_flow_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(7 + h)
+    flow0 = torch.randn(B, 2, h, w, device="cuda", generator=g) * 4
+    mask0 = torch.randn(B, 576, h, w, device="cuda", generator=g) * 2
+    up = torch.randn(B, 2, 8 * h, 8 * w, device="cuda", generator=g)
+    res = []
+    for ours in (False, True):
+        flow = flow0.clone().requires_grad_(True)
+        mask = mask0.clone()
+        if channels_last:
+            mask = mask.contiguous(memory_format=torch.channels_last)
+        mask.requires_grad_(True)
+        out = ops.convex_upsample(flow, mask) if ours else eager_upsample(flow, mask)
+        (out * up).sum().backward()
+        res.append((out.detach(), flow.grad.clone(), mask.grad.clone()))
+    (o_a, df_a, dm_a), (o_b, df_b, dm_b) = res
+    assert rel(o_b, o_a) < 1e-5
+    assert rel(df_b, df_a) < 1e-5 and rel(dm_b, dm_a) < 1e-5
+    if channels_last:
+        assert dm_b.is_contiguous(memory_format=torch.channels_last)
+
+
 def test_uniform_loss_terms_and_gradients():
     from prior_flow_b200 import train as T
     g = torch.Generator(device="cuda").manual_seed(3)
