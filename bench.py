@@ -317,6 +317,12 @@ def main_ours(a):
     _, e2e_ms = timed(step_e2e, a.steps)
     value = world * B * a.steps / (dev_ms / 1e3)
     e2e_value = world * B * a.steps / (e2e_ms / 1e3)
+    # the same forward through the eager product API (`model(image1, image2, ...)`, no CUDA graph): launch-bound, reported beside it
+    eager_steps = max(3, min(a.steps, 10))
+    for _ in range(2):
+        forward(d1, d2)
+    eager_ms, _ = timed(lambda: forward(d1, d2), eager_steps)
+    eager_value = world * B * eager_steps / (eager_ms / 1e3)
 
     # The timed, collective part is over: tear the process group down NOW, so that nothing below (rank 0's roofline section)
     # runs while other ranks spin in an NCCL barrier.  Ranks != 0 are done.
@@ -496,6 +502,8 @@ def main_ours(a):
                                             "convolutions; 3.4e-3 px with TF32 convolutions, where the reference's own TF32 run is 6.1e-3 px from its fp32 run", "hot_path": "fp32 (tcgen05 fp16x2 split, fp32 accumulate)"},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 2 * host1.numel() * 4,
                     "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": round(e2e_ms / a.steps, 4)},
+            "product_api_eager": {"value": round(eager_value, 3), "unit": "pairs/s", "ms_per_step": round(eager_ms / eager_steps, 4), "steps": eager_steps,
+                                  "what": "PriOrRAFT.forward without a CUDA graph (inputs resident), device-timed like `value`"},
             "gpu_launches": launches_per_forward * a.steps,
             "gpu_launches_per_step": launches_per_forward,
             "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline,
