@@ -155,23 +155,6 @@ __device__ __forceinline__ void box_add_tap(int *s_box, int x0, int y0, int Wl, 
     atomicMax(&s_box[5], min(y0 + 1, Hl - 1));
   }
 }
-// The same for a whole (converged or not) warp into ONE box: reduce across the active lanes first, one lane does the atomics.
-__device__ __forceinline__ void box_add_tap_warp(int *s_box, int x0, int y0, int Wl, int Hl) {
-  const unsigned active = __activemask();
-  int v[6] = {INT_MAX, INT_MIN, INT_MAX, INT_MIN, INT_MAX, INT_MIN};
-  if (x0 + 1 >= 0 && x0 < Wl && y0 + 1 >= 0 && y0 < Hl) {
-    const int xa = max(x0, 0), xb = min(x0 + 1, Wl - 1);
-    const int ua = unwrap1(xa, Wl), ub = unwrap1(xb, Wl);
-    v[0] = xa, v[1] = xb, v[2] = min(ua, ub), v[3] = max(ua, ub), v[4] = max(y0, 0), v[5] = min(y0 + 1, Hl - 1);
-  }
-#pragma unroll
-  for (int i = 0; i < 6; i += 2) v[i] = __reduce_min_sync(active, v[i]), v[i + 1] = __reduce_max_sync(active, v[i + 1]);
-  if ((threadIdx.x & 31) == (__ffs(active) - 1) && v[4] <= v[5]) {
-#pragma unroll
-    for (int i = 0; i < 6; i += 2) atomicMin(&s_box[i], v[i]), atomicMax(&s_box[i + 1], v[i + 1]);
-  }
-}
-
 __global__ void __launch_bounds__(kBlendThreads) otf_box_kernel(const OtfTcParams p) {
   __shared__ int s_box[6];
   __shared__ float s_axis[kBlendQueries * 18];
@@ -201,10 +184,23 @@ __global__ void __launch_bounds__(kBlendThreads) otf_box_kernel(const OtfTcParam
     if (s_box[0] > s_box[1]) return;      // no column touched: leave the tile's box as it is (uniform)
   } else {
     float2 *xy = p.tapxy + (((long long)lvl * p.B + b) * p.N + n0) * kMaxTaps;
+    // a thread folds the corners of its own taps into registers; one warp reduction and six shared atomics per warp at the end
+    int v[6] = {INT_MAX, INT_MIN, INT_MAX, INT_MIN, INT_MAX, INT_MIN};
     cta_tap_coords(p, branch, lvl, b, n0, s_axis, [&](int q, int t, float ix, float iy) {
       xy[q * kMaxTaps + t] = make_float2(ix, iy);
-      box_add_tap_warp(s_box, (int)floorf(ix), (int)floorf(iy), Wl, Hl);
+      const int x0 = (int)floorf(ix), y0 = (int)floorf(iy);
+      if (x0 + 1 >= 0 && x0 < Wl && y0 + 1 >= 0 && y0 < Hl) {
+        const int xa = max(x0, 0), xb = min(x0 + 1, Wl - 1), ua = unwrap1(xa, Wl), ub = unwrap1(xb, Wl);
+        v[0] = min(v[0], xa), v[1] = max(v[1], xb), v[2] = min(v[2], min(ua, ub)), v[3] = max(v[3], max(ua, ub));
+        v[4] = min(v[4], max(y0, 0)), v[5] = max(v[5], min(y0 + 1, Hl - 1));
+      }
     });
+#pragma unroll
+    for (int i = 0; i < 6; i += 2) v[i] = __reduce_min_sync(0xffffffffu, v[i]), v[i + 1] = __reduce_max_sync(0xffffffffu, v[i + 1]);
+    if ((threadIdx.x & 31) == 0 && v[4] <= v[5]) {
+#pragma unroll
+      for (int i = 0; i < 6; i += 2) atomicMin(&s_box[i], v[i]), atomicMax(&s_box[i + 1], v[i + 1]);
+    }
     __syncthreads();
   }
   if (threadIdx.x < 3 && s_box[4] <= s_box[5]) {
