@@ -34,6 +34,8 @@ int pf_abi_version(void) { return PF_ABI_VERSION; }
 
 const char *pf_last_error(void) { return pf::g_error; }
 
-const char *pf_build_info(void) { return "sm_100a;tcgen05;tma;abi=4"; }
+#define PF_STR2(x) #x
+#define PF_STR(x) PF_STR2(x)
+const char *pf_build_info(void) { return "sm_100a;tcgen05;tma;abi=" PF_STR(PF_ABI_VERSION); }
 
 }  // extern "C"
