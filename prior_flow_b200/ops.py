@@ -426,7 +426,8 @@ _OTF_SCRATCH = {}
 
 def _otf_scratch(dev, views: int, L: int, B: int, h: int, w: int):
     """The local-plane pool and the work buffer of pf_lookup_onthefly_tc: per device and shape, reused by every call (calls are
-    stream-ordered; allocate outside CUDA-graph capture — PriOrRAFT.graphed() warms up eagerly first)."""
+    stream-ordered; allocate outside CUDA-graph capture — PriOrRAFT.graphed() warms up eagerly first).  Entries are never
+    evicted: a captured CUDA graph holds the raw pointers.  `ops._OTF_SCRATCH.clear()` releases them when no graph uses them."""
     key = (dev.index, views, L, B, h, w, OnTheFlyPlanes.POOL_SEGMENTS_PER_QUERY)
     got = _OTF_SCRATCH.get(key)
     if got is None:
