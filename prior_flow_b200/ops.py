@@ -437,8 +437,6 @@ def _otf_scratch(dev, views: int, L: int, B: int, h: int, w: int):
         pool = torch.empty((segs, 128, 32), device=dev, dtype=torch.float32)
         work = torch.empty(16 + 10 * T + 2 + 2 * (segs // 8 + T), device=dev, dtype=torch.int32)      # PF_OTF_WORK_INTS
         tap_xy = torch.empty((L, B, h * w, 81, 2), device=dev, dtype=torch.float32) if views == 2 else None
-        while len(_OTF_SCRATCH) >= 4:                      # a few shapes at most: the pools are gigabytes at high resolution
-            _OTF_SCRATCH.pop(next(iter(_OTF_SCRATCH)))
         got = _OTF_SCRATCH[key] = (pool, work, T, tap_xy)
     return got
 
