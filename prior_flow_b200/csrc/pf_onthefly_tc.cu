@@ -623,90 +623,89 @@ __global__ void __launch_bounds__(kBlendThreads) otf_fallback_kernel(const OtfTc
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int items = p.ctr[0] * OT_TH;
   for (;;) {
-  __syncthreads();
-  if (threadIdx.x == 0) s_item = atomicAdd(p.ctr + 1, 1);
-  __syncthreads();
-  const int item = s_item;
-  if (item >= items) return;
-  const Entry en = decode_entry(p, p.fb_list[item / OT_TH]);
-  const int tile = en.tile, b = en.b, lvl = en.lvl, branch = en.branch;
-  const int Hl = p.h >> lvl, Wl = p.w >> lvl;
-  const int n0 = ((tile / p.tiles_x) * OT_TH + item % OT_TH) * p.w + (tile % p.tiles_x) * OT_TW;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // CUDA-core path (the r01 kernel's): per query, the plane on its own box if that is fewer dot products than four per tap
-  if (threadIdx.x < kBlendQueries) box_reset(s_box[threadIdx.x]);
-  __syncthreads();       // (cta_tap_coords syncs once more before any tap is consumed)
-  cta_tap_coords(p, branch, lvl, b, n0, s_axis, [&](int q, int t, float ix, float iy) {
-    s_ix[q * K2 + t] = ix, s_iy[q * K2 + t] = iy;
-    box_add_tap(s_box[q], (int)floorf(ix), (int)floorf(iy), Wl, Hl);
-  });
-  __syncthreads();
-  const float *f2 = p.f2[branch][lvl] + (long long)b * Hl * Wl * p.C;
-  const int nvec = p.C / 128;
-  for (int q = 0; q < kBlendQueries; ++q) {
-    const int n = n0 + q;
-    if (n >= p.N) break;
-    const float *q_ix = s_ix + q * K2, *q_iy = s_iy + q * K2;
-    const int x_lo = s_box[q][0], x_hi = s_box[q][1], y_lo = s_box[q][4], y_hi = s_box[q][5];      // plain columns
-    const bool empty = y_lo > y_hi;
-    const int bw = empty ? 0 : x_hi - x_lo + 1, bh = empty ? 0 : y_hi - y_lo + 1;
-    const int area = bw * bh;
-    float4 qv[kMaxVec];
-    const float4 *f1v = reinterpret_cast<const float4 *>(p.f1[branch] + ((long long)b * p.N + n) * p.C);
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(p.ctr + 1, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= items) return;
+    const Entry en = decode_entry(p, p.fb_list[item / OT_TH]);
+    const int tile = en.tile, b = en.b, lvl = en.lvl, branch = en.branch;
+    const int Hl = p.h >> lvl, Wl = p.w >> lvl;
+    const int n0 = ((tile / p.tiles_x) * OT_TH + item % OT_TH) * p.w + (tile % p.tiles_x) * OT_TW;
+    // CUDA-core path (the r01 kernel's): per query, the plane on its own box if that is fewer dot products than four per tap
+    if (threadIdx.x < kBlendQueries) box_reset(s_box[threadIdx.x]);
+    __syncthreads();       // (cta_tap_coords syncs once more before any tap is consumed)
+    cta_tap_coords(p, branch, lvl, b, n0, s_axis, [&](int q, int t, float ix, float iy) {
+      s_ix[q * K2 + t] = ix, s_iy[q * K2 + t] = iy;
+      box_add_tap(s_box[q], (int)floorf(ix), (int)floorf(iy), Wl, Hl);
+    });
+    __syncthreads();
+    const float *f2 = p.f2[branch][lvl] + (long long)b * Hl * Wl * p.C;
+    const int nvec = p.C / 128;
+    for (int q = 0; q < kBlendQueries; ++q) {
+      const int n = n0 + q;
+      if (n >= p.N) break;
+      const float *q_ix = s_ix + q * K2, *q_iy = s_iy + q * K2;
+      const int x_lo = s_box[q][0], x_hi = s_box[q][1], y_lo = s_box[q][4], y_hi = s_box[q][5];      // plain columns
+      const bool empty = y_lo > y_hi;
+      const int bw = empty ? 0 : x_hi - x_lo + 1, bh = empty ? 0 : y_hi - y_lo + 1;
+      const int area = bw * bh;
+      float4 qv[kMaxVec];
+      const float4 *f1v = reinterpret_cast<const float4 *>(p.f1[branch] + ((long long)b * p.N + n) * p.C);
 #pragma unroll
-    for (int j = 0; j < kMaxVec; ++j) qv[j] = (j < nvec) ? __ldg(f1v + j * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (area <= kBoxDots) {
-      for (int pix = warp * 4; pix < area; pix += kBlendThreads / 8) {       // four pixels per warp step
-        const float *ptr[4];
+      for (int j = 0; j < kMaxVec; ++j) qv[j] = (j < nvec) ? __ldg(f1v + j * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (area <= kBoxDots) {
+        for (int pix = warp * 4; pix < area; pix += kBlendThreads / 8) {       // four pixels per warp step
+          const float *ptr[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int pc = pix + c, yy = pc / bw, xx = pc - yy * bw;
-          ptr[c] = pc < area ? f2 + ((long long)(y_lo + yy) * Wl + (x_lo + xx)) * p.C : nullptr;
+          for (int c = 0; c < 4; ++c) {
+            const int pc = pix + c, yy = pc / bw, xx = pc - yy * bw;
+            ptr[c] = pc < area ? f2 + ((long long)(y_lo + yy) * Wl + (x_lo + xx)) * p.C : nullptr;
+          }
+          const float d = ot_dot4(ptr, qv, nvec, lane);
+          if ((lane & 7) == 0 && pix + (lane >> 3) < area) s_dots[pix + (lane >> 3)] = d * p.scale;
         }
-        const float d = ot_dot4(ptr, qv, nvec, lane);
-        if ((lane & 7) == 0 && pix + (lane >> 3) < area) s_dots[pix + (lane >> 3)] = d * p.scale;
-      }
-      __syncthreads();
-      for (int t = threadIdx.x; t < K2; t += kBlendThreads) {
-        const Taps tp = make_taps(q_ix[t], q_iy[t]);
-        const bool xin0 = (unsigned)tp.x0 < (unsigned)Wl, xin1 = (unsigned)(tp.x0 + 1) < (unsigned)Wl;
-        const bool yin0 = (unsigned)tp.y0 < (unsigned)Hl, yin1 = (unsigned)(tp.y0 + 1) < (unsigned)Hl;
-        const int base = (tp.y0 - y_lo) * bw + (tp.x0 - x_lo);
-        const float v_nw = (yin0 && xin0) ? s_dots[base] : 0.f;
-        const float v_ne = (yin0 && xin1) ? s_dots[base + 1] : 0.f;
-        const float v_sw = (yin1 && xin0) ? s_dots[base + bw] : 0.f;
-        const float v_se = (yin1 && xin1) ? s_dots[base + bw + 1] : 0.f;
-        float acc = __fmul_rn(v_nw, tp.nw);
-        acc = __fmaf_rn(v_ne, tp.ne, acc);
-        acc = __fmaf_rn(v_sw, tp.sw, acc);
-        acc = __fmaf_rn(v_se, tp.se, acc);
-        s_out[t][q] = acc;
-      }
-    } else {
-      // large boxes (poles of the rotation map): a warp per tap, its four corners in one step
-      for (int t = warp; t < K2; t += kBlendThreads / 32) {
-        const Taps tp = make_taps(q_ix[t], q_iy[t]);
-        const float *ptr[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int xx = tp.x0 + (c & 1), yy = tp.y0 + (c >> 1);
-          const bool in = (unsigned)xx < (unsigned)Wl && (unsigned)yy < (unsigned)Hl;
-          ptr[c] = in ? f2 + ((long long)yy * Wl + xx) * p.C : nullptr;
-        }
-        const float d = ot_dot4(ptr, qv, nvec, lane) * p.scale;
-        const float v1 = __shfl_sync(0xffffffffu, d, 8), v2 = __shfl_sync(0xffffffffu, d, 16), v3 = __shfl_sync(0xffffffffu, d, 24);
-        if (lane == 0) {
-          float acc = __fmul_rn(d, tp.nw);
-          acc = __fmaf_rn(v1, tp.ne, acc);
-          acc = __fmaf_rn(v2, tp.sw, acc);
-          acc = __fmaf_rn(v3, tp.se, acc);
+        __syncthreads();
+        for (int t = threadIdx.x; t < K2; t += kBlendThreads) {
+          const Taps tp = make_taps(q_ix[t], q_iy[t]);
+          const bool xin0 = (unsigned)tp.x0 < (unsigned)Wl, xin1 = (unsigned)(tp.x0 + 1) < (unsigned)Wl;
+          const bool yin0 = (unsigned)tp.y0 < (unsigned)Hl, yin1 = (unsigned)(tp.y0 + 1) < (unsigned)Hl;
+          const int base = (tp.y0 - y_lo) * bw + (tp.x0 - x_lo);
+          const float v_nw = (yin0 && xin0) ? s_dots[base] : 0.f;
+          const float v_ne = (yin0 && xin1) ? s_dots[base + 1] : 0.f;
+          const float v_sw = (yin1 && xin0) ? s_dots[base + bw] : 0.f;
+          const float v_se = (yin1 && xin1) ? s_dots[base + bw + 1] : 0.f;
+          float acc = __fmul_rn(v_nw, tp.nw);
+          acc = __fmaf_rn(v_ne, tp.ne, acc);
+          acc = __fmaf_rn(v_sw, tp.sw, acc);
+          acc = __fmaf_rn(v_se, tp.se, acc);
           s_out[t][q] = acc;
         }
+      } else {
+        // large boxes (poles of the rotation map): a warp per tap, its four corners in one step
+        for (int t = warp; t < K2; t += kBlendThreads / 32) {
+          const Taps tp = make_taps(q_ix[t], q_iy[t]);
+          const float *ptr[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int xx = tp.x0 + (c & 1), yy = tp.y0 + (c >> 1);
+            const bool in = (unsigned)xx < (unsigned)Wl && (unsigned)yy < (unsigned)Hl;
+            ptr[c] = in ? f2 + ((long long)yy * Wl + xx) * p.C : nullptr;
+          }
+          const float d = ot_dot4(ptr, qv, nvec, lane) * p.scale;
+          const float v1 = __shfl_sync(0xffffffffu, d, 8), v2 = __shfl_sync(0xffffffffu, d, 16), v3 = __shfl_sync(0xffffffffu, d, 24);
+          if (lane == 0) {
+            float acc = __fmul_rn(d, tp.nw);
+            acc = __fmaf_rn(v1, tp.ne, acc);
+            acc = __fmaf_rn(v2, tp.sw, acc);
+            acc = __fmaf_rn(v3, tp.se, acc);
+            s_out[t][q] = acc;
+          }
+        }
       }
+      __syncthreads();
     }
-    __syncthreads();
-  }
-  write_taps(p, s_out, branch, lvl, b, n0);
+    write_taps(p, s_out, branch, lvl, b, n0);
   }
 }
 
