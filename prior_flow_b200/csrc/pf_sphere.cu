@@ -11,14 +11,30 @@
 
 namespace pf {
 
-// thread = (coarse pixel, d = di*8 + dj): with a channels-last mask the 64 logits of one k are contiguous -> coalesced
+// Thread = (coarse pixel, sub-pixel d = di*8 + dj), 4 coarse pixels per CTA.  Two mappings, by the mask's memory format:
+//   channels-last mask: 64 consecutive threads = the 64 sub-pixels of one pixel (their logits of one k are contiguous)
+//   NCHW mask:          warp = di, lane = 8 * pixel + dj: a warp reads 4 consecutive pixels of 8 channel planes (16-byte pieces)
+//                       and writes 32 consecutive floats of one output row
+template <bool kCL>
+__device__ __forceinline__ void upsample_thread(int &pl, int &d) {
+  if (kCL) {
+    pl = threadIdx.x >> 6, d = threadIdx.x & 63;
+  } else {
+    const int lane = threadIdx.x & 31;
+    pl = lane >> 3, d = (threadIdx.x >> 5) * 8 + (lane & 7);
+  }
+}
+
+template <bool kCL>
 __global__ void __launch_bounds__(256) convex_upsample_kernel(const float *__restrict__ flow, const float *__restrict__ mask,
                                                               float *__restrict__ out, int h, int w, long long m_bs,
                                                               long long m_cs, long long m_ps) {
   const int b = blockIdx.y;
-  const int pix = blockIdx.x * 4 + (threadIdx.x >> 6);       // 4 coarse pixels per CTA
+  int pl, d;
+  upsample_thread<kCL>(pl, d);
+  const int pix = blockIdx.x * 4 + pl;                       // 4 coarse pixels per CTA
   if (pix >= h * w) return;
-  const int d = threadIdx.x & 63, di = d >> 3, dj = d & 7;
+  const int di = d >> 3, dj = d & 7;
   const int i = pix / w, j = pix - i * w;
   const float *mp = mask + (long long)b * m_bs + (long long)pix * m_ps + (long long)d * m_cs;
   float lg[9], mx = -INFINITY;
@@ -51,18 +67,28 @@ __global__ void __launch_bounds__(256) convex_upsample_kernel(const float *__res
   o[HW] = v;
 }
 
-// Adjoint of convex_upsample_kernel, same thread mapping (the softmax is recomputed, nothing is saved):
+// Adjoint of convex_upsample_kernel, same thread mappings (the softmax is recomputed, nothing is saved):
 //   dmask[k*64+d] = w_k (dw_k - sum_m w_m dw_m),  dw_k = 8 (g_u flow_u[nbr_k] + g_v flow_v[nbr_k])      (0 outside the image)
-//   dflow_c[nbr_k] += 8 sum_d w_k g_c          — reduced over the 64 sub-pixels of the coarse pixel first, then 18 atomics
+//   dflow_c[nbr_k] += 8 sum_d w_k g_c          — reduced over the 64 sub-pixels of the coarse pixel first (warp shuffles, then
+//   shared-memory atomics across the warps that share a pixel), then 18 global atomics per coarse pixel
+template <bool kCL>
 __global__ void __launch_bounds__(256) convex_upsample_bwd_kernel(const float *__restrict__ flow, const float *__restrict__ mask,
                                                                   const float *__restrict__ gout, float *__restrict__ dflow,
                                                                   float *__restrict__ dmask, int h, int w, long long m_bs,
                                                                   long long m_cs, long long m_ps) {
+  __shared__ float s_df[4][18];
   const int b = blockIdx.y;
-  const int pix = blockIdx.x * 4 + (threadIdx.x >> 6);       // 4 coarse pixels per CTA, 2 warps each
-  if (pix >= h * w) return;                                  // (warp-uniform: 64 threads per pixel)
-  const int d = threadIdx.x & 63, di = d >> 3, dj = d & 7, lane = threadIdx.x & 31;
+  int pl, d;
+  upsample_thread<kCL>(pl, d);
+  if (threadIdx.x < 72) (&s_df[0][0])[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int pix_raw = blockIdx.x * 4 + pl;
+  const bool live = pix_raw < h * w;
+  const int pix = live ? pix_raw : h * w - 1;      // lanes past the end compute on the last pixel and contribute nothing (the warp
+                                                   // shuffles below need every lane)
+  const int di = d >> 3, dj = d & 7, lane = threadIdx.x & 31;
   const int i = pix / w, j = pix - i * w;
+  float *df = dflow + (long long)b * 2 * h * w;
   const long long moff = (long long)b * m_bs + (long long)pix * m_ps + (long long)d * m_cs;
   float wk[9], mx = -INFINITY;
 #pragma unroll
@@ -81,29 +107,39 @@ __global__ void __launch_bounds__(256) convex_upsample_bwd_kernel(const float *_
   const float *g = gout + (long long)b * 2 * HW + (long long)(8 * i + di) * (8 * w) + 8 * j + dj;
   const float gu = 8.f * __ldg(g), gv = 8.f * __ldg(g + HW);
   const float *f = flow + (long long)b * 2 * h * w;
-  float *df = dflow + (long long)b * 2 * h * w;
   float dw[9], dot = 0.f;
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
     const int y = i + k / 3 - 1, x = j + k % 3 - 1;
-    const bool in = (unsigned)y < (unsigned)h && (unsigned)x < (unsigned)w;
+    const bool in = live && (unsigned)y < (unsigned)h && (unsigned)x < (unsigned)w;
     wk[k] *= inv;
     dw[k] = in ? fmaf(gu, __ldg(f + y * w + x), gv * __ldg(f + h * w + y * w + x)) : 0.f;
     dot = fmaf(wk[k], dw[k], dot);
-    // flow gradient: reduce w_k g over the warp's 32 sub-pixels, one atomic per warp, component and neighbour
+    // flow gradient: reduce w_k g over the lanes of this warp that belong to the pixel (all 32, or the 8 of a dj group)
     float cu = in ? wk[k] * gu : 0.f, cv = in ? wk[k] * gv : 0.f;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
+    for (int o = kCL ? 16 : 4; o; o >>= 1) {
       cu += __shfl_xor_sync(0xffffffffu, cu, o);
       cv += __shfl_xor_sync(0xffffffffu, cv, o);
     }
-    if (lane == 0 && in) {
-      atomicAdd(df + y * w + x, cu);
-      atomicAdd(df + h * w + y * w + x, cv);
+    if ((kCL ? lane == 0 : (lane & 7) == 0) && in) {
+      atomicAdd(&s_df[pl][2 * k], cu);
+      atomicAdd(&s_df[pl][2 * k + 1], cv);
     }
   }
+  if (live) {
 #pragma unroll
-  for (int k = 0; k < 9; ++k) dmask[moff + (long long)(k * 64) * m_cs] = wk[k] * (dw[k] - dot);
+    for (int k = 0; k < 9; ++k) dmask[moff + (long long)(k * 64) * m_cs] = wk[k] * (dw[k] - dot);
+  }
+  __syncthreads();
+  if (threadIdx.x < 72) {
+    const int q = threadIdx.x / 18, r = threadIdx.x - q * 18, k = r >> 1, c = r & 1;
+    const int px = blockIdx.x * 4 + q;
+    if (px < h * w) {
+      const int y = px / w + k / 3 - 1, x = px % w + k % 3 - 1;
+      if ((unsigned)y < (unsigned)h && (unsigned)x < (unsigned)w) atomicAdd(df + c * h * w + y * w + x, s_df[q][r]);
+    }
+  }
 }
 
 // one loss term: acc += term_weight * sum(ok * lat[y] * (|pu - gu| + |pv - gv|))
@@ -180,7 +216,10 @@ extern "C" int pf_convex_upsample(const float *flow, const float *mask, float *o
   PF_REQUIRE(flow && mask && out && batch > 0 && h > 0 && w > 0, "pf_convex_upsample: bad arguments");
   const long long N = (long long)h * w;
   const long long m_bs = 576 * N, m_cs = mask_channels_last ? 1 : N, m_ps = mask_channels_last ? 576 : 1;
-  convex_upsample_kernel<<<dim3(ceil_div(N, 4), batch), 256, 0, (cudaStream_t)stream>>>(flow, mask, out, h, w, m_bs, m_cs, m_ps);
+  if (mask_channels_last)
+    convex_upsample_kernel<true><<<dim3(ceil_div(N, 4), batch), 256, 0, (cudaStream_t)stream>>>(flow, mask, out, h, w, m_bs, m_cs, m_ps);
+  else
+    convex_upsample_kernel<false><<<dim3(ceil_div(N, 4), batch), 256, 0, (cudaStream_t)stream>>>(flow, mask, out, h, w, m_bs, m_cs, m_ps);
   return check_launch("pf_convex_upsample");
 }
 
@@ -191,7 +230,10 @@ extern "C" int pf_convex_upsample_bwd(const float *flow, const float *mask, cons
   const long long N = (long long)h * w;
   const long long m_bs = 576 * N, m_cs = mask_channels_last ? 1 : N, m_ps = mask_channels_last ? 576 : 1;
   if (cudaMemsetAsync(dflow, 0, sizeof(float) * 2 * N * batch, (cudaStream_t)stream) != cudaSuccess) return check_launch("pf_convex_upsample_bwd(memset)");
-  convex_upsample_bwd_kernel<<<dim3(ceil_div(N, 4), batch), 256, 0, (cudaStream_t)stream>>>(flow, mask, grad_out, dflow, dmask, h, w, m_bs, m_cs, m_ps);
+  if (mask_channels_last)
+    convex_upsample_bwd_kernel<true><<<dim3(ceil_div(N, 4), batch), 256, 0, (cudaStream_t)stream>>>(flow, mask, grad_out, dflow, dmask, h, w, m_bs, m_cs, m_ps);
+  else
+    convex_upsample_bwd_kernel<false><<<dim3(ceil_div(N, 4), batch), 256, 0, (cudaStream_t)stream>>>(flow, mask, grad_out, dflow, dmask, h, w, m_bs, m_cs, m_ps);
   return check_launch("pf_convex_upsample_bwd");
 }
 
