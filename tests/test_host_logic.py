@@ -117,3 +117,23 @@ def test_dccl_auto_mode_decides_by_free_memory_once(monkeypatch):
     for _ in range(5):
         assert pcorr.DCCL(4, 4, mode="auto")._use_onthefly(fmap) is False
     assert calls["n"] == 1
+
+
+def test_onthefly_tensor_core_path_shape_rules_and_scratch_sizes():
+    """Host logic of the tensor-core on-the-fly lookup: which feature grids take it, and the scratch sizes the C ABI documents
+    (PF_OTF_WORK_INTS in include/priorcorr.h) as the Python layer computes them."""
+    import re
+    from prior_flow_b200 import ops
+    ok = lambda *shape, radius=4: ops.OnTheFlyPlanes.supported(torch.empty(*shape), radius)
+    assert ok(1, 64, 128, 256) and ok(2, 8, 16, 128) and ok(1, 128, 256, 512)
+    assert not ok(1, 60, 128, 256)          # h % 8
+    assert not ok(1, 64, 120, 256)          # w % 16
+    assert not ok(1, 64, 128, 192)          # channels % 128
+    assert not ok(1, 64, 128, 640)          # channels > 512
+    assert not ok(1, 64, 128, 256, radius=3)
+    header = open(os.path.join(ROOT, "include", "priorcorr.h")).read()
+    m = re.search(r"#define PF_OTF_WORK_INTS\(T, segs\) \((.*)\)\n", header)
+    assert m, "PF_OTF_WORK_INTS not found"
+    expr = m.group(1).replace("(long long)", "").replace("/", "//")
+    for T, segs in ((512, 32768), (4096, 131072), (8, 8)):
+        assert eval(expr, {"T": T, "segs": segs}) == 16 + 10 * T + 2 + 2 * (segs // 8 + T)      # ops._otf_scratch
