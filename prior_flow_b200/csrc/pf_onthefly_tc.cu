@@ -235,24 +235,41 @@ __device__ __forceinline__ bool read_box(const OtfTcParams &p, int e, TileBox &t
 }
 
 // ------------------------------------------------------------------------------------------------ pool allocation, work items
-__device__ __forceinline__ int block_exclusive_scan(int v, int *s_scan, int &total) {   // 1024 threads
-  const int t = threadIdx.x;
-  s_scan[t] = v;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    const int add = t >= o ? s_scan[t - o] : 0;
-    __syncthreads();
-    s_scan[t] += add;
-    __syncthreads();
+__device__ __forceinline__ int block_exclusive_scan(int v, int *s_warp /*[32]*/, int &total) {   // 1024 threads
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
   }
-  total = s_scan[1023];
-  const int excl = s_scan[t] - v;
+  if (lane == 31) s_warp[warp] = x;
   __syncthreads();
-  return excl;
+  if (warp == 0) {
+    int w = s_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  const int base = warp ? s_warp[warp - 1] : 0;
+  total = s_warp[31];
+  __syncthreads();       // s_warp is reused by the next scan
+  return base + x - v;
+}
+
+// counters to zero, boxes to (+large, -large): one launch in front of the box kernel
+__global__ void __launch_bounds__(256) otf_init_kernel(const OtfTcParams p) {
+  const int n = 4 * p.T;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p.box_lo[i] = INT_MAX, p.box_hi[i] = INT_MIN;
+  if (blockIdx.x == 0 && threadIdx.x < 16) p.ctr[threadIdx.x] = 0;
 }
 
 __global__ void __launch_bounds__(1024) otf_alloc_kernel(const OtfTcParams p) {
-  __shared__ int s_scan[1024];
+  __shared__ int s_scan[32];
   const int per = (p.T + 1023) / 1024, e0 = threadIdx.x * per, e1 = min(e0 + per, p.T);
   // 1. pool segments of the boxes one MMA pass can cover; a box beyond the pool's end goes to the CUDA-core path
   int segs = 0;
@@ -802,10 +819,8 @@ extern "C" int pf_lookup_onthefly_tc(const pf_onthefly_tc_args *t, void *stream)
   p.amax[0] = reinterpret_cast<const uint32_t *>(t->amax_own), p.amax[1] = reinterpret_cast<const uint32_t *>(t->amax_other);
   p.out_own = a->out_own, p.out_raw = a->scratch, p.own_cl = t->no_rotate ? 1 : 0;
   p.tapxy = reinterpret_cast<float2 *>(t->tap_xy);
-  const size_t table = (size_t)p.T * 4 * sizeof(int);
-  if (cudaMemsetAsync(p.ctr, 0, 16 * sizeof(int), st) != cudaSuccess || cudaMemsetAsync(p.box_lo, 0x7f, table, st) != cudaSuccess ||
-      cudaMemsetAsync(p.box_hi, 0x80, table, st) != cudaSuccess)
-    return check_launch("pf_lookup_onthefly_tc(memset)");
+  otf_init_kernel<<<ceil_div(4ll * p.T, 256) < 296 ? ceil_div(4ll * p.T, 256) : 296, 256, 0, st>>>(p);
+  if (int e = check_launch("pf_lookup_onthefly_tc(init)")) return e;
   const dim3 qgrid(ceil_div(N, kBlendQueries), L * views, B);
   otf_box_kernel<<<qgrid, kBlendThreads, 0, st>>>(p);
   if (int e = check_launch("pf_lookup_onthefly_tc(box)")) return e;
